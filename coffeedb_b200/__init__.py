@@ -1,0 +1,265 @@
+"""coffeedb_b200 — B200-native string index (suffix-array build + batched substring locate) behind
+CoffeeDB's ``string_index`` surface (src/index.h:54-86 of the reference).
+
+This package is a thin ctypes binding of the C-ABI library ``libcoffeedb_b200.so`` (include/coffeedb_b200.h).
+All computation happens in hand-written sm_100a CUDA kernels inside that library; there is no CPU
+fallback — importing works anywhere (so the symbol-export test can run without a GPU) but every compute
+call raises if the library or a CUDA device is missing.
+
+``StringIndex`` mirrors the reference class: ``add(id, value)``, ``build()``, ``query(keyword)`` returning the
+list of ``(id, count)`` pairs in ascending doc index, raising ``RuntimeError`` with the reference's messages
+(src/index.cpp:196,199,240).  ``locate_batch`` is the batched form of ``query``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcoffeedb_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+# every symbol include/coffeedb_b200.h declares
+EXPORTS = [
+    "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
+    "cdb_build", "cdb_build_device", "cdb_info", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
+    "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
+    "cdb_splice", "cdb_build_stats",
+]
+
+CDB_OK = 0
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("compat_signed", C.c_int32), ("workspace_bytes", C.c_int64),
+                ("keep_host_copy", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("npat", C.c_int64), ("total_pairs", C.c_int64), ("total_occurrences", C.c_int64),
+                ("row_off", C.POINTER(C.c_int64)), ("pairs", C.POINTER(C.c_int64)), ("_owner", C.c_void_p)]
+
+
+class DeviceResult(C.Structure):
+    _fields_ = [("npat", C.c_int64), ("total_pairs", C.c_int64), ("total_occurrences", C.c_int64),
+                ("row_off", C.c_void_p), ("pairs", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
+                ("_owner", C.c_void_p)]
+
+
+class Spans(C.Structure):
+    _fields_ = [("ntext", C.c_int64), ("total_spans", C.c_int64), ("span_off", C.POINTER(C.c_int64)),
+                ("spans", C.POINTER(C.c_int64)), ("_owner", C.c_void_p)]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    args = ["make", "-C", CSRC, "-j4"] + (["-B"] if force else [])
+    r = subprocess.run(args, capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libcoffeedb_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the C-ABI library.  Fails loudly when it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(coffeedb_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+        L.cdb_last_error.restype = C.c_char_p
+        L.cdb_version.restype = C.c_char_p
+        L.cdb_device_count.restype = C.c_int
+        L.cdb_create.argtypes = [C.POINTER(Options), C.POINTER(vp)]
+        L.cdb_destroy.argtypes = [vp]
+        L.cdb_destroy.restype = None
+        L.cdb_add.argtypes = [vp, C.c_int64, vp, C.c_int64]
+        L.cdb_add_many.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.cdb_build.argtypes = [vp]
+        L.cdb_build_device.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
+        L.cdb_info.argtypes = [vp, i64p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.cdb_export_sa.argtypes = [vp, vp, C.c_int64]
+        L.cdb_sa_device_ptr.argtypes = [vp, C.POINTER(vp)]
+        L.cdb_locate_batch.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Result)]
+        L.cdb_result_free.argtypes = [C.POINTER(Result)]
+        L.cdb_result_free.restype = None
+        L.cdb_locate_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp, C.POINTER(DeviceResult)]
+        L.cdb_device_result_free.argtypes = [C.POINTER(DeviceResult)]
+        L.cdb_device_result_free.restype = None
+        L.cdb_locate_spans.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(Spans)]
+        L.cdb_spans_free.argtypes = [C.POINTER(Spans)]
+        L.cdb_spans_free.restype = None
+        L.cdb_splice.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
+        L.cdb_splice.restype = C.c_int64
+        L.cdb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != CDB_OK:
+        raise RuntimeError(lib().cdb_last_error().decode())
+
+
+def _u8(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        return np.ascontiguousarray(b, dtype=np.uint8)
+    return np.frombuffer(bytes(b), dtype=np.uint8)
+
+
+def pack(items) -> tuple[np.ndarray, np.ndarray]:
+    """list of bytes -> (bytes uint8[total], off int64[len+1])"""
+    off = np.zeros(len(items) + 1, np.int64)
+    if len(items):
+        off[1:] = np.cumsum([len(x) for x in items])
+    data = np.frombuffer(b"".join(bytes(x) for x in items), dtype=np.uint8) if off[-1] else np.zeros(0, np.uint8)
+    return data, off
+
+
+class StringIndex:
+    """Drop-in for the reference's ``string_index`` (src/index.h:54-86)."""
+
+    def __init__(self, device: int = -1, compat_signed: bool = True, workspace_bytes: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        opt = Options(device, 1 if compat_signed else 0, workspace_bytes, 0, 0)
+        _check(self._L.cdb_create(C.byref(opt), C.byref(self._h)))
+        self._keep = []  # device tensors borrowed by build_device
+
+    # -- reference surface ----------------------------------------------------------------------------
+    def add(self, id_: int, value: bytes):
+        """string_index::add (src/index.cpp:174-177)"""
+        v = _u8(value)
+        _check(self._L.cdb_add(self._h, int(id_), v.ctypes.data if len(v) else None, len(v)))
+
+    def add_many(self, ids, text, doc_off):
+        ids = np.ascontiguousarray(ids, np.int64)
+        text = _u8(text)
+        doc_off = np.ascontiguousarray(doc_off, np.int64)
+        _check(self._L.cdb_add_many(self._h, ids.ctypes.data, text.ctypes.data if len(text) else None,
+                                    doc_off.ctypes.data, len(ids)))
+
+    def build(self):
+        """string_index::build (src/index.cpp:178-236)"""
+        _check(self._L.cdb_build(self._h))
+
+    def query(self, keyword: bytes) -> list[tuple[int, int]]:
+        """string_index::query (src/index.cpp:237-326): [(id, count)] in ascending doc index."""
+        row_off, pairs = self.locate_batch([keyword])
+        return [(int(a), int(b)) for a, b in pairs]
+
+    # -- batched / device forms ------------------------------------------------------------------------
+    def locate_batch(self, patterns, pat_off=None):
+        """patterns: list of bytes, or (uint8 array, int64 offsets).  -> (row_off int64[npat+1], pairs int64[total,2])"""
+        if pat_off is None:
+            pat, pat_off = pack(list(patterns))
+        else:
+            pat, pat_off = _u8(patterns), np.ascontiguousarray(pat_off, np.int64)
+        npat = len(pat_off) - 1
+        res = Result()
+        _check(self._L.cdb_locate_batch(self._h, pat.ctypes.data if len(pat) else None, pat_off.ctypes.data, npat,
+                                        C.byref(res)))
+        try:
+            row_off = np.ctypeslib.as_array(res.row_off, shape=(npat + 1,)).copy()
+            tp = res.total_pairs
+            pairs = (np.ctypeslib.as_array(res.pairs, shape=(tp, 2)).copy() if tp else np.zeros((0, 2), np.int64))
+            self.last_total_occurrences = res.total_occurrences
+        finally:
+            self._L.cdb_result_free(C.byref(res))
+        return row_off, pairs
+
+    def locate_batch_raw(self, pat: np.ndarray, pat_off: np.ndarray) -> Result:
+        """Host-buffer call without copying the result out (caller must result_free)."""
+        res = Result()
+        _check(self._L.cdb_locate_batch(self._h, pat.ctypes.data, pat_off.ctypes.data, len(pat_off) - 1, C.byref(res)))
+        return res
+
+    def result_free(self, res):
+        self._L.cdb_result_free(C.byref(res))
+
+    def build_device(self, d_text_ptr: int, d_doc_off_ptr: int, d_ids_ptr: int, nd: int, stream: int = 0, keep=()):
+        """Build from a corpus resident in device memory (pointers are borrowed; `keep` holds their owners).
+        The text buffer must be padded with at least 64 readable bytes after the last document."""
+        self._keep = list(keep)
+        _check(self._L.cdb_build_device(self._h, d_text_ptr, d_doc_off_ptr, d_ids_ptr, nd, stream))
+
+    def locate_batch_device(self, d_pat_ptr: int, d_pat_off_ptr: int, npat: int, stream: int = 0) -> DeviceResult:
+        res = DeviceResult()
+        _check(self._L.cdb_locate_batch_device(self._h, d_pat_ptr, d_pat_off_ptr, npat, stream, C.byref(res)))
+        return res
+
+    def device_result_free(self, res: DeviceResult):
+        self._L.cdb_device_result_free(C.byref(res))
+
+    def info(self) -> dict:
+        n, nd, w, bits, mask = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_uint64()
+        _check(self._L.cdb_info(self._h, C.byref(n), C.byref(nd), C.byref(w), C.byref(bits), C.byref(mask)))
+        return {"n": n.value, "nd": nd.value, "width": w.value, "bits": bits.value, "mask": mask.value}
+
+    def build_stats(self) -> dict:
+        t, s, r, c = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+        _check(self._L.cdb_build_stats(self._h, C.byref(t), C.byref(s), C.byref(r), C.byref(c)))
+        return {"total_ms": t.value, "sort_ms": s.value, "rounds": r.value, "chunks": c.value}
+
+    def export_sa(self) -> np.ndarray:
+        """The packed suffix array widened to uint64 (element = (offset << bits) | doc, src/index.cpp:209-215)."""
+        inf = self.info()
+        buf = np.zeros(max(inf["n"], 1), np.uint32 if inf["width"] == 4 else np.uint64)
+        _check(self._L.cdb_export_sa(self._h, buf.ctypes.data, buf.nbytes))
+        return buf[: inf["n"]].astype(np.uint64)
+
+    def sa_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(self._L.cdb_sa_device_ptr(self._h, C.byref(p)))
+        return p.value or 0
+
+    def spans(self, keywords, docs) -> list[np.ndarray]:
+        """Merged highlight spans (inclusive [begin,end]) of `keywords` inside each doc index in `docs`
+        (replaces the span loop of ac_automaton::render, src/database.cpp:58-77)."""
+        kw, kw_off = pack(list(keywords))
+        docs = np.ascontiguousarray(docs, np.int64)
+        sp = Spans()
+        _check(self._L.cdb_locate_spans(self._h, kw.ctypes.data if len(kw) else None, kw_off.ctypes.data, len(kw_off) - 1,
+                                        docs.ctypes.data if len(docs) else None, len(docs), C.byref(sp)))
+        try:
+            off = np.ctypeslib.as_array(sp.span_off, shape=(len(docs) + 1,)).copy() if len(docs) else np.zeros(1, np.int64)
+            allsp = (np.ctypeslib.as_array(sp.spans, shape=(sp.total_spans, 2)).copy() if sp.total_spans
+                     else np.zeros((0, 2), np.int64))
+        finally:
+            self._L.cdb_spans_free(C.byref(sp))
+        return [allsp[off[i]:off[i + 1]] for i in range(len(docs))]
+
+    def close(self):
+        if self._h:
+            self._L.cdb_destroy(self._h)
+            self._h = C.c_void_p()
+            self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def splice(text: bytes, spans: np.ndarray, left: bytes, right: bytes) -> bytes:
+    """Marker splicing (src/database.cpp:78-90) — host-side, C-ABI cdb_splice."""
+    L = lib()
+    t, l, r = _u8(text), _u8(left), _u8(right)
+    sp = np.ascontiguousarray(spans, np.int64).reshape(-1)
+    ns = len(sp) // 2
+    need = L.cdb_splice(t.ctypes.data if len(t) else None, len(t), sp.ctypes.data if ns else None, ns,
+                        l.ctypes.data if len(l) else None, len(l), r.ctypes.data if len(r) else None, len(r), None, 0)
+    out = np.zeros(max(need, 1), np.uint8)
+    got = L.cdb_splice(t.ctypes.data if len(t) else None, len(t), sp.ctypes.data if ns else None, ns,
+                       l.ctypes.data if len(l) else None, len(l), r.ctypes.data if len(r) else None, len(r),
+                       out.ctypes.data, need)
+    return out[:got].tobytes()

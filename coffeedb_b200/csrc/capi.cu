@@ -1,0 +1,470 @@
+// C ABI (include/coffeedb_b200.h) over the device index.  Every entry point converts C++ exceptions into a
+// status code + thread-local message; the three conditions the reference throws on carry the reference's
+// exact text (src/index.cpp:196,199,240).
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+
+#include "index.cuh"
+#include "locate.cuh"
+
+namespace cdb {
+
+static thread_local std::string g_last_error;
+
+Index::~Index() { free_device(); }
+
+void Index::free_device() {
+    if (d_sa) cudaFree(d_sa);
+    if (own_text) cudaFree(own_text);
+    if (own_off) cudaFree(own_off);
+    if (own_ids) cudaFree(own_ids);
+    d_sa = own_text = own_off = own_ids = nullptr;
+    d_text = nullptr;
+    d_off = nullptr;
+    d_ids = nullptr;
+    built = false;
+}
+
+// Pinned host buffers are expensive to create (~0.3 s/GB), so freed result buffers are kept for re-use.
+class PinnedPool {
+public:
+    void* get(size_t bytes, size_t* cap_out) {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            auto it = free_.lower_bound(bytes);
+            if (it != free_.end() && it->first <= bytes * 2 + (1 << 20)) {
+                void* p = it->second;
+                *cap_out = it->first;
+                free_.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        size_t cap = bytes < 4096 ? 4096 : bytes;
+        CDB_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+        *cap_out = cap;
+        return p;
+    }
+    void put(void* p, size_t cap) {
+        std::lock_guard<std::mutex> g(mu_);
+        free_.emplace(cap, p);
+    }
+    ~PinnedPool() {
+        for (auto& kv : free_) cudaFreeHost(kv.second);
+    }
+
+private:
+    std::mutex mu_;
+    std::multimap<size_t, void*> free_;
+};
+static PinnedPool g_pinned;
+
+struct HostResultOwner {
+    void* row_off;
+    size_t row_cap;
+    void* pairs;
+    size_t pairs_cap;
+};
+
+struct DeviceSetter {
+    int prev = -1;
+    explicit DeviceSetter(int dev) {
+        cudaGetDevice(&prev);
+        if (dev >= 0 && dev != prev) CDB_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceSetter() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static void require_device() {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        throw Error(CDB_ERR_CUDA, "no CUDA device available: coffeedb_b200 has no CPU fallback");
+    }
+}
+
+static void keep_pool_memory(int dev) {
+    // keep freed temporaries in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+}
+
+}  // namespace cdb
+
+using namespace cdb;
+
+#define CDB_TRY try {
+#define CDB_CATCH                                            \
+    }                                                        \
+    catch (const cdb::Error& e) {                            \
+        g_last_error = e.what();                             \
+        return e.code;                                       \
+    }                                                        \
+    catch (const std::bad_alloc&) {                          \
+        g_last_error = "out of host memory";                 \
+        return CDB_ERR_NOMEM;                                \
+    }                                                        \
+    catch (const std::exception& e) {                        \
+        g_last_error = e.what();                             \
+        return CDB_ERR_ARG;                                  \
+    }
+
+extern "C" {
+
+const char* cdb_last_error(void) { return g_last_error.c_str(); }
+const char* cdb_version(void) { return "coffeedb_b200 0.1 (sm_100a)"; }
+
+int cdb_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return cnt;
+}
+
+cdb_status cdb_create(const cdb_options* opts, cdb_index** out) {
+    CDB_TRY
+    if (!out) throw Error(CDB_ERR_ARG, "cdb_create: out is NULL");
+    Index* ix = new Index();
+    if (opts) ix->opt = *opts;
+    else {
+        ix->opt.device = -1;
+        ix->opt.compat_signed = 1;
+        ix->opt.workspace_bytes = 0;
+        ix->opt.keep_host_copy = 0;
+    }
+    ix->device = ix->opt.device;
+    *out = reinterpret_cast<cdb_index*>(ix);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_destroy(cdb_index* h) {
+    if (!h) return;
+    Index* ix = reinterpret_cast<Index*>(h);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (ix->device >= 0 && ix->built) cudaSetDevice(ix->device);
+    delete ix;
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+cdb_status cdb_add(cdb_index* h, int64_t id, const void* value, int64_t len) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix || len < 0 || (len > 0 && !value)) throw Error(CDB_ERR_ARG, "cdb_add: bad argument");
+    ix->h_ids.push_back(id);
+    const u8* p = static_cast<const u8*>(value);
+    ix->h_text.insert(ix->h_text.end(), p, p + len);
+    ix->h_off.push_back((i64)ix->h_text.size());
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_add_many(cdb_index* h, const int64_t* ids, const void* text, const int64_t* doc_off, int64_t nd) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix || nd < 0 || (nd > 0 && (!ids || !doc_off))) throw Error(CDB_ERR_ARG, "cdb_add_many: bad argument");
+    if (nd == 0) return CDB_OK;
+    const u8* p = static_cast<const u8*>(text);
+    const i64 base = (i64)ix->h_text.size() - doc_off[0];
+    ix->h_text.insert(ix->h_text.end(), p + doc_off[0], p + doc_off[nd]);
+    ix->h_ids.insert(ix->h_ids.end(), ids, ids + nd);
+    ix->h_off.reserve(ix->h_off.size() + nd);
+    for (i64 d = 1; d <= nd; ++d) {
+        if (doc_off[d] < doc_off[d - 1]) throw Error(CDB_ERR_ARG, "cdb_add_many: doc_off must be non-decreasing");
+        ix->h_off.push_back(base + doc_off[d]);
+    }
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_build(cdb_index* h) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix) throw Error(CDB_ERR_ARG, "cdb_build: index is NULL");
+    require_device();
+    if (ix->device < 0) CDB_CUDA(cudaGetDevice(&ix->device));
+    DeviceSetter ds(ix->device);
+    keep_pool_memory(ix->device);
+    ix->free_device();
+    const i64 nd = (i64)ix->h_ids.size();
+    const i64 n = (i64)ix->h_text.size();
+    cudaStream_t st;
+    CDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    try {
+        CDB_CUDA(cudaMalloc(&ix->own_text, (size_t)(n + kTextPad)));
+        CDB_CUDA(cudaMalloc(&ix->own_off, (size_t)(nd + 1) * 8));
+        CDB_CUDA(cudaMalloc(&ix->own_ids, (size_t)(nd ? nd : 1) * 8));
+        CDB_CUDA(cudaMemsetAsync((u8*)ix->own_text + n, 0, kTextPad, st));
+        if (n) CDB_CUDA(cudaMemcpyAsync(ix->own_text, ix->h_text.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+        CDB_CUDA(cudaMemcpyAsync(ix->own_off, ix->h_off.data(), (size_t)(nd + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (nd) CDB_CUDA(cudaMemcpyAsync(ix->own_ids, ix->h_ids.data(), (size_t)nd * 8, cudaMemcpyHostToDevice, st));
+        ix->d_text = (const u8*)ix->own_text;
+        ix->d_off = (const i64*)ix->own_off;
+        ix->d_ids = (const i64*)ix->own_ids;
+        ix->nd = nd;
+        build_index(*ix, st);
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        ix->free_device();
+        throw;
+    }
+    cudaStreamDestroy(st);
+    if (!ix->opt.keep_host_copy) {
+        std::vector<u8>().swap(ix->h_text);
+    }
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_build_device(cdb_index* h, const void* d_text, const int64_t* d_doc_off, const int64_t* d_ids, int64_t nd,
+                            void* stream) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix || nd < 0 || !d_doc_off) throw Error(CDB_ERR_ARG, "cdb_build_device: bad argument");
+    require_device();
+    if (ix->device < 0) CDB_CUDA(cudaGetDevice(&ix->device));
+    DeviceSetter ds(ix->device);
+    keep_pool_memory(ix->device);
+    ix->free_device();
+    ix->d_text = (const u8*)d_text;
+    ix->d_off = d_doc_off;
+    ix->d_ids = d_ids;
+    ix->nd = nd;
+    try {
+        build_index(*ix, (cudaStream_t)stream);
+    } catch (...) {
+        cudaStreamSynchronize((cudaStream_t)stream);
+        ix->free_device();
+        throw;
+    }
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_info(const cdb_index* h, int64_t* n, int64_t* nd, int32_t* width, int32_t* bits, uint64_t* mask) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    if (n) *n = ix->n;
+    if (nd) *nd = ix->nd;
+    if (width) *width = ix->width;
+    if (bits) *bits = ix->bits1;
+    if (mask) *mask = ix->mask;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_export_sa(const cdb_index* h, void* buf, int64_t buf_bytes) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    const i64 need = ix->n * ix->width;
+    if (buf_bytes < need || (need && !buf)) throw Error(CDB_ERR_ARG, "cdb_export_sa: buffer too small");
+    DeviceSetter ds(ix->device);
+    if (need) CDB_CUDA(cudaMemcpy(buf, ix->d_sa, (size_t)need, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_sa_device_ptr(const cdb_index* h, const void** d_sa) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built || !d_sa) throw Error(CDB_ERR_STATE, "index has not been built");
+    *d_sa = ix->d_sa;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_build_stats(const cdb_index* h, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    if (total_ms) *total_ms = ix->build_ms;
+    if (sort_ms) *sort_ms = ix->sort_ms;
+    if (rounds) *rounds = ix->rounds;
+    if (chunks) *chunks = ix->chunks;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_locate_batch_device(const cdb_index* h, const void* d_pat, const int64_t* d_pat_off, int64_t npat,
+                                   void* stream, cdb_device_result* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || npat < 0) throw Error(CDB_ERR_ARG, "cdb_locate_batch_device: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npat == 0) {
+        DevBuf<i64> ro(1, st);
+        CDB_CUDA(cudaMemsetAsync(ro.p, 0, 8, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        out->row_off = ro.detach();
+        out->_owner = (void*)st;
+        return CDB_OK;
+    }
+    locate_device(*ix, (const u8*)d_pat, d_pat_off, npat, st, out);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_device_result_free(cdb_device_result* r) {
+    if (!r) return;
+    cudaStream_t st = (cudaStream_t)r->_owner;
+    if (r->row_off) cudaFreeAsync(r->row_off, st);
+    if (r->pairs) cudaFreeAsync(r->pairs, st);
+    if (r->left) cudaFreeAsync(r->left, st);
+    if (r->right) cudaFreeAsync(r->right, st);
+    std::memset(r, 0, sizeof(*r));
+}
+
+cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* pat_off, int64_t npat, cdb_result* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || npat < 0 || (npat > 0 && !pat_off)) throw Error(CDB_ERR_ARG, "cdb_locate_batch: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ix->device);
+    // the reference rejects an empty keyword before touching the index (src/index.cpp:239-241)
+    for (i64 q = 0; q < npat; ++q)
+        if (pat_off[q + 1] <= pat_off[q]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
+    cudaStream_t st;
+    CDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
+    cdb_device_result dr;
+    std::memset(&dr, 0, sizeof(dr));
+    try {
+        const i64 pbytes = npat ? pat_off[npat] - pat_off[0] : 0;
+        DevBuf<u8> d_pat((size_t)pbytes + 8, st);
+        DevBuf<i64> d_poff((size_t)npat + 1, st);
+        std::vector<i64> rel((size_t)npat + 1, 0);
+        for (i64 q = 0; q <= npat && npat; ++q) rel[q] = pat_off[q] - pat_off[0];
+        if (pbytes) CDB_CUDA(cudaMemcpyAsync(d_pat.p, (const u8*)pat + pat_off[0], (size_t)pbytes, cudaMemcpyHostToDevice, st));
+        CDB_CUDA(cudaMemcpyAsync(d_poff.p, rel.data(), (size_t)(npat + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (npat == 0) {
+            CDB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            locate_device(*ix, d_pat.p, d_poff.p, npat, st, &dr);
+        }
+        own->row_off = g_pinned.get((size_t)(npat + 1) * 8, &own->row_cap);
+        own->pairs = g_pinned.get((size_t)(dr.total_pairs ? dr.total_pairs : 1) * 16, &own->pairs_cap);
+        if (npat) {
+            CDB_CUDA(cudaMemcpyAsync(own->row_off, dr.row_off, (size_t)(npat + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (dr.total_pairs)
+                CDB_CUDA(cudaMemcpyAsync(own->pairs, dr.pairs, (size_t)dr.total_pairs * 16, cudaMemcpyDeviceToHost, st));
+        } else {
+            *(i64*)own->row_off = 0;
+        }
+        CDB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cdb_device_result_free(&dr);
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+        if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+        delete own;
+        throw;
+    }
+    out->npat = npat;
+    out->total_pairs = dr.total_pairs;
+    out->total_occurrences = dr.total_occurrences;
+    out->row_off = (const i64*)own->row_off;
+    out->pairs = (const i64*)own->pairs;
+    out->_owner = own;
+    cdb_device_result_free(&dr);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_result_free(cdb_result* r) {
+    if (!r || !r->_owner) return;
+    HostResultOwner* own = static_cast<HostResultOwner*>(r->_owner);
+    if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+    if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+    delete own;
+    std::memset(r, 0, sizeof(*r));
+}
+
+cdb_status cdb_locate_spans(const cdb_index* h, const void* kw, const int64_t* kw_off, int64_t nkw, const int64_t* docs,
+                            int64_t ndocs, cdb_spans* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || nkw < 0 || ndocs < 0) throw Error(CDB_ERR_ARG, "cdb_locate_spans: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ix->device);
+    cudaStream_t st;
+    CDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    std::vector<i64>* so = new std::vector<i64>();
+    std::vector<i64>* sp = new std::vector<i64>();
+    try {
+        locate_spans(*ix, (const u8*)kw, kw_off, nkw, docs, ndocs, st, *so, *sp);
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        delete so;
+        delete sp;
+        throw;
+    }
+    cudaStreamDestroy(st);
+    auto* pair = new std::pair<std::vector<i64>*, std::vector<i64>*>(so, sp);
+    out->ntext = ndocs;
+    out->total_spans = (i64)sp->size() / 2;
+    out->span_off = so->data();
+    out->spans = sp->data();
+    out->_owner = pair;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_spans_free(cdb_spans* s) {
+    if (!s || !s->_owner) return;
+    auto* pair = static_cast<std::pair<std::vector<i64>*, std::vector<i64>*>*>(s->_owner);
+    delete pair->first;
+    delete pair->second;
+    delete pair;
+    std::memset(s, 0, sizeof(*s));
+}
+
+// src/database.cpp:78-90
+int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t nspans, const void* left, int64_t llen,
+                   const void* right, int64_t rlen, void* out, int64_t out_cap) {
+    const int64_t need = tlen + (llen + rlen) * nspans;
+    if (!out || out_cap < need) return need;
+    const char* t = static_cast<const char*>(text);
+    char* o = static_cast<char*>(out);
+    int64_t w = 0, prev = 0;
+    for (int64_t s = 0; s < nspans; ++s) {
+        const int64_t b = spans[2 * s], e = spans[2 * s + 1];
+        std::memcpy(o + w, t + prev, (size_t)(b - prev));
+        w += b - prev;
+        std::memcpy(o + w, left, (size_t)llen);
+        w += llen;
+        std::memcpy(o + w, t + b, (size_t)(e - b + 1));
+        w += e - b + 1;
+        std::memcpy(o + w, right, (size_t)rlen);
+        w += rlen;
+        prev = e + 1;
+    }
+    std::memcpy(o + w, t + prev, (size_t)(tlen - prev));
+    w += tlen - prev;
+    return w;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// coffeedb_b200 — shared device/host helpers.  sm_100a only (B200): 148 SMs, 32 B DRAM sectors, 126 MB L2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/coffeedb_b200.h"
+
+namespace cdb {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+constexpr int kNumSMs = 148;  // B200
+
+struct Error : std::runtime_error {
+    cdb_status code;
+    Error(cdb_status c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear sticky-less errors
+        cdb_status c = (e == cudaErrorMemoryAllocation) ? CDB_ERR_NOMEM : CDB_ERR_CUDA;
+        throw Error(c, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+                           std::to_string(line) + ")");
+    }
+}
+#define CDB_CUDA(x) ::cdb::cuda_check((x), #x, __FILE__, __LINE__)
+#define CDB_LAUNCH_CHECK() ::cdb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// Stream-ordered temporary device buffer (cudaMallocAsync pool): allocation is cheap after warm-up and the
+// calls are re-entrant, which the locate path needs (several host threads query one index concurrently).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(size_t count, cudaStream_t stream) { alloc(count, stream); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; s = o.s;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    void alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        CDB_CUDA(cudaMallocAsync((void**)&p, bytes, stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    T* detach() { T* q = p; p = nullptr; n = 0; return q; }
+    ~DevBuf() { release(); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int ceil_div_i(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------- device side
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// 64-bit load that bypasses L1 allocation: for streams read exactly once (suffix-array intervals, sort passes)
+__device__ __forceinline__ u64 ld_stream_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ld_stream_u32(const u32* p) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+// relaxed gpu-scope load/store of one 64-bit word: the decoupled look-back status words
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// 8 bytes of text starting at an arbitrary byte address, returned big-endian (first byte most significant)
+// so that unsigned integer comparison == memcmp order.  Reads the two aligned 8-byte words that cover the
+// window; the text buffer is padded so that both are in bounds.
+__device__ __forceinline__ u64 load_be64(const u8* text, i64 pos) {
+    const u64* w = reinterpret_cast<const u64*>(text + (pos & ~(i64)7));
+    u64 lo = __ldg(w), hi = __ldg(w + 1);
+    u32 sh = (u32)(pos & 7) * 8;
+    u64 v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;  // little-endian: byte at pos is the low byte
+    u32 a = (u32)v, b = (u32)(v >> 32);
+    a = __byte_perm(a, 0, 0x0123);
+    b = __byte_perm(b, 0, 0x0123);
+    return ((u64)a << 32) | b;
+}
+
+}  // namespace cdb

@@ -1,0 +1,49 @@
+// The device-resident string index: the state string_index keeps in src/index.h:56-60, laid out for HBM.
+//
+//   text     u8  [n + pad]   all documents back to back (doc d = text[doc_off[d], doc_off[d+1]))
+//   doc_off  i64 [nd + 1]    document-boundary array (replaces std::vector<std::string_view> data)
+//   ids      i64 [nd]        external object id per doc index (src/index.h:59)
+//   sa       u32|u64 [n]     packed suffix array, element = (offset_in_doc << bits1) | doc_index — the
+//                            reference's own element format (src/index.cpp:209-215), so export is a memcpy
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cdb {
+
+constexpr i64 kTextPad = 64;  // bytes of zero padding after the text (16-byte window loads never fault)
+
+struct Index {
+    cdb_options opt{};
+    int device = 0;
+    // host staging filled by cdb_add (src/index.cpp:174-177)
+    std::vector<u8> h_text;
+    std::vector<i64> h_off{0};
+    std::vector<i64> h_ids;
+    // device corpus
+    const u8* d_text = nullptr;
+    const i64* d_off = nullptr;
+    const i64* d_ids = nullptr;
+    void* own_text = nullptr;
+    void* own_off = nullptr;
+    void* own_ids = nullptr;
+    i64 n = 0, nd = 0;
+    int width = 0, bits1 = 0, bits2 = 0;
+    u64 mask = 0;
+    void* d_sa = nullptr;
+    bool built = false;
+    bool mixed = false;  // text holds bytes on both sides of 0x80 (note N1 applies when n > 4096)
+    i64 chuck_size = 0;  // max(4096, n/256), src/index.cpp:218
+    // build statistics
+    double build_ms = 0, sort_ms = 0;
+    i64 rounds = 0, chunks = 0;
+
+    ~Index();
+    void free_device();
+};
+
+void build_index(Index& ix, cudaStream_t st);
+
+}  // namespace cdb

@@ -1,0 +1,551 @@
+// Batched substring locate — replaces string_index::query() (src/index.cpp:237-326; kernels K4-K7 of
+// SURVEY.md §2a) for a whole batch of patterns at once.
+//
+//   K4  search_kernel      one thread per pattern runs the reference's two binary-search recurrences verbatim
+//                          (same midpoints, same predicates), so the interval is identical even on the
+//                          not-quite-sorted arrays of note N1.  Each probe = SA element -> doc_off pair ->
+//                          16 bytes of text, compared as big-endian integers (== unsigned memcmp).
+//   K5-K7 small path       one warp per pattern with occ <= kSmallCap: coalesced read of the SA interval,
+//                          doc = element & mask, sort in shared memory, run-length, ids[] gather, 16-byte
+//                          (id, count) stores.  Run twice: count rows -> exclusive scan -> emit (exact CSR).
+//   K5-K7 large path       patterns with longer intervals are expanded into (entry << 32 | doc) keys, sorted by
+//                          the device radix sort (the same engine as the build) and run-length encoded.
+// All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
+#include <algorithm>
+
+#include "index.cuh"
+#include "locate.cuh"
+#include "primitives.cuh"
+#include "radix_sort.cuh"
+
+namespace cdb {
+
+constexpr int kSmallCap = 1024;  // occurrences handled by one warp in shared memory
+constexpr int kSmallWarps = 4;   // warps per CTA in the small path
+
+// ---- K4 ------------------------------------------------------------------------------------------------------
+struct SearchCtx {
+    const void* sa;
+    i64 n;
+    int bits1;
+    u64 mask;
+    const i64* doc_off;
+    const u8* text;
+};
+
+// three-way comparison of keyword vs the suffix stored at SA rank M:
+//   -1: keyword <  suffix            0: keyword is a prefix of suffix (keyword <= suffix, starts_with)
+//   +1: keyword >  suffix (including "suffix is a proper prefix of keyword")
+// == std::string_view::compare / substr(0,m)== of src/index.cpp:268,280 (unsigned bytes, shorter first)
+template <typename SAT>
+__device__ __forceinline__ int compare_at(const SearchCtx& c, i64 M, const u8* __restrict__ kw, i64 m, u64 p8) {
+    const u64 e = (u64) reinterpret_cast<const SAT*>(c.sa)[M];
+    const i64 doc = (i64)(e & c.mask);
+    const i64 off = (i64)(e >> c.bits1);
+    const i64 ds = __ldg(c.doc_off + doc), de = __ldg(c.doc_off + doc + 1);
+    const i64 s = ds + off;
+    const i64 slen = de - s;
+    u64 pp = p8;
+    i64 o = 0;
+    for (;;) {
+        const i64 rm = m - o, rs_ = slen - o;
+        if (rm <= 0) return 0;
+        if (rs_ <= 0) return 1;
+        i64 kk = rm < rs_ ? rm : rs_;
+        if (kk > 8) kk = 8;
+        const u64 tt = load_be64(c.text, s + o);
+        const int sh = 64 - 8 * (int)kk;
+        const u64 a = pp >> sh, b = tt >> sh;
+        if (a != b) return a < b ? -1 : 1;
+        o += kk;
+        if (o < m && kk == 8) {  // next 8 keyword bytes (rare: keywords longer than 8 that match so far)
+            pp = 0;
+            const i64 r2 = m - o < 8 ? m - o : 8;
+            for (i64 i = 0; i < r2; ++i) pp |= (u64)kw[o + i] << (56 - 8 * i);
+        }
+    }
+}
+
+template <typename SAT>
+__global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __restrict__ pat,
+                                                     const i64* __restrict__ pat_off, i64 npat,
+                                                     i64* __restrict__ left_out, i64* __restrict__ right_out,
+                                                     int* __restrict__ err) {
+    const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    const i64 ps = pat_off[q];
+    const i64 m = pat_off[q + 1] - ps;
+    if (m <= 0) {  // src/index.cpp:239-241
+        *err = 1;
+        left_out[q] = 0;
+        right_out[q] = 0;
+        return;
+    }
+    const u8* kw = pat + ps;
+    u64 p8 = 0;
+    {
+        const int m8 = m < 8 ? (int)m : 8;
+        for (int i = 0; i < m8; ++i) p8 |= (u64)kw[i] << (56 - 8 * i);
+    }
+    if (c.n == 0) {
+        left_out[q] = 0;
+        right_out[q] = 0;
+        return;
+    }
+    // src/index.cpp:262-274
+    i64 L = 0, R = c.n - 1;
+    while (L < R) {
+        const i64 M = L + (R - L) / 2;
+        if (compare_at<SAT>(c, M, kw, m, p8) <= 0)
+            R = M;
+        else
+            L = M + 1;
+    }
+    const i64 left = L;
+    // src/index.cpp:275-287
+    L = left - 1;
+    R = c.n - 1;
+    while (L < R) {
+        const i64 M = L + (R - L + 1) / 2;
+        if (compare_at<SAT>(c, M, kw, m, p8) == 0)
+            L = M;
+        else
+            R = M - 1;
+    }
+    left_out[q] = left;
+    right_out[q] = L + 1 > left ? L + 1 : left;
+}
+
+// ---- K5-K7 small path -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_bitonic_sort(u32* s, int N, int lane) {
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (N >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const u32 a = s[i], b = s[l];
+                if ((a > b) == up) {
+                    s[i] = b;
+                    s[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Loads the doc indices of SA[left, left+occ) into shared memory and sorts them.  Returns the padded size.
+template <typename SAT>
+__device__ __forceinline__ void load_and_sort_docs(const SAT* __restrict__ sa, i64 left, int occ, u64 mask, u32* s, int lane) {
+    int N = 32;
+    while (N < occ) N <<= 1;
+    for (int i = lane; i < N; i += 32) s[i] = i < occ ? (u32)((u64)sa[left + i] & mask) : 0xffffffffu;
+    __syncwarp();
+    if (occ > 1) warp_bitonic_sort(s, N, lane);
+}
+
+// EMIT=false: dcount[q] = number of distinct docs, large patterns appended to large_list.
+// EMIT=true : rows written at row_off[q].
+template <typename SAT, bool EMIT>
+__global__ void __launch_bounds__(kSmallWarps * 32) small_path_kernel(const SAT* __restrict__ sa, u64 mask,
+                                                                      const i64* __restrict__ ids,
+                                                                      const i64* __restrict__ left,
+                                                                      const i64* __restrict__ right, i64 npat,
+                                                                      u64* __restrict__ dcount, u32* __restrict__ large_list,
+                                                                      unsigned long long* __restrict__ counters,
+                                                                      const u64* __restrict__ row_off,
+                                                                      i64* __restrict__ pairs) {
+    extern __shared__ u32 smem_u32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32* s = smem_u32 + (size_t)warp * (2 * kSmallCap);
+    u32* hp = s + kSmallCap;
+    const i64 q = (i64)blockIdx.x * kSmallWarps + warp;
+    if (q >= npat) return;
+    const i64 l = left[q];
+    const i64 occ64 = right[q] - l;
+    if (occ64 > kSmallCap) {
+        if (!EMIT && lane == 0) {
+            unsigned long long slot = atomicAdd(counters + 0, 1ull);
+            large_list[slot] = (u32)q;
+            dcount[q] = 0;
+        }
+        return;
+    }
+    const int occ = (int)occ64;
+    if (occ == 0) {
+        if (!EMIT && lane == 0) dcount[q] = 0;
+        return;
+    }
+    load_and_sort_docs<SAT>(sa, l, occ, mask, s, lane);
+    // run heads
+    int nheads = 0;
+    for (int base = 0; base < occ; base += 32) {
+        const int t = base + lane;
+        const bool head = t < occ && (t == 0 || s[t] != s[t - 1]);
+        const u32 bal = __ballot_sync(0xffffffffu, head);
+        if (EMIT && head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u32)t;
+        nheads += __popc(bal);
+    }
+    if (!EMIT) {
+        if (lane == 0) {
+            dcount[q] = (u64)nheads;
+            atomicAdd(counters + 1, (unsigned long long)occ);
+        }
+        return;
+    }
+    __syncwarp();
+    const u64 row = row_off[q];
+    for (int r = lane; r < nheads; r += 32) {
+        const int start = (int)hp[r];
+        const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
+        const i64 id = __ldg(ids + s[start]);
+        longlong2 v;
+        v.x = id;
+        v.y = (i64)(end - start);
+        *reinterpret_cast<longlong2*>(pairs + 2 * (row + r)) = v;
+    }
+}
+
+// ---- K5-K7 large path -------------------------------------------------------------------------------------------
+__global__ void large_occ_kernel(const u32* __restrict__ list, u64 nl, const i64* __restrict__ left,
+                                 const i64* __restrict__ right, u64* __restrict__ occ) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nl) occ[j] = (u64)(right[list[j]] - left[list[j]]);
+}
+
+template <typename SAT>
+__global__ void large_expand_kernel(const SAT* __restrict__ sa, u64 mask, const u32* __restrict__ list, u64 nl,
+                                    const i64* __restrict__ left, const u64* __restrict__ ooff, u64 total,
+                                    u64* __restrict__ keys) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        u64 lo = 0, hi = nl - 1;  // largest j with ooff[j] <= e
+        while (lo < hi) {
+            u64 mid = lo + (hi - lo + 1) / 2;
+            if (__ldg(ooff + mid) <= e)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const u64 i = (u64)left[list[lo]] + (e - __ldg(ooff + lo));
+        keys[e] = (lo << 32) | ((u64)sa[i] & mask);
+    }
+}
+
+__global__ void large_flag_kernel(const u64* __restrict__ keys, u64 total, u8* __restrict__ flags) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x)
+        flags[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1 : 0;
+}
+
+__global__ void large_unique_kernel(const u64* __restrict__ keys, const u8* __restrict__ flags,
+                                    const u64* __restrict__ pos, u64 total, u64* __restrict__ ukey,
+                                    u64* __restrict__ ustart, u64* __restrict__ entry_first) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        if (!flags[e]) continue;
+        const u64 u = pos[e], k = keys[e];
+        ukey[u] = k;
+        ustart[u] = e;
+        if (e == 0 || (keys[e - 1] >> 32) != (k >> 32)) entry_first[k >> 32] = u;
+    }
+}
+
+__global__ void large_dcount_kernel(const u32* __restrict__ list, u64 nl, const u64* __restrict__ entry_first,
+                                    u64* __restrict__ dcount) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nl) dcount[list[j]] = entry_first[j + 1] - entry_first[j];
+}
+
+__global__ void large_emit_kernel(const u64* __restrict__ ukey, const u64* __restrict__ ustart, u64 nu, u64 total,
+                                  const u32* __restrict__ list, const u64* __restrict__ entry_first,
+                                  const u64* __restrict__ row_off, const i64* __restrict__ ids, i64* __restrict__ pairs) {
+    for (u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += (u64)gridDim.x * blockDim.x) {
+        const u64 k = ukey[u];
+        const u64 j = k >> 32;
+        const u64 cnt = (u + 1 < nu ? ustart[u + 1] : total) - ustart[u];
+        const u64 dst = row_off[list[j]] + (u - entry_first[j]);
+        longlong2 v;
+        v.x = __ldg(ids + (k & 0xffffffffull));
+        v.y = (i64)cnt;
+        *reinterpret_cast<longlong2*>(pairs + 2 * dst) = v;
+    }
+}
+
+static int bits_for_u64(u64 v) {
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
+    return b;
+}
+
+// ---- host driver ------------------------------------------------------------------------------------------------
+template <typename SAT>
+static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
+                         cdb_device_result* out) {
+    const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
+    DevBuf<i64> left(npat, st), right(npat, st);
+    DevBuf<u64> dcount(npat + 1, st);      // becomes row_off after the in-place scan
+    DevBuf<unsigned long long> counters(4, st);  // [0] large patterns, [1] occurrences (small path), [2] err
+    DevBuf<u32> large_list(npat, st);
+    CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+    SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
+    int* err = reinterpret_cast<int*>(counters.p + 2);
+    search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, d_pat, d_pat_off, npat, left.p, right.p, err);
+    CDB_LAUNCH_CHECK();
+    const size_t small_smem = (size_t)kSmallWarps * 2 * kSmallCap * sizeof(u32);
+    static_assert(kSmallWarps * 2 * kSmallCap * sizeof(u32) <= 48 * 1024, "small path uses static-limit shared memory");
+    const unsigned small_grid = (unsigned)ceil_div(npat, kSmallWarps);
+    small_path_kernel<SAT, false><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
+        sa, ix.mask, ix.d_ids, left.p, right.p, npat, dcount.p, large_list.p, counters.p, nullptr, nullptr);
+    CDB_LAUNCH_CHECK();
+    unsigned long long hc[4];
+    CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    if ((int)(hc[2] & 0xffffffffu)) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
+    const u64 nl = hc[0];
+    u64 total_occ = hc[1];
+    // large path, phase 1
+    DevBuf<u64> ooff, lkeys, ukey, ustart, entry_first;
+    u64 ltotal = 0, nu = 0;
+    if (nl > 0) {
+        ooff.alloc(nl + 1, st);
+        large_occ_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, left.p, right.p, ooff.p);
+        CDB_LAUNCH_CHECK();
+        prim::exclusive_scan<u64>(ooff.p, ooff.p, nl, st);
+        CDB_CUDA(cudaMemcpyAsync(&ltotal, ooff.p + nl, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        total_occ += ltotal;
+        DevBuf<u64> k0(ltotal, st), k1(ltotal, st);
+        const int grid = (int)std::min<i64>(ceil_div((i64)ltotal, 256), kNumSMs * 16);
+        large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p, nl, left.p, ooff.p, ltotal, k0.p);
+        CDB_LAUNCH_CHECK();
+        int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, ltotal, 0, 32 + bits_for_u64(nl - 1), st);
+        u64* sorted = cbuf ? k1.p : k0.p;
+        u64* scratch = cbuf ? k0.p : k1.p;  // re-used for the positions of the unique keys
+        DevBuf<u8> flags(ltotal, st);
+        large_flag_kernel<<<grid, 256, 0, st>>>(sorted, ltotal, flags.p);
+        CDB_LAUNCH_CHECK();
+        DevBuf<u64> pos(ltotal + 1, st);
+        prim::exclusive_scan<u8>(flags.p, pos.p, ltotal, st);
+        CDB_CUDA(cudaMemcpyAsync(&nu, pos.p + ltotal, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        (void)scratch;
+        ukey.alloc(nu, st);
+        ustart.alloc(nu, st);
+        entry_first.alloc(nl + 1, st);
+        large_unique_kernel<<<grid, 256, 0, st>>>(sorted, flags.p, pos.p, ltotal, ukey.p, ustart.p, entry_first.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaMemcpyAsync(entry_first.p + nl, pos.p + ltotal, 8, cudaMemcpyDeviceToDevice, st));
+        large_dcount_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, entry_first.p, dcount.p);
+        CDB_LAUNCH_CHECK();
+    }
+    // exact CSR offsets
+    prim::exclusive_scan<u64>(dcount.p, dcount.p, (u64)npat, st);
+    u64 total_pairs = 0;
+    CDB_CUDA(cudaMemcpyAsync(&total_pairs, dcount.p + npat, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    DevBuf<i64> pairs((size_t)total_pairs * 2, st);
+    small_path_kernel<SAT, true><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
+        sa, ix.mask, ix.d_ids, left.p, right.p, npat, nullptr, nullptr, nullptr, dcount.p, pairs.p);
+    CDB_LAUNCH_CHECK();
+    if (nl > 0 && nu > 0) {
+        const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
+        large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, dcount.p,
+                                                ix.d_ids, pairs.p);
+        CDB_LAUNCH_CHECK();
+    }
+    CDB_CUDA(cudaStreamSynchronize(st));
+    out->npat = npat;
+    out->total_pairs = (i64)total_pairs;
+    out->total_occurrences = (i64)total_occ;
+    out->row_off = reinterpret_cast<i64*>(dcount.detach());
+    out->pairs = pairs.detach();
+    out->left = left.detach();
+    out->right = right.detach();
+    out->_owner = (void*)st;
+}
+
+// ---- K8 highlight spans ----------------------------------------------------------------------------------------
+// Replaces the occurrence enumeration of ac_automaton::render (src/database.cpp:58-77): every occurrence of every
+// keyword is an SA element inside that keyword's interval; the ones that fall in a requested document become
+// (doc, begin) -> end records, are sorted by the device radix sort and merged per document (overlapping
+// intervals merge, touching ones do not — database.cpp:66-76).
+__global__ void span_occ_kernel(const i64* __restrict__ left, const i64* __restrict__ right, u64 nkw, u64* __restrict__ occ) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nkw) occ[j] = (u64)(right[j] - left[j]);
+}
+
+template <typename SAT>
+__global__ void span_expand_kernel(const SAT* __restrict__ sa, u64 mask, int bits1, int bits2,
+                                   const i64* __restrict__ left, const u64* __restrict__ ooff, u64 nkw, u64 total,
+                                   const i64* __restrict__ kw_off, const i64* __restrict__ udocs, u64 nu,
+                                   u64* __restrict__ keys, u64* __restrict__ ends, unsigned long long* __restrict__ cursor) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        u64 lo = 0, hi = nkw - 1;
+        while (lo < hi) {
+            u64 mid = lo + (hi - lo + 1) / 2;
+            if (__ldg(ooff + mid) <= e)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const u64 x = (u64)sa[(u64)left[lo] + (e - __ldg(ooff + lo))];
+        const i64 doc = (i64)(x & mask);
+        const u64 off = x >> bits1;
+        // membership in the sorted list of requested documents
+        u64 a = 0, b = nu;
+        while (a < b) {
+            u64 mid = (a + b) >> 1;
+            if (__ldg(udocs + mid) < doc)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        if (a < nu && __ldg(udocs + a) == doc) {
+            const u64 slot = atomicAdd(cursor, 1ull);
+            keys[slot] = (a << bits2) | off;
+            ends[slot] = off + (u64)(kw_off[lo + 1] - kw_off[lo]) - 1;
+        }
+    }
+}
+
+// one thread per requested document: merge its records (sorted by begin).  WRITE=false counts spans.
+template <bool WRITE>
+__global__ void span_merge_kernel(const u64* __restrict__ keys, const u64* __restrict__ ends, u64 nrec, int bits2, u64 nu,
+                                  u64* __restrict__ cnt, const u64* __restrict__ soff, i64* __restrict__ spans) {
+    const u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    const u64 klo = u << bits2;
+    u64 a = 0, b = nrec;
+    while (a < b) {
+        u64 mid = (a + b) >> 1;
+        if (keys[mid] < klo)
+            a = mid + 1;
+        else
+            b = mid;
+    }
+    const u64 offmask = bits2 >= 64 ? ~0ull : ((1ull << bits2) - 1);
+    u64 n = 0;
+    u64 out = WRITE ? soff[u] : 0;
+    bool open = false;
+    u64 cb = 0, ce = 0;
+    for (u64 r = a; r < nrec && (keys[r] >> bits2) == u; ++r) {
+        const u64 bg = keys[r] & offmask, en = ends[r];
+        if (open && bg <= ce) {
+            ce = en > ce ? en : ce;
+        } else {
+            if (open) {
+                if (WRITE) {
+                    spans[2 * out] = (i64)cb;
+                    spans[2 * out + 1] = (i64)ce;
+                    ++out;
+                }
+                ++n;
+            }
+            open = true;
+            cb = bg;
+            ce = en;
+        }
+    }
+    if (open) {
+        if (WRITE) {
+            spans[2 * out] = (i64)cb;
+            spans[2 * out + 1] = (i64)ce;
+        }
+        ++n;
+    }
+    if (!WRITE) cnt[u] = n;
+}
+
+template <typename SAT>
+static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const std::vector<i64>& udocs,
+                        cudaStream_t st, std::vector<u64>& uoff, std::vector<i64>& uspans) {
+    const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
+    const u64 nu = udocs.size();
+    const i64 kbytes = kw_off[nkw] - kw_off[0];
+    DevBuf<u8> d_kw((size_t)kbytes + 8, st);
+    DevBuf<i64> d_koff((size_t)nkw + 1, st), d_udocs(nu, st);
+    std::vector<i64> rel((size_t)nkw + 1);
+    for (i64 k = 0; k <= nkw; ++k) rel[k] = kw_off[k] - kw_off[0];
+    CDB_CUDA(cudaMemcpyAsync(d_kw.p, kw + kw_off[0], (size_t)kbytes, cudaMemcpyHostToDevice, st));
+    CDB_CUDA(cudaMemcpyAsync(d_koff.p, rel.data(), (size_t)(nkw + 1) * 8, cudaMemcpyHostToDevice, st));
+    CDB_CUDA(cudaMemcpyAsync(d_udocs.p, udocs.data(), (size_t)nu * 8, cudaMemcpyHostToDevice, st));
+    DevBuf<i64> left(nkw, st), right(nkw, st);
+    DevBuf<unsigned long long> counters(2, st);
+    CDB_CUDA(cudaMemsetAsync(counters.p, 0, 16, st));
+    SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
+    search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, d_kw.p, d_koff.p, nkw, left.p, right.p,
+                                                                      reinterpret_cast<int*>(counters.p + 1));
+    CDB_LAUNCH_CHECK();
+    DevBuf<u64> ooff((size_t)nkw + 1, st);
+    span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
+    CDB_LAUNCH_CHECK();
+    prim::exclusive_scan<u64>(ooff.p, ooff.p, (u64)nkw, st);
+    u64 total = 0;
+    CDB_CUDA(cudaMemcpyAsync(&total, ooff.p + nkw, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    uoff.assign(nu + 1, 0);
+    uspans.clear();
+    if (total == 0) return;
+    DevBuf<u64> k0(total, st), k1(total, st), e0(total, st), e1(total, st);
+    const int grid = (int)std::min<i64>(ceil_div((i64)total, 256), kNumSMs * 16);
+    span_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, ix.bits1, ix.bits2, left.p, ooff.p, (u64)nkw, total, d_koff.p,
+                                                   d_udocs.p, nu, k0.p, e0.p, counters.p);
+    CDB_LAUNCH_CHECK();
+    unsigned long long nrec = 0;
+    CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    if (nrec == 0) return;
+    int cb = rs::radix_sort_pairs<u64>(k0.p, k1.p, e0.p, e1.p, nrec, 0, ix.bits2 + bits_for_u64(nu - 1), st);
+    const u64* ks = cb ? k1.p : k0.p;
+    const u64* es = cb ? e1.p : e0.p;
+    DevBuf<u64> cnt(nu + 1, st);
+    span_merge_kernel<false><<<(unsigned)ceil_div((i64)nu, 128), 128, 0, st>>>(ks, es, nrec, ix.bits2, nu, cnt.p, nullptr, nullptr);
+    CDB_LAUNCH_CHECK();
+    prim::exclusive_scan<u64>(cnt.p, cnt.p, nu, st);
+    CDB_CUDA(cudaMemcpyAsync(uoff.data(), cnt.p, (nu + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    const u64 ns = uoff[nu];
+    if (ns == 0) return;
+    DevBuf<i64> d_spans(ns * 2, st);
+    span_merge_kernel<true><<<(unsigned)ceil_div((i64)nu, 128), 128, 0, st>>>(ks, es, nrec, ix.bits2, nu, nullptr, cnt.p, d_spans.p);
+    CDB_LAUNCH_CHECK();
+    uspans.resize(ns * 2);
+    CDB_CUDA(cudaMemcpyAsync(uspans.data(), d_spans.p, ns * 16, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+}
+
+void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const i64* docs, i64 ndocs, cudaStream_t st,
+                  std::vector<i64>& span_off, std::vector<i64>& spans) {
+    span_off.assign((size_t)ndocs + 1, 0);
+    spans.clear();
+    for (i64 k = 0; k < nkw; ++k)
+        if (kw_off[k + 1] <= kw_off[k]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
+    for (i64 t = 0; t < ndocs; ++t)
+        if (docs[t] < 0 || docs[t] >= ix.nd) throw Error(CDB_ERR_ARG, "cdb_locate_spans: document index out of range");
+    if (nkw == 0 || ndocs == 0 || ix.n == 0) return;
+    std::vector<i64> udocs(docs, docs + ndocs);
+    std::sort(udocs.begin(), udocs.end());
+    udocs.erase(std::unique(udocs.begin(), udocs.end()), udocs.end());
+    std::vector<u64> uoff;
+    std::vector<i64> uspans;
+    if (ix.width == 4)
+        spans_typed<u32>(ix, kw, kw_off, nkw, udocs, st, uoff, uspans);
+    else
+        spans_typed<u64>(ix, kw, kw_off, nkw, udocs, st, uoff, uspans);
+    // back to the caller's document order (duplicates allowed)
+    for (i64 t = 0; t < ndocs; ++t) {
+        const size_t u = std::lower_bound(udocs.begin(), udocs.end(), docs[t]) - udocs.begin();
+        const u64 a = uoff[u], b = uoff[u + 1];
+        spans.insert(spans.end(), uspans.begin() + 2 * a, uspans.begin() + 2 * b);
+        span_off[t + 1] = (i64)spans.size() / 2;
+    }
+}
+
+void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
+                   cdb_device_result* out) {
+    if (ix.width == 4)
+        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out);
+    else
+        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out);
+}
+
+}  // namespace cdb

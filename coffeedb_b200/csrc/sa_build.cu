@@ -1,0 +1,603 @@
+// Suffix-array construction on the device — replaces string_index::build() + parallel_sort<T>()
+// (src/index.cpp:178-236, 75-128; kernels K1-K3 of SURVEY.md §2a).
+//
+// Algorithm (B200-first, not the reference's work-queue MSD radix):
+//   round 0   every suffix gets a 64-bit key holding its first S symbols; the alphabet is re-coded to
+//             b = ceil(log2(sigma+1)) bits with 0 = end-of-document, so S = 64/b (12 symbols for a-z).  The
+//             reference's 257-symbol order "end-of-document < every byte" (src/index.h:66-73) is exactly
+//             integer order of these keys.  (key, packed) pairs are sorted by the onesweep radix sort.
+//   round r   only suffixes still tied with a neighbour stay on a worklist.  A tied group whose members have
+//             ended (their remaining length < compared depth) consists of byte-identical suffixes: their
+//             final order is ascending packed value (the canonical order of note N2).  Every other tied
+//             suffix gets the next S symbols as its key.  The worklist is sorted by key, then stably by
+//             group number, and written back in place; new ties form the next worklist.
+//   chunks    when 2*(8+w) bytes per suffix do not fit the workspace, suffixes are partitioned by the top
+//             12 bits of their round-0 key and the partitions are sorted one after another straight into
+//             their final suffix-array range (a 10 GB corpus needs ~8 chunks on one 180 GB B200).
+// The payload carried through every sort is the reference's own packed element (offset << bits1) | doc, so the
+// finished array is byte-for-byte what src/index.cpp:209-215 + the sort would hold (up to note N2 ties).
+#include <algorithm>
+#include <cstring>
+
+#include "index.cuh"
+#include "primitives.cuh"
+#include "radix_sort.cuh"
+
+namespace cdb {
+
+struct SymTab {
+    u16 sym[256];  // 0 is reserved for end-of-document; present bytes map to 1..sigma in unsigned order
+};
+
+// ---- corpus statistics ----------------------------------------------------------------------------------
+__global__ void doc_stats_kernel(const i64* __restrict__ doc_off, i64 nd, unsigned long long* maxlen) {
+    u64 m = 0;
+    for (i64 d = (i64)blockIdx.x * blockDim.x + threadIdx.x; d < nd; d += (i64)gridDim.x * blockDim.x) {
+        u64 len = (u64)(doc_off[d + 1] - doc_off[d]);
+        m = len > m ? len : m;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        u64 t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(maxlen, (unsigned long long)m);
+}
+
+__global__ void byte_presence_kernel(const u8* __restrict__ text, i64 n, u32* __restrict__ present) {
+    __shared__ u32 sp[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sp[i] = 0;
+    __syncthreads();
+    const i64 nvec = n >> 4;
+    const uint4* t4 = reinterpret_cast<const uint4*>(text);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (i64)gridDim.x * blockDim.x) {
+        uint4 v = ld_stream_v4(t4 + i);
+        u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sp[w[k] & 255] = 1;  // benign race: every writer stores 1
+            sp[(w[k] >> 8) & 255] = 1;
+            sp[(w[k] >> 16) & 255] = 1;
+            sp[w[k] >> 24] = 1;
+        }
+    }
+    if (blockIdx.x == 0)
+        for (i64 i = (nvec << 4) + threadIdx.x; i < n; i += blockDim.x) sp[text[i]] = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sp[i]) present[i] = 1;
+}
+
+// largest d in [lo, hi] with doc_off[d] <= g   (doc_off[lo] <= g is guaranteed by the caller)
+__device__ __forceinline__ i64 doc_of(const i64* __restrict__ doc_off, i64 lo, i64 hi, i64 g) {
+    while (lo < hi) {
+        i64 mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(doc_off + mid) <= g)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- K1 + key extraction --------------------------------------------------------------------------------
+// One CTA handles 1024 consecutive text positions: the bytes (plus S-1 lookahead) are re-coded into shared
+// memory once, each thread then assembles the keys of 4 positions.  MODE 0: histogram of the top `cb` key bits
+// (chunk planning).  MODE 1: all positions, output index = position.  MODE 2: positions whose bucket lies in
+// [blo, bhi), appended through a CTA-aggregated atomic cursor.
+constexpr int EX_THREADS = 256;
+constexpr int EX_IPT = 4;
+constexpr int EX_TILE = EX_THREADS * EX_IPT;
+constexpr int EX_MAXS = 32;
+
+template <typename P, int MODE>
+__global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restrict__ text, const i64* __restrict__ doc_off,
+                                                             i64 nd, i64 n, SymTab tab, int b, int S, int bits1,
+                                                             int cbshift, u32 blo, u32 bhi, u64* __restrict__ keys,
+                                                             P* __restrict__ vals, unsigned long long* cursor,
+                                                             unsigned long long* bucket_hist) {
+    __shared__ u16 s_tab[256];
+    __shared__ u16 s_sym[EX_TILE + EX_MAXS];
+    __shared__ i64 s_dlo, s_dhi;
+    __shared__ u64 s_ws[32];
+    __shared__ u64 s_base;
+    const int tid = threadIdx.x;
+    s_tab[tid] = tab.sym[tid];
+    const i64 t0 = (i64)blockIdx.x * EX_TILE;
+    if (tid == 0) s_dlo = doc_of(doc_off, 0, nd - 1, t0);
+    if (tid == 32) {
+        i64 last = t0 + EX_TILE - 1;
+        s_dhi = doc_of(doc_off, 0, nd - 1, last < n - 1 ? last : n - 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < EX_TILE + S; i += EX_THREADS) {
+        i64 g = t0 + i;
+        s_sym[i] = g < n ? s_tab[text[g]] : 0;
+    }
+    __syncthreads();
+    const i64 dlo = s_dlo, dhi = s_dhi;
+    u64 key[EX_IPT];
+    P val[EX_IPT];
+    bool sel[EX_IPT];
+    u32 nsel = 0;
+#pragma unroll
+    for (int r = 0; r < EX_IPT; ++r) {
+        const int li = r * EX_THREADS + tid;
+        const i64 g = t0 + li;
+        sel[r] = false;
+        key[r] = 0;
+        val[r] = 0;
+        if (g < n) {
+            i64 d = doc_of(doc_off, dlo, dhi, g);
+            i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
+            i64 rem = de - g;
+            int lim = rem < (i64)S ? (int)rem : S;
+            u64 k = 0;
+            for (int j = 0; j < S; ++j) k = (k << b) | (u64)(j < lim ? s_sym[li + j] : 0);
+            key[r] = k;
+            val[r] = (P)(((u64)(g - ds) << bits1) | (u64)d);
+            if (MODE == 1) {
+                sel[r] = true;
+            } else {
+                u32 bucket = (u32)(k >> cbshift);
+                if (MODE == 0)
+                    atomicAdd(bucket_hist + bucket, 1ull);
+                else
+                    sel[r] = bucket >= blo && bucket < bhi;
+            }
+            nsel += sel[r] ? 1 : 0;
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int r = 0; r < EX_IPT; ++r) {
+            const i64 g = t0 + r * EX_THREADS + tid;
+            if (sel[r]) {
+                keys[g] = key[r];
+                vals[g] = val[r];
+            }
+        }
+    } else if (MODE == 2) {
+        u64 tot;
+        u64 ex = prim::block_exclusive_scan_u64(nsel, &tot, s_ws);
+        if (tid == 0) s_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0;
+        __syncthreads();
+        u64 o = s_base + ex;
+#pragma unroll
+        for (int r = 0; r < EX_IPT; ++r) {
+            if (sel[r]) {
+                keys[o] = key[r];
+                vals[o] = val[r];
+                ++o;
+            }
+        }
+    }
+}
+
+// ---- tie detection + ordered compaction --------------------------------------------------------------------
+constexpr int TC_THREADS = 256;
+constexpr int TC_IPT = 8;
+constexpr int TC_TILE = TC_THREADS * TC_IPT;
+
+template <bool HasGid>
+__device__ __forceinline__ bool same_group(const u64* __restrict__ keys, const u32* __restrict__ gid, u64 i, u64 j) {
+    if (keys[i] != keys[j]) return false;
+    if (HasGid) return gid[i] == gid[j];
+    return true;
+}
+
+// packed count: low 32 bits = tied elements, high 32 bits = group heads among them
+template <bool HasGid>
+__device__ __forceinline__ void tie_flags(const u64* __restrict__ keys, const u32* __restrict__ gid, u64 m, u64 base,
+                                          bool tied[TC_IPT], bool head[TC_IPT]) {
+    bool eq_prev = base > 0 && base < m && same_group<HasGid>(keys, gid, base, base - 1);
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) {
+        u64 i = base + r;
+        bool eq_next = (i + 1 < m) && same_group<HasGid>(keys, gid, i + 1, i);
+        bool valid = i < m;
+        tied[r] = valid && (eq_prev || eq_next);
+        head[r] = tied[r] && !eq_prev;
+        eq_prev = eq_next;
+    }
+}
+
+template <bool HasGid>
+__global__ void __launch_bounds__(TC_THREADS) ties_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ gid,
+                                                                u64 m, u64* __restrict__ bsum) {
+    __shared__ u64 ws[32];
+    bool tied[TC_IPT], head[TC_IPT];
+    tie_flags<HasGid>(keys, gid, m, (u64)blockIdx.x * TC_TILE + (u64)threadIdx.x * TC_IPT, tied, head);
+    u64 s = 0;
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) s += (u64)tied[r] + ((u64)head[r] << 32);
+    u64 tot;
+    prim::block_exclusive_scan_u64(s, &tot, ws);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+template <bool HasGid, typename P>
+__global__ void __launch_bounds__(TC_THREADS) ties_write_kernel(const u64* __restrict__ keys, const u32* __restrict__ gid,
+                                                                const u32* __restrict__ widx_in, const P* __restrict__ pay_in,
+                                                                u64 m, const u64* __restrict__ bsum,
+                                                                u32* __restrict__ widx_out, P* __restrict__ pay_out,
+                                                                u32* __restrict__ gid_out) {
+    __shared__ u64 ws[32];
+    bool tied[TC_IPT], head[TC_IPT];
+    const u64 base = (u64)blockIdx.x * TC_TILE + (u64)threadIdx.x * TC_IPT;
+    tie_flags<HasGid>(keys, gid, m, base, tied, head);
+    u64 s = 0;
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) s += (u64)tied[r] + ((u64)head[r] << 32);
+    u64 tot;
+    u64 ex = prim::block_exclusive_scan_u64(s, &tot, ws) + bsum[blockIdx.x];
+    u32 pos = (u32)ex, heads = (u32)(ex >> 32);
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) {
+        if (tied[r]) {
+            heads += head[r] ? 1 : 0;
+            u64 i = base + r;
+            widx_out[pos] = HasGid ? widx_in[i] : (u32)i;
+            pay_out[pos] = pay_in[i];
+            gid_out[pos] = heads - 1;
+            ++pos;
+        }
+    }
+}
+
+// ---- refinement keys ---------------------------------------------------------------------------------------
+// depth = number of symbols already known equal inside the element's group.
+template <typename P>
+__global__ void nextkey_kernel(const P* __restrict__ pay, u64 m, const u8* __restrict__ text,
+                               const i64* __restrict__ doc_off, SymTab tab, int b, int S, int bits1, u64 mask,
+                               i64 depth, u64* __restrict__ keys, u32* __restrict__ iota) {
+    __shared__ u16 s_tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = tab.sym[i];
+    __syncthreads();
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    u64 p = (u64)pay[j];
+    i64 d = (i64)(p & mask);
+    i64 off = (i64)(p >> bits1);
+    i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
+    i64 rem = de - ds - off;
+    u64 k;
+    if (rem < depth) {
+        k = p;  // byte-identical group: final order is ascending packed value (note N2)
+    } else {
+        i64 g = ds + off + depth;
+        i64 left = rem - depth;
+        int lim = left < (i64)S ? (int)left : S;
+        k = 0;
+        for (int q = 0; q < S; ++q) k = (k << b) | (u64)(q < lim ? s_tab[__ldg(text + g + q)] : 0);
+    }
+    keys[j] = k;
+    iota[j] = (u32)j;
+}
+
+__global__ void gather_gid_kernel(const u32* __restrict__ gid, const u32* __restrict__ perm, u64 m,
+                                  u64* __restrict__ gkeys, u32* __restrict__ iota) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    gkeys[j] = gid[perm[j]];
+    iota[j] = (u32)j;
+}
+
+// perm2[j] = position in key order (ks/ps) of the element that belongs at worklist slot j
+template <typename P>
+__global__ void apply_perm_kernel(const u32* __restrict__ perm2, const u64* __restrict__ ks, const u32* __restrict__ ps,
+                                  const P* __restrict__ pay, const u32* __restrict__ widx, u64 m,
+                                  u64* __restrict__ key2, P* __restrict__ pay2, P* __restrict__ chunk_vals) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    u32 q = perm2[j];
+    P v = pay[ps[q]];
+    key2[j] = ks[q];
+    pay2[j] = v;
+    chunk_vals[widx[j]] = v;
+}
+
+template <typename P>
+__global__ void copy_kernel(const P* __restrict__ src, P* __restrict__ dst, u64 m) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ---- host driver ------------------------------------------------------------------------------------------------
+static int bits_for(u64 v) {  // number of bits needed to represent values 0..v
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
+    return b;
+}
+
+// the reference's width rule (src/index.cpp:183-194): all-ones masks grown until they cover nd / maxlen
+static int ones_needed(u64 v) {
+    u64 m = 1;
+    int b = 1;
+    while (m < v) {
+        m = (m << 1) + 1;
+        ++b;
+        if (b == 64) break;
+    }
+    return b;
+}
+
+struct BuildTimers {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sort_events;
+    void begin(cudaStream_t st) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        sort_events.push_back({a, b});
+    }
+    void end(cudaStream_t st) { cudaEventRecord(sort_events.back().second, st); }
+    double total_ms() {
+        double t = 0;
+        for (auto& e : sort_events) {
+            float ms = 0;
+            cudaEventSynchronize(e.second);
+            cudaEventElapsedTime(&ms, e.first, e.second);
+            t += ms;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        sort_events.clear();
+        return t;
+    }
+};
+
+template <typename P>
+struct ChunkSorter {
+    Index& ix;
+    const SymTab& tab;
+    int b, S;
+    cudaStream_t st;
+    BuildTimers& timers;
+
+    // Sorts the m (key, packed) pairs in (k[0], v[0]) completely; returns the index of the buffer whose
+    // values hold the finished suffix-array slice.
+    int run(u64* k[2], P* v[2], u64 m) {
+        const int keybits = b * S;
+        timers.begin(st);
+        int c = rs::radix_sort_pairs<P>(k[0], k[1], v[0], v[1], m, 0, keybits, st);
+        timers.end(st);
+        u64* keys = k[c];
+        P* vals = v[c];
+        // round-0 ties -> worklist
+        DevBuf<u32> widx, gid;
+        DevBuf<P> pay;
+        u64 wm = 0, ngroups = 0;
+        compact<false>(keys, nullptr, nullptr, vals, m, widx, pay, gid, wm, ngroups);
+        i64 depth = S;
+        const int tiebits = ix.bits1 + ix.bits2;
+        const int sortbits = keybits > tiebits ? keybits : tiebits;
+        while (wm > 0) {
+            ix.rounds++;
+            const unsigned gb = (unsigned)ceil_div((i64)wm, 256);
+            DevBuf<u64> nk(wm, st), nk2(wm, st);
+            DevBuf<u32> p0(wm, st), p1(wm, st);
+            nextkey_kernel<P><<<gb, 256, 0, st>>>(pay.p, wm, ix.d_text, ix.d_off, tab, b, S, ix.bits1, ix.mask, depth,
+                                                  nk.p, p0.p);
+            CDB_LAUNCH_CHECK();
+            timers.begin(st);
+            int c1 = rs::radix_sort_pairs<u32>(nk.p, nk2.p, p0.p, p1.p, wm, 0, sortbits, st);
+            timers.end(st);
+            u64* ks = c1 ? nk2.p : nk.p;
+            u32* ps = c1 ? p1.p : p0.p;
+            u64* kfree = c1 ? nk.p : nk2.p;  // scratch from here on
+            u32* pfree = c1 ? p0.p : p1.p;
+            // stable sort of the key order by group number
+            DevBuf<u64> gk(wm, st), gk2(wm, st);
+            DevBuf<u32> q1(wm, st);
+            gather_gid_kernel<<<gb, 256, 0, st>>>(gid.p, ps, wm, gk.p, pfree);
+            CDB_LAUNCH_CHECK();
+            timers.begin(st);
+            int c2 = rs::radix_sort_pairs<u32>(gk.p, gk2.p, pfree, q1.p, wm, 0, bits_for(ngroups ? ngroups - 1 : 0), st);
+            timers.end(st);
+            u32* perm2 = c2 ? q1.p : pfree;
+            DevBuf<P> pay2(wm, st);
+            apply_perm_kernel<P><<<gb, 256, 0, st>>>(perm2, ks, ps, pay.p, widx.p, wm, kfree, pay2.p, vals);
+            CDB_LAUNCH_CHECK();
+            // new ties inside the worklist
+            DevBuf<u32> widx2, gid2;
+            DevBuf<P> pay3;
+            u64 wm2 = 0, ng2 = 0;
+            compact<true>(kfree, gid.p, widx.p, pay2.p, wm, widx2, pay3, gid2, wm2, ng2);
+            widx = std::move(widx2);
+            gid = std::move(gid2);
+            pay = std::move(pay3);
+            wm = wm2;
+            ngroups = ng2;
+            depth += S;
+        }
+        return c;
+    }
+
+    template <bool HasGid>
+    void compact(const u64* keys, const u32* gid_in, const u32* widx_in, const P* pay_in, u64 m, DevBuf<u32>& widx,
+                 DevBuf<P>& pay, DevBuf<u32>& gid, u64& wm, u64& ngroups) {
+        wm = 0;
+        ngroups = 0;
+        if (m < 2) return;
+        const u64 nb = (m + TC_TILE - 1) / TC_TILE;
+        DevBuf<u64> bsum(nb + 1, st);
+        ties_count_kernel<HasGid><<<(unsigned)nb, TC_THREADS, 0, st>>>(keys, gid_in, m, bsum.p);
+        CDB_LAUNCH_CHECK();
+        prim::scan_blocksums_kernel<<<1, 1024, 0, st>>>(bsum.p, nb);
+        CDB_LAUNCH_CHECK();
+        u64 tot = 0;
+        CDB_CUDA(cudaMemcpyAsync(&tot, bsum.p + nb, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        wm = tot & 0xffffffffull;
+        ngroups = tot >> 32;
+        if (wm == 0) return;
+        widx.alloc(wm, st);
+        pay.alloc(wm, st);
+        gid.alloc(wm, st);
+        ties_write_kernel<HasGid, P><<<(unsigned)nb, TC_THREADS, 0, st>>>(keys, gid_in, widx_in, pay_in, m, bsum.p,
+                                                                        widx.p, pay.p, gid.p);
+        CDB_LAUNCH_CHECK();
+    }
+};
+
+template <typename P>
+static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t st) {
+    const i64 n = ix.n;
+    BuildTimers timers;
+    const int keybits = b * S;
+    // workspace -> chunk capacity
+    size_t free_b = 0, total_b = 0;
+    CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_item = 2 * (8 + sizeof(P)) + 1;  // ping-pong (key, packed) + look-back status share
+    const size_t sa_bytes = (size_t)n * sizeof(P);
+    i64 cap;
+    {
+        size_t ws = ix.opt.workspace_bytes > 0 ? (size_t)ix.opt.workspace_bytes : 0;
+        if (ws == 0) {
+            // single-chunk case re-uses the value buffer as the suffix array, so it needs no separate SA
+            size_t single = (size_t)n * per_item;
+            if (single < (size_t)(free_b * 0.85))
+                ws = single + per_item * rs::TILE;
+            else
+                ws = free_b > sa_bytes ? (size_t)((free_b - sa_bytes) * 0.80) : 0;
+        }
+        cap = (i64)(ws / per_item);
+        const i64 hard = ((i64)1 << 32) - 2 * rs::TILE;
+        if (cap > hard) cap = hard;
+        if (cap < 2 * rs::TILE) throw Error(CDB_ERR_NOMEM, "not enough device memory for the suffix-array build workspace");
+    }
+    const unsigned ex_grid = (unsigned)ceil_div(n, EX_TILE);
+    if (n <= cap) {
+        // ---- one chunk: the sorted value buffer becomes the suffix array itself
+        ix.chunks = 1;
+        DevBuf<u64> k0(n, st), k1(n, st);
+        DevBuf<P> v0(n, st), v1(n, st);
+        extract_kernel<P, 1><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, 0, 0, 0,
+                                                             k0.p, v0.p, nullptr, nullptr);
+        CDB_LAUNCH_CHECK();
+        u64* k[2] = {k0.p, k1.p};
+        P* v[2] = {v0.p, v1.p};
+        ChunkSorter<P> cs{ix, tab, b, S, st, timers};
+        int c = cs.run(k, v, (u64)n);
+        CDB_CUDA(cudaStreamSynchronize(st));
+        ix.d_sa = c ? (void*)v1.detach() : (void*)v0.detach();
+        ix.sort_ms = timers.total_ms();
+        return;
+    }
+    // ---- several chunks: partition by the top cb bits of the round-0 key
+    const int cb = keybits < 12 ? keybits : 12;
+    const int cbshift = keybits - cb;
+    const u32 nbuckets = 1u << cb;
+    DevBuf<unsigned long long> d_hist(nbuckets + 1, st);
+    CDB_CUDA(cudaMemsetAsync(d_hist.p, 0, d_hist.bytes(), st));
+    extract_kernel<P, 0><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, cbshift, 0, 0,
+                                                         nullptr, nullptr, nullptr, d_hist.p);
+    CDB_LAUNCH_CHECK();
+    std::vector<unsigned long long> hist(nbuckets);
+    CDB_CUDA(cudaMemcpyAsync(hist.data(), d_hist.p, nbuckets * 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    DevBuf<P> sa(n, st);
+    DevBuf<u64> k0(cap, st), k1(cap, st);
+    DevBuf<P> v0(cap, st), v1(cap, st);
+    unsigned long long* cursor = d_hist.p + nbuckets;
+    i64 sa_base = 0;
+    u32 blo = 0;
+    while (blo < nbuckets) {
+        i64 cnt = 0;
+        u32 bhi = blo;
+        while (bhi < nbuckets && cnt + (i64)hist[bhi] <= cap) cnt += (i64)hist[bhi++];
+        if (bhi == blo) throw Error(CDB_ERR_NOMEM, "a single 12-bit key bucket exceeds the suffix-array build workspace");
+        if (cnt > 0) {
+            ix.chunks++;
+            CDB_CUDA(cudaMemsetAsync(cursor, 0, 8, st));
+            extract_kernel<P, 2><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, cbshift,
+                                                                 blo, bhi, k0.p, v0.p, cursor, nullptr);
+            CDB_LAUNCH_CHECK();
+            u64* k[2] = {k0.p, k1.p};
+            P* v[2] = {v0.p, v1.p};
+            ChunkSorter<P> cs{ix, tab, b, S, st, timers};
+            int c = cs.run(k, v, (u64)cnt);
+            copy_kernel<P><<<kNumSMs * 8, 256, 0, st>>>(v[c], sa.p + sa_base, (u64)cnt);
+            CDB_LAUNCH_CHECK();
+            sa_base += cnt;
+        }
+        blo = bhi;
+    }
+    CDB_CUDA(cudaStreamSynchronize(st));
+    ix.d_sa = (void*)sa.detach();
+    ix.sort_ms = timers.total_ms();
+}
+
+void build_index(Index& ix, cudaStream_t st) {
+    cudaEvent_t e0, e1;
+    CDB_CUDA(cudaEventCreate(&e0));
+    CDB_CUDA(cudaEventCreate(&e1));
+    CDB_CUDA(cudaEventRecord(e0, st));
+    ix.rounds = 0;
+    ix.chunks = 0;
+    ix.sort_ms = 0;
+    // n and the width rule (src/index.cpp:183-208)
+    i64 ends[2] = {0, 0};
+    CDB_CUDA(cudaMemcpyAsync(&ends[0], ix.d_off, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaMemcpyAsync(&ends[1], ix.d_off + ix.nd, 8, cudaMemcpyDeviceToHost, st));
+    DevBuf<unsigned long long> d_max(1, st);
+    DevBuf<u32> d_present(256, st);
+    CDB_CUDA(cudaMemsetAsync(d_max.p, 0, 8, st));
+    CDB_CUDA(cudaMemsetAsync(d_present.p, 0, 1024, st));
+    if (ix.nd > 0) {
+        int g = (int)std::min<i64>(ceil_div(ix.nd, 256), kNumSMs * 8);
+        doc_stats_kernel<<<g, 256, 0, st>>>(ix.d_off, ix.nd, d_max.p);
+        CDB_LAUNCH_CHECK();
+    }
+    unsigned long long maxlen = 0;
+    CDB_CUDA(cudaMemcpyAsync(&maxlen, d_max.p, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    if (ends[0] != 0) throw Error(CDB_ERR_ARG, "doc_off[0] must be 0");
+    ix.n = ends[1];
+    ix.bits1 = ones_needed((u64)ix.nd);
+    ix.bits2 = ones_needed((u64)maxlen);
+    if (ix.bits1 + ix.bits2 > 64)
+        throw Error(CDB_ERR_TOO_MUCH_DATA, "The amount of data exceeds the maximum range that CoffeeDB can handle");
+    if (ix.bits1 > 32)
+        throw Error(CDB_ERR_TOO_MANY_OBJECTS, "The number of objects exceeds the maximum range that CoffeeDB can handle");
+    ix.mask = ix.bits1 >= 64 ? ~0ull : ((1ull << ix.bits1) - 1);
+    ix.width = (ix.bits1 + ix.bits2 <= 32) ? 4 : 8;
+    ix.chuck_size = std::max<i64>(4096, ix.n / 256);
+    ix.mixed = false;
+    if (ix.n > 0) {
+        int g = (int)std::min<i64>(ceil_div(ix.n / 16 + 1, 256), kNumSMs * 8);
+        byte_presence_kernel<<<g, 256, 0, st>>>(ix.d_text, ix.n, d_present.p);
+        CDB_LAUNCH_CHECK();
+        u32 present[256];
+        CDB_CUDA(cudaMemcpyAsync(present, d_present.p, 1024, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        SymTab tab;
+        int sigma = 0;
+        bool lo = false, hi = false;
+        for (int c = 0; c < 256; ++c) {
+            tab.sym[c] = 0;
+            if (present[c]) {
+                tab.sym[c] = (u16)(++sigma);
+                (c < 0x80 ? lo : hi) = true;
+            }
+        }
+        ix.mixed = lo && hi;
+        int b = bits_for((u64)sigma);  // symbols 0..sigma
+        int S = 64 / b;
+        if (S > EX_MAXS) S = EX_MAXS;
+        if (ix.width == 4)
+            build_typed<u32>(ix, tab, b, S, st);
+        else
+            build_typed<u64>(ix, tab, b, S, st);
+    }
+    CDB_CUDA(cudaEventRecord(e1, st));
+    CDB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ix.build_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ix.built = true;
+}
+
+}  // namespace cdb

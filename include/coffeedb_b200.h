@@ -1,0 +1,144 @@
+/* coffeedb_b200 — C ABI of the B200-native string index (suffix-array build + batched substring locate).
+ *
+ * This is the drop-in boundary for CoffeeDB's string-index hot path.  The reference has no
+ * FFI layer; its seam is the abstract C++ class `index` (src/index.h:9-23) and the three call sites in
+ * src/database.cpp (add :255-264, build :276-278, query :387-393).  Every entry point below names the
+ * reference interface it replaces.  A `class string_index : public index` adaptor over this ABI is in
+ * coffeedb_b200/host/string_index.hpp; INTEGRATION.md shows how a maintainer links it under database.cpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all integers little-endian host types
+ *   - every function returns a cdb_status; on failure cdb_last_error() (thread-local) holds the message.
+ *     For the three conditions the reference throws on, the message is the reference's exact text, so the
+ *     adaptor can rethrow std::runtime_error(cdb_last_error()) and the server's catch (src/server.cpp:58-62)
+ *     produces the same HTTP 500 body.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with CDB_ERR_CUDA.
+ *   - documents are identified by their "doc index" = order of cdb_add calls (src/index.cpp:174-177);
+ *     results are reported as (ids[doc index], occurrences), rows in ascending doc index, exactly as
+ *     string_index::query does (src/index.cpp:316-322).
+ */
+#ifndef COFFEEDB_B200_H
+#define COFFEEDB_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cdb_status {
+    CDB_OK = 0,
+    CDB_ERR_TOO_MUCH_DATA = 1,    /* src/index.cpp:195-197 "The amount of data exceeds the maximum range that CoffeeDB can handle" */
+    CDB_ERR_TOO_MANY_OBJECTS = 2, /* src/index.cpp:198-200 "The number of objects exceeds the maximum range that CoffeeDB can handle" */
+    CDB_ERR_EMPTY_KEYWORD = 3,    /* src/index.cpp:239-241 "Empty keywords are not allowed" */
+    CDB_ERR_CUDA = 4,             /* CUDA runtime failure or no device */
+    CDB_ERR_NOMEM = 5,            /* host or device allocation failed */
+    CDB_ERR_STATE = 6,            /* call order violated (e.g. locate before build, add after build) */
+    CDB_ERR_ARG = 7               /* bad argument */
+} cdb_status;
+
+typedef struct cdb_index cdb_index; /* replaces one `string_index` object (src/index.h:54-86) */
+
+typedef struct cdb_options {
+    int32_t device;            /* CUDA device ordinal; -1 = current device */
+    int32_t compat_signed;     /* 1 (default) = reproduce the reference's signed-radix / unsigned-leaf order on
+                                  corpora mixing bytes <0x80 and >=0x80 (SURVEY.md §8 note N1); 0 = plain unsigned */
+    int64_t workspace_bytes;   /* cap on temporary device memory used by build (0 = 60 % of free memory) */
+    int32_t keep_host_copy;    /* 1 = keep the host staging copy of the text after build (needed for re-build) */
+    int32_t reserved;
+} cdb_options;
+
+/* Result of a batched locate, host memory.  Row q (pattern q) is pairs[2*row_off[q] .. 2*row_off[q+1]):
+ * consecutive (id, count) int64 pairs — the memory layout of std::vector<std::pair<int64_t,int64_t>>,
+ * which is what string_index::query returns (src/index.h:83). */
+typedef struct cdb_result {
+    int64_t npat;
+    int64_t total_pairs;
+    int64_t total_occurrences;
+    const int64_t* row_off; /* [npat+1] */
+    const int64_t* pairs;   /* [2*total_pairs] */
+    void* _owner;
+} cdb_result;
+
+/* Same, device memory (valid until cdb_device_result_free). */
+typedef struct cdb_device_result {
+    int64_t npat;
+    int64_t total_pairs;
+    int64_t total_occurrences;
+    int64_t* row_off; /* device [npat+1] */
+    int64_t* pairs;   /* device [2*total_pairs] */
+    int64_t* left;    /* device [npat]  SA interval [left,right) of every pattern (src/index.cpp:262-287) */
+    int64_t* right;   /* device [npat] */
+    void* _owner;
+} cdb_device_result;
+
+/* Highlight spans (replaces the occurrence enumeration of ac_automaton::render, src/database.cpp:58-77):
+ * for text t, spans[2*span_off[t] .. 2*span_off[t+1]) are inclusive [begin,end] byte ranges, ascending,
+ * overlapping matches merged, touching ones not. */
+typedef struct cdb_spans {
+    int64_t ntext;
+    int64_t total_spans;
+    const int64_t* span_off; /* [ntext+1] */
+    const int64_t* spans;    /* [2*total_spans] */
+    void* _owner;
+} cdb_spans;
+
+const char* cdb_last_error(void);
+const char* cdb_version(void);
+int cdb_device_count(void);
+
+/* string_index::string_index() (src/index.h:54).  opts may be NULL. */
+cdb_status cdb_create(const cdb_options* opts, cdb_index** out);
+/* string_index::~string_index() (src/index.h:79-83) */
+void cdb_destroy(cdb_index* idx);
+
+/* string_index::add(int64_t id, std::string_view value) (src/index.cpp:174-177).  The bytes are copied;
+ * the caller may release them on return (the reference borrows them, database.cpp:263-264). */
+cdb_status cdb_add(cdb_index* idx, int64_t id, const void* value, int64_t len);
+/* nd add() calls at once: document d = text[doc_off[d], doc_off[d+1]). */
+cdb_status cdb_add_many(cdb_index* idx, const int64_t* ids, const void* text, const int64_t* doc_off, int64_t nd);
+
+/* string_index::build() (src/index.cpp:178-236): uploads the staged text and constructs the packed suffix
+ * array on the device.  Element = (offset_in_doc << bits) | doc_index, 4 bytes wide iff bits1+bits2 <= 32. */
+cdb_status cdb_build(cdb_index* idx);
+/* Same, from a corpus already resident in device memory (text[n], doc_off[nd+1], ids[nd] are BORROWED and
+ * must outlive the index).  `stream` is a cudaStream_t (NULL = default stream). */
+cdb_status cdb_build_device(cdb_index* idx, const void* d_text, const int64_t* d_doc_off, const int64_t* d_ids,
+                            int64_t nd, void* stream);
+
+/* Index geometry after build: SA length n, element width (4|8), doc-index field width and mask
+ * (src/index.h:56-58). */
+cdb_status cdb_info(const cdb_index* idx, int64_t* n, int64_t* nd, int32_t* width, int32_t* bits, uint64_t* mask);
+/* Copies the packed suffix array to host memory (n*width bytes), for parity checks. */
+cdb_status cdb_export_sa(const cdb_index* idx, void* buf, int64_t buf_bytes);
+/* Device pointer of the packed suffix array (borrowed). */
+cdb_status cdb_sa_device_ptr(const cdb_index* idx, const void** d_sa);
+
+/* Batched string_index::query(keyword) (src/index.cpp:237-326): pattern q = pat[pat_off[q], pat_off[q+1]).
+ * An empty pattern fails the whole batch with CDB_ERR_EMPTY_KEYWORD.  Re-entrant: may be called concurrently
+ * from several host threads on the same index (the reference's query() is const and runs under a shared
+ * lock, database.cpp:387-393). */
+cdb_status cdb_locate_batch(const cdb_index* idx, const void* pat, const int64_t* pat_off, int64_t npat, cdb_result* out);
+void cdb_result_free(cdb_result* r);
+/* Same with patterns and results resident in device memory; work is enqueued on `stream` and the call
+ * returns after the stream has drained (result sizes are data dependent). */
+cdb_status cdb_locate_batch_device(const cdb_index* idx, const void* d_pat, const int64_t* d_pat_off, int64_t npat,
+                                   void* stream, cdb_device_result* out);
+void cdb_device_result_free(cdb_device_result* r);
+
+/* Highlight: merged occurrence spans of the keyword set kw (nkw keywords, kw_off[nkw+1]) inside each of the
+ * documents docs[0..ndocs) (doc indices).  Replaces ac_automaton::render's span loop (database.cpp:58-77);
+ * marker splicing (database.cpp:78-90) stays on the host (cdb_splice). */
+cdb_status cdb_locate_spans(const cdb_index* idx, const void* kw, const int64_t* kw_off, int64_t nkw,
+                            const int64_t* docs, int64_t ndocs, cdb_spans* out);
+void cdb_spans_free(cdb_spans* s);
+/* database.cpp:78-90: writes text with left/right spliced around the spans into out (capacity out_cap);
+ * returns the rendered length (also when out is too small or NULL). */
+int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t nspans, const void* left, int64_t llen,
+                   const void* right, int64_t rlen, void* out, int64_t out_cap);
+
+/* Timing of the last cdb_build*/ /* (milliseconds, CUDA events): total and the radix-sort share. */
+cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,159 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI library
+(coffeedb_b200 is a ctypes binding); expected values are the golden vectors generated from the compiled
+reference, the live oracle, and size-independent properties at larger sizes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import coffeedb_b200 as cdb
+import oracle
+from tests import cases, corpora
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a, np.uint64).tobytes()).hexdigest()
+
+
+def build(text, off, ids, **kw):
+    ix = cdb.StringIndex(**kw)
+    ix.add_many(ids, text, off)
+    ix.build()
+    return ix
+
+
+PLAIN_CASES = [c for c in cases.CASES if c not in cases.N1_CASES]
+
+
+@pytest.mark.parametrize("name", PLAIN_CASES)
+def test_suffix_array_matches_reference(name, golden):
+    text, off, ids, _ = cases.CASES[name]()
+    ix = build(text, off, ids)
+    inf = ix.info()
+    assert inf["bits"] == int(golden[f"{name}/bits1"]) and inf["width"] == int(golden[f"{name}/width"])
+    assert inf["n"] == int(golden[f"{name}/n"]) and inf["mask"] == (1 << inf["bits"]) - 1
+    sa = ix.export_sa()
+    if f"{name}/sa" in golden:
+        assert np.array_equal(sa, golden[f"{name}/sa"])
+    assert sha(sa) == str(golden[f"{name}/sa_sha"])
+    ix.close()
+
+
+@pytest.mark.parametrize("name", PLAIN_CASES)
+def test_locate_matches_reference(name, golden):
+    text, off, ids, pats = cases.CASES[name]()
+    ix = build(text, off, ids)
+    row_off, pairs = ix.locate_batch(golden[f"{name}/pat"], golden[f"{name}/pat_off"])
+    assert np.array_equal(row_off, golden[f"{name}/row_off"])
+    assert np.array_equal(pairs, golden[f"{name}/pairs"])
+    # single-keyword form == string_index::query
+    for i in (0, len(pats) // 2, len(pats) - 1):
+        g = golden[f"{name}/pairs"][golden[f"{name}/row_off"][i]:golden[f"{name}/row_off"][i + 1]]
+        assert ix.query(pats[i]) == [tuple(r) for r in g.tolist()]
+    ix.close()
+
+
+def test_known_answers_and_errors():
+    ix = cdb.StringIndex()
+    ix.add(100, b"3010103")
+    ix.add(101, b"301022")
+    ix.build()
+    assert ix.query(b"010") == [(100, 2), (101, 1)]      # README.md:91
+    assert ix.query(b"0") == [(100, 3), (101, 2)]
+    assert ix.query(b"9") == [] and ix.query(b"30101034") == []
+    with pytest.raises(RuntimeError, match="^Empty keywords are not allowed$"):
+        ix.query(b"")
+    with pytest.raises(RuntimeError, match="^Empty keywords are not allowed$"):
+        ix.locate_batch([b"a", b"", b"b"])
+    ix.close()
+
+
+def test_empty_index_and_empty_batch():
+    ix = cdb.StringIndex()
+    ix.build()
+    assert ix.info()["n"] == 0 and ix.info()["bits"] == 1 and ix.info()["width"] == 4
+    assert ix.query(b"a") == []
+    ro, pr = ix.locate_batch([])
+    assert ro.tolist() == [0] and pr.shape == (0, 2)
+    ix.close()
+    ix = cdb.StringIndex()
+    for i in range(5):
+        ix.add(i, b"")
+    ix.build()
+    assert ix.info()["n"] == 0 and ix.query(b"a") == []
+    ix.close()
+
+
+def test_against_live_oracle_random():
+    """Random corpora the golden file does not hold: compare with the oracle port run here."""
+    for seed in range(4):
+        text, off, ids = corpora.ragged(2000 + 500 * seed, 40 + 30 * seed, seed=100 + seed,
+                                        alphabet=[b"ab", b"abc", b"acgt", b"abcdefgh"][seed])
+        ix = build(text, off, ids)
+        sa, b1, w = oracle.port.build_sa(text, off)
+        assert np.array_equal(ix.export_sa(), sa)
+        pat, poff = corpora.sampled_patterns(text, off, 200, 1, 12, seed=200 + seed)
+        row_off, pairs = ix.locate_batch(pat, poff)
+        for q in range(200):
+            kw = bytes(pat[poff[q]:poff[q + 1]])
+            assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+        ix.close()
+
+
+def test_chunked_build_equals_single_chunk():
+    """A workspace cap forces the multi-chunk path (the 10 GB configuration's path); result must not change."""
+    text, off, ids = corpora.uniform(3000, 200, seed=41)
+    a = build(text, off, ids)
+    b = build(text, off, ids, workspace_bytes=3_000_000)
+    assert b.build_stats()["chunks"] > 1 and a.build_stats()["chunks"] == 1
+    assert np.array_equal(a.export_sa(), b.export_sa())
+    a.close()
+    b.close()
+
+
+def test_large_interval_path():
+    """Intervals longer than the warp path's capacity go through the device radix sort."""
+    text, off, ids = corpora.uniform(20000, 50, seed=43, lo=ord("a"), hi=ord("c"))
+    ix = build(text, off, ids)
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    pats = [b"a", b"ab", b"abc", b"abca", b"c", b"cc", b"abcabcabc", b"bbbbbbbbbbbbbbbbbbbbbbbb"]
+    row_off, pairs = ix.locate_batch(pats)
+    for q, kw in enumerate(pats):
+        assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+    ix.close()
+
+
+def test_brute_force_property_medium():
+    """test-string.py:52-56 property at a size the oracle does not need to see."""
+    text, off, ids = corpora.uniform(2000, 2000, seed=47)
+    ix = build(text, off, ids)
+    pat, poff = corpora.uniform_patterns(40, 3, seed=48)
+    row_off, pairs = ix.locate_batch(pat, poff)
+    for q in range(40):
+        kw = bytes(pat[poff[q]:poff[q + 1]])
+        assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], corpora.brute_count(text, off, ids, kw))
+    ix.close()
+
+
+def test_highlight_spans_match_reference(golden):
+    """K8: spans from SA positions == ac_automaton::render's spans (database.cpp:58-77)."""
+    hl = cases.highlight_cases()
+    rend, roff = golden["highlight/rendered"], golden["highlight/rendered_off"]
+    texts = [t for _k, t in hl]
+    ix = cdb.StringIndex()
+    for i, t in enumerate(texts):
+        ix.add(i, t)
+    ix.build()
+    for i, (kws, text) in enumerate(hl):
+        spans = ix.spans(kws, [i])[0]
+        assert np.array_equal(spans, oracle.port.spans(kws, text)), (kws, text)
+        assert cdb.splice(text, spans, b"<b>", b"</b>") == rend[roff[i]:roff[i + 1]].tobytes()
+    # several documents at once, duplicates and arbitrary order
+    kws = [b"ab", b"b"]
+    docs = [5, 3, 5, 0, 40]
+    got = ix.spans(kws, docs)
+    for d, sp in zip(docs, got):
+        assert np.array_equal(sp, oracle.port.spans(kws, texts[d]))
+    ix.close()
