@@ -464,7 +464,8 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         cap = (i64)(ws / per_item);
         const i64 hard = ((i64)1 << 32) - 2 * rs::TILE;
         if (cap > hard) cap = hard;
-        if (cap < 2 * rs::TILE) throw Error(CDB_ERR_NOMEM, "not enough device memory for the suffix-array build workspace");
+        if (n > cap && cap < 2 * rs::TILE)
+            throw Error(CDB_ERR_NOMEM, "not enough device memory for the suffix-array build workspace");
     }
     const unsigned ex_grid = (unsigned)ceil_div(n, EX_TILE);
     if (n <= cap) {
