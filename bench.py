@@ -1,0 +1,478 @@
+#!/usr/bin/env python
+"""bench.py — measures the string-index hot path on B200 (BASELINE.json metric: substring queries/sec over a
+10 GB corpus; SA build GB/s vs HBM peak).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # the reference's own CPU query() on the host cores
+
+A "step" is one batched locate of the workload's pattern batch over the resident index.  Workloads
+(SURVEY.md §8d): cfg3 = 10^8 docs x 100 B a-z (10 GB) + 10^6 five-byte patterns (the configuration the metric is
+quoted on; fits one 180 GB B200), cfg2 = 10^7 docs (1 GB) + 10^5 patterns, cfg1 = 1000 x 1 KB + 100 patterns.
+With N > 1 the cfg3 corpus is sharded by contiguous doc range over the ranks (BASELINE config 4), every rank
+gets the whole pattern batch (NCCL broadcast), runs its shard and the per-pattern row lengths / occurrence
+counts are merged with NCCL — total work is fixed, so scaling is "strong".
+
+Prints ONE JSON line (rank 0).  `value` = queries/s with patterns and results resident in HBM; `e2e` = the same
+through the host-buffer C-ABI call (cdb_locate_batch: H2D of the patterns, D2H of the full CSR result inside the
+timed region).  `roofline` describes the dominant kernel, `cpu_baseline` the reference's query() timed on this
+box's host cores in the same run.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg1": dict(nd=1_000, doclen=1024, npat=100, m=3, seed=1),
+    "cfg2": dict(nd=10_000_000, doclen=100, npat=100_000, m=5, seed=2),
+    "cfg3": dict(nd=100_000_000, doclen=100, npat=1_000_000, m=5, seed=3),
+}
+NBLOCKS = 8  # the corpus is defined as 8 equal doc-range blocks so that it is the same for every N
+METRIC = "substring_queries_per_sec"
+UNIT = "queries/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class DevArray:
+    """__cuda_array_interface__ view of library-owned device memory (so torch can wrap it without a copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def make_patterns(w):
+    from tests import corpora
+    return corpora.uniform_patterns(w["npat"], w["m"], seed=1000 + w["seed"])
+
+
+def make_shard(w, rank: int, world: int, device):
+    """Shard `rank` of `world`: blocks [rank*8/world, (rank+1)*8/world) of the corpus, generated on the device."""
+    import torch
+    nd, L = w["nd"], w["doclen"]
+    per = nd // NBLOCKS
+    b0, b1 = rank * NBLOCKS // world, (rank + 1) * NBLOCKS // world
+    if nd < NBLOCKS * 8:
+        assert world == 1
+        b0, b1, per = 0, 1, nd
+    snd = (b1 - b0) * per
+    text = torch.zeros(snd * L + 64, dtype=torch.uint8, device=device)  # 64 B of padding (cdb_build_device contract)
+    for b in range(b0, b1):
+        g = torch.Generator(device=device)
+        g.manual_seed(w["seed"] * 1000 + b)
+        lo = (b - b0) * per * L
+        text[lo:lo + per * L] = torch.randint(97, 123, (per * L,), dtype=torch.uint8, device=device, generator=g)
+    doc_off = torch.arange(snd + 1, dtype=torch.int64, device=device) * L
+    gdoc = torch.arange(b0 * per, b0 * per + snd, dtype=torch.int64, device=device)
+    ids = (gdoc * 2654435761) % (1 << 40) + 10 ** 12  # unique, not in doc order
+    return text, doc_off, ids, snd
+
+
+def algorithmic_bytes_per_pattern(n, w, occ, d):
+    """64*S + w*occ + 24*d with S = 2*ceil(log2 n) probes."""
+    S = 2 * int(np.ceil(np.log2(max(n, 2))))
+    return {"search": 64.0 * S, "gather": float(w) * occ + 24.0 * d, "S": S}
+
+
+def pick_workload(name, world):
+    if name != "auto":
+        return name
+    env = os.environ.get("CDB_BENCH_WORKLOAD")
+    if env:
+        return env
+    try:
+        import torch
+        free, _tot = torch.cuda.mem_get_info()
+        if world == 1 and free < 150 * (1 << 30):
+            return "cfg2"
+    except Exception:
+        pass
+    return "cfg3"
+
+
+# ------------------------------------------------------------------------------------------------ reference
+def reference_index_from_gpu(w, verbose=False):
+    """Full-size index for the reference's query(): corpus generated as in our arm, suffix array built on the GPU
+    (the reference's own build of 10^10 suffixes takes tens of minutes) and injected into an unmodified
+    string_index; query() itself is 100 % the reference's code on the host cores."""
+    import torch
+    import coffeedb_b200 as cdb
+    import oracle
+    dev = torch.device("cuda", 0)
+    text, doc_off, ids, snd = make_shard(w, 0, 1, dev)
+    ix = cdb.StringIndex(device=0)
+    ix.build_device(text.data_ptr(), doc_off.data_ptr(), ids.data_ptr(), snd, torch.cuda.current_stream().cuda_stream,
+                    keep=(text, doc_off, ids))
+    inf = ix.info()
+    h_text = text[: inf["n"]].cpu().numpy()
+    h_off = doc_off.cpu().numpy()
+    h_ids = ids.cpu().numpy()
+    sa = np.empty(max(inf["n"], 1), np.uint32 if inf["width"] == 4 else np.uint64)
+    cdb._check(cdb.lib().cdb_export_sa(ix._h, sa.ctypes.data, sa.nbytes))
+    sa = sa[: inf["n"]]
+    ix.close()
+    del text, doc_off, ids
+    torch.cuda.empty_cache()
+    r = oracle.Ref()
+    r.add_many_borrowed(h_ids, h_text, h_off)
+    r.adopt_sa(sa, inf["bits"])
+    return r, inf
+
+
+def reference_self_built(w, nd_cap=1_000_000):
+    """No GPU: the reference builds its own index on a bounded prefix of the corpus."""
+    import oracle
+    from tests import corpora
+    nd = min(w["nd"], nd_cap)
+    text, off, ids = corpora.uniform(nd, w["doclen"], seed=w["seed"])
+    r = oracle.Ref()
+    r.add_many_borrowed(ids, text, off)
+    t0 = time.perf_counter()
+    r.build()
+    return r, {"n": int(off[-1]), "nd": nd, "build_s": time.perf_counter() - t0}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    wname = pick_workload(args.workload, 1)
+    w = WORKLOADS[wname]
+    pat, poff = make_patterns(w)
+    threads = oracle.hardware_threads()
+    have_gpu = False
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    if have_gpu:
+        ref, inf = reference_index_from_gpu(w)
+        how = (f"reference query() (src/index.cpp:237-326, compiled unmodified) on the full {wname} index; the packed "
+               f"suffix array was built on the GPU and injected because the reference build of n={inf['n']:.3g} suffixes "
+               "takes tens of minutes")
+    else:
+        ref, inf = reference_self_built(w)
+        how = f"reference build()+query() on the first {inf['nd']} documents of {wname} (no GPU to build the full index)"
+    # bounded sample per step: ~3 s of host time
+    probe = min(w["npat"], 20_000)
+    s, _tp, _to = ref.query_batch_timed(pat[: poff[probe]], poff[: probe + 1], threads)
+    per_step = int(min(w["npat"], max(probe, 3.0 / max(s / probe, 1e-9))))
+    times = []
+    tp = to = 0
+    for it in range(args.warmup + args.steps):
+        s, tp, to = ref.query_batch_timed(pat[: poff[per_step]], poff[: per_step + 1], threads)
+        if it >= args.warmup:
+            times.append(s)
+    total = float(np.sum(times))
+    val = per_step * len(times) / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": wname, "docs": w["nd"], "doc_bytes": w["doclen"], "patterns_per_step": per_step,
+                   "pattern_bytes": w["m"], "n_suffixes": inf["n"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"{per_step} of {w['npat']} patterns per step; {how}",
+                         "pairs_per_step": tp, "occurrences_per_step": to},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import coffeedb_b200 as cdb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — coffeedb_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wname = pick_workload(args.workload, world)
+    w = dict(WORKLOADS[wname])
+    if args.npat:
+        w["npat"] = args.npat
+    hbm_peak, peak_src = peaks()
+
+    # ---- corpus shard + index build (setup; build throughput is reported, not part of the locate step)
+    text, doc_off, ids, snd = make_shard(w, rank, world, dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    ix = cdb.StringIndex(device=local)
+    t0 = time.perf_counter()
+    ix.build_device(text.data_ptr(), doc_off.data_ptr(), ids.data_ptr(), snd, stream, keep=(text, doc_off, ids))
+    build_wall = time.perf_counter() - t0
+    inf, bst = ix.info(), ix.build_stats()
+    n_shard, width = inf["n"], inf["width"]
+
+    # ---- patterns: pinned host copy (e2e) and device copy (value)
+    pat, poff = make_patterns(w)
+    npat = w["npat"]
+    h_pat = torch.from_numpy(pat).pin_memory()
+    h_poff = torch.from_numpy(poff).pin_memory()
+    d_pat = torch.zeros(len(pat) + 8, dtype=torch.uint8, device=dev)
+    d_poff = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        d_pat[: len(pat)].copy_(h_pat, non_blocking=True)
+        d_poff.copy_(h_poff, non_blocking=True)
+    tot_occ = torch.zeros(npat, dtype=torch.int64, device=dev)
+
+    def step():
+        """One pass of the hot path over one pattern batch, inputs resident in HBM."""
+        if world > 1:  # pattern broadcast (BASELINE config 4)
+            dist.broadcast(d_pat, 0)
+            dist.broadcast(d_poff, 0)
+        res = ix.locate_batch_device(d_pat.data_ptr(), d_poff.data_ptr(), npat, stream)
+        info = (res.total_pairs, res.total_occurrences)
+        if world > 1:
+            # count merge: per-pattern row lengths of every shard (global CSR offsets = their scan in rank order)
+            # and per-pattern occurrence totals; the rows themselves stay sharded
+            ro = torch.as_tensor(DevArray(res.row_off, npat + 1), device=dev)
+            rows = ro[1:] - ro[:-1]
+            gathered = torch.empty(world * npat, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, rows)
+            occ = (torch.as_tensor(DevArray(res.right, npat), device=dev) - torch.as_tensor(DevArray(res.left, npat), device=dev))
+            tot_occ.copy_(occ)
+            dist.all_reduce(tot_occ)
+        ix.device_result_free(res)
+        return info
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    phase = {k: 0.0 for k in ("search_ms", "count_ms", "large_ms", "scan_ms", "emit_ms", "total_ms")}
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = cdb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pairs, occs = step()
+        st = cdb.last_locate_stats()
+        for k in phase:
+            phase[k] += st[k]
+    e1.record()
+    barrier()
+    launches = cdb.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = npat * args.steps / (ms_total / 1e3)
+    for k in phase:
+        phase[k] /= args.steps
+
+    # ---- e2e: host buffers through cdb_locate_batch, H2D + D2H inside the timed region
+    def e2e_step():
+        res = ix.locate_batch_raw(h_pat.numpy(), h_poff.numpy())  # pinned host buffers
+        b = (res.npat + 1) * 8 + res.total_pairs * 16
+        first = res.pairs[0] if res.total_pairs else 0  # touch the host result
+        ix.result_free(res)
+        return b, first
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        d2h_bytes, _ = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d2h_bytes, _ = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = npat * e2e_steps / float(e2e_s.item())
+    h2d_bytes = int(pat.nbytes + poff.nbytes)
+
+    # ---- roofline of the dominant kernel (CUDA-event phase times measured inside the library on `stream`)
+    occ_pp = occs / npat
+    d_pp = pairs / npat
+    alg = algorithmic_bytes_per_pattern(n_shard, width, occ_pp, d_pp)
+    kernels = {
+        "search_kernel": (phase["search_ms"], alg["search"] * npat),
+        "small_path_kernel<count>": (phase["count_ms"], width * occ_pp * npat),
+        "small_path_kernel<emit>": (phase["emit_ms"], alg["gather"] * npat),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    path_bytes = (alg["search"] + alg["gather"]) * npat
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+        "phases_ms": phase,
+        "path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (phase["total_ms"] / 1e3) / 1e9,
+                 "frac": path_bytes / (phase["total_ms"] / 1e3) / 1e9 / hbm_peak},
+    }
+
+    # ---- CPU baseline: the reference's query() on this box's host cores, same index, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname)
+        except Exception as e:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": wname + ("" if world == 1 else f"-sharded{world}"), "docs": w["nd"],
+                       "doc_bytes": w["doclen"], "corpus_bytes": w["nd"] * w["doclen"], "patterns_per_step": npat,
+                       "pattern_bytes": w["m"], "n_suffixes_per_gpu": n_shard, "sa_width": width,
+                       "l2": "inputs (suffix array + text) far larger than L2, no flush needed",
+                       "parallelism": "replica" if world == 1 else f"doc-range shards x{world}, NCCL pattern bcast + count merge"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "build": {"corpus_GB_per_s": n_shard / 1e9 / (bst["total_ms"] / 1e3), "ms": bst["total_ms"],
+                      "sort_ms": bst["sort_ms"], "rounds": bst["rounds"], "chunks": bst["chunks"], "wall_s": build_wall,
+                      "compulsory_bytes": n_shard * (1 + width),
+                      "frac_of_hbm_peak": n_shard * (1 + width) / 1e9 / (bst["total_ms"] / 1e3) / hbm_peak},
+            "pairs_per_step": int(pairs), "occurrences_per_step": int(occs),
+        }
+        print(json.dumps(out))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname):
+    import coffeedb_b200 as cdb
+    import oracle
+    h_text = text[: inf["n"]].cpu().numpy()
+    h_off = doc_off.cpu().numpy()
+    h_ids = ids.cpu().numpy()
+    sa = np.empty(max(inf["n"], 1), np.uint32 if inf["width"] == 4 else np.uint64)
+    cdb._check(cdb.lib().cdb_export_sa(ix._h, sa.ctypes.data, sa.nbytes))
+    sa = sa[: inf["n"]]
+    ref = oracle.Ref()
+    ref.add_many_borrowed(h_ids, h_text, h_off)
+    ref.adopt_sa(sa, inf["bits"])
+    threads = oracle.hardware_threads()
+    probe = min(w["npat"], 20_000)
+    s, _a, _b = ref.query_batch_timed(pat[: poff[probe]], poff[: probe + 1], threads)
+    nsample = int(min(w["npat"], max(probe, 12.0 / max(s / probe, 1e-9))))
+    s, tp, to = ref.query_batch_timed(pat[: poff[nsample]], poff[: nsample + 1], threads)
+    # full-size parity check on the same sample: identical totals of (id,count) pairs and occurrences
+    row_off, pairs = ix.locate_batch(pat[: poff[nsample]], poff[: nsample + 1])
+    ok = (len(pairs) == tp) and (int(pairs[:, 1].sum()) == to)
+    # and identical rows on a handful of patterns
+    for q in range(0, nsample, max(1, nsample // 16)):
+        got = pairs[row_off[q]:row_off[q + 1]]
+        ok = ok and np.array_equal(got, ref.query(bytes(pat[poff[q]:poff[q + 1]])))
+    ref.close()
+    return {"value": nsample / s, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": (f"{nsample} of {w['npat']} patterns on the full {wname} index; reference query() "
+                       "(src/index.cpp:237-326, compiled unmodified) over the GPU-built packed suffix array, "
+                       f"{threads} host threads pulling 64-pattern blocks"),
+            "pairs": int(tp), "occurrences": int(to), "parity_with_gpu": "ok" if ok else "MISMATCH"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--npat", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

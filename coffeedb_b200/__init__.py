@@ -27,7 +27,7 @@ EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
     "cdb_build", "cdb_build_device", "cdb_info", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
-    "cdb_splice", "cdb_build_stats",
+    "cdb_splice", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count",
 ]
 
 CDB_OK = 0
@@ -100,8 +100,23 @@ def lib():
         L.cdb_splice.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
         L.cdb_splice.restype = C.c_int64
         L.cdb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p]
+        L.cdb_last_locate_stats.argtypes = [C.POINTER(C.c_double), i64p]
+        L.cdb_last_locate_stats.restype = None
+        L.cdb_launch_count.restype = C.c_uint64
         _lib = L
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().cdb_launch_count())
+
+
+def last_locate_stats() -> dict:
+    ms = (C.c_double * 6)()
+    cn = (C.c_int64 * 4)()
+    lib().cdb_last_locate_stats(ms, cn)
+    return {"search_ms": ms[0], "count_ms": ms[1], "large_ms": ms[2], "scan_ms": ms[3], "emit_ms": ms[4],
+            "total_ms": ms[5], "npat": cn[0], "pairs": cn[1], "occurrences": cn[2], "nlarge": cn[3]}
 
 
 def _check(rc: int):

@@ -13,6 +13,8 @@
 namespace cdb {
 
 static thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+thread_local LocateStats g_locate_stats;
 
 Index::~Index() { free_device(); }
 
@@ -122,6 +124,19 @@ extern "C" {
 
 const char* cdb_last_error(void) { return g_last_error.c_str(); }
 const char* cdb_version(void) { return "coffeedb_b200 0.1 (sm_100a)"; }
+
+uint64_t cdb_launch_count(void) { return g_launches.load(); }
+
+void cdb_last_locate_stats(double* ms6, int64_t* counts4) {
+    const LocateStats& s = g_locate_stats;
+    if (ms6) {
+        ms6[0] = s.search_ms; ms6[1] = s.count_ms; ms6[2] = s.large_ms;
+        ms6[3] = s.scan_ms; ms6[4] = s.emit_ms; ms6[5] = s.total_ms;
+    }
+    if (counts4) {
+        counts4[0] = s.npat; counts4[1] = s.total_pairs; counts4[2] = s.total_occ; counts4[3] = s.nlarge;
+    }
+}
 
 int cdb_device_count(void) {
     int cnt = 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -32,7 +33,21 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define CDB_CUDA(x) ::cdb::cuda_check((x), #x, __FILE__, __LINE__)
-#define CDB_LAUNCH_CHECK() ::cdb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+// every kernel launch of this library goes through this macro: it checks the launch and counts it
+// (cdb_launch_count() — bench.py reports the count as gpu_launches)
+extern std::atomic<unsigned long long> g_launches;
+#define CDB_LAUNCH_CHECK()                                                             \
+    do {                                                                               \
+        ::cdb::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
+        ::cdb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__);    \
+    } while (0)
+
+// per-thread timing of the last locate call (CUDA events on the launching stream), milliseconds
+struct LocateStats {
+    float search_ms = 0, count_ms = 0, large_ms = 0, scan_ms = 0, emit_ms = 0, total_ms = 0;
+    long long npat = 0, total_pairs = 0, total_occ = 0, nlarge = 0;
+};
+extern thread_local LocateStats g_locate_stats;
 
 // Stream-ordered temporary device buffer (cudaMallocAsync pool): allocation is cheap after warm-up and the
 // calls are re-entrant, which the locate path needs (several host threads query one index concurrently).

@@ -286,16 +286,27 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<unsigned long long> counters(4, st);  // [0] large patterns, [1] occurrences (small path), [2] err
     DevBuf<u32> large_list(npat, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+    cudaEvent_t ev[6];
+    for (auto& e : ev) CDB_CUDA(cudaEventCreate(&e));
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() {
+            for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]);
+        }
+    } ev_guard{ev};
+    CDB_CUDA(cudaEventRecord(ev[0], st));
     SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
     int* err = reinterpret_cast<int*>(counters.p + 2);
     search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, d_pat, d_pat_off, npat, left.p, right.p, err);
     CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaEventRecord(ev[1], st));
     const size_t small_smem = (size_t)kSmallWarps * 2 * kSmallCap * sizeof(u32);
     static_assert(kSmallWarps * 2 * kSmallCap * sizeof(u32) <= 48 * 1024, "small path uses static-limit shared memory");
     const unsigned small_grid = (unsigned)ceil_div(npat, kSmallWarps);
     small_path_kernel<SAT, false><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
         sa, ix.mask, ix.d_ids, left.p, right.p, npat, dcount.p, large_list.p, counters.p, nullptr, nullptr);
     CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaEventRecord(ev[2], st));
     unsigned long long hc[4];
     CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
@@ -338,11 +349,13 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
     }
     // exact CSR offsets
+    CDB_CUDA(cudaEventRecord(ev[3], st));
     prim::exclusive_scan<u64>(dcount.p, dcount.p, (u64)npat, st);
     u64 total_pairs = 0;
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, dcount.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
     DevBuf<i64> pairs((size_t)total_pairs * 2, st);
+    CDB_CUDA(cudaEventRecord(ev[4], st));
     small_path_kernel<SAT, true><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
         sa, ix.mask, ix.d_ids, left.p, right.p, npat, nullptr, nullptr, nullptr, dcount.p, pairs.p);
     CDB_LAUNCH_CHECK();
@@ -352,7 +365,21 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
                                                 ix.d_ids, pairs.p);
         CDB_LAUNCH_CHECK();
     }
+    CDB_CUDA(cudaEventRecord(ev[5], st));
     CDB_CUDA(cudaStreamSynchronize(st));
+    {
+        LocateStats& ls = g_locate_stats;
+        cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&ls.count_ms, ev[1], ev[2]);
+        cudaEventElapsedTime(&ls.large_ms, ev[2], ev[3]);
+        cudaEventElapsedTime(&ls.scan_ms, ev[3], ev[4]);
+        cudaEventElapsedTime(&ls.emit_ms, ev[4], ev[5]);
+        cudaEventElapsedTime(&ls.total_ms, ev[0], ev[5]);
+        ls.npat = npat;
+        ls.total_pairs = (long long)total_pairs;
+        ls.total_occ = (long long)total_occ;
+        ls.nlarge = (long long)nl;
+    }
     out->npat = npat;
     out->total_pairs = (i64)total_pairs;
     out->total_occurrences = (i64)total_occ;

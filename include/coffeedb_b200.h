@@ -135,8 +135,15 @@ void cdb_spans_free(cdb_spans* s);
 int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t nspans, const void* left, int64_t llen,
                    const void* right, int64_t rlen, void* out, int64_t out_cap);
 
-/* Timing of the last cdb_build*/ /* (milliseconds, CUDA events): total and the radix-sort share. */
+/* Timing of the last build (milliseconds, CUDA events): total and the radix-sort share; refinement rounds
+ * and number of key-range chunks. */
 cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks);
+/* Phase timing of the calling thread's last locate (milliseconds, CUDA events on the launching stream):
+ * ms6 = {search, count, large-interval path, offset scan, emit, total}; counts4 = {npat, pairs, occurrences,
+ * patterns that took the large-interval path}. */
+void cdb_last_locate_stats(double* ms6, int64_t* counts4);
+/* Number of CUDA kernels this library has launched in this process. */
+uint64_t cdb_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,8 @@ def _ref():
         lib.ref_destroy.argtypes = [C.c_void_p]
         lib.ref_add.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
         lib.ref_add_many.argtypes = [C.c_void_p, i64p, C.c_void_p, i64p, C.c_int64]
+        lib.ref_add_many_borrowed.argtypes = [C.c_void_p, i64p, C.c_void_p, i64p, C.c_int64]
+        lib.ref_adopt_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
         lib.ref_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.ref_build.restype = C.c_int
         lib.ref_export_sa.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -254,6 +256,20 @@ class Ref:
         text = np.concatenate([_bytes_arr(text), np.zeros(1, np.uint8)]) if len(text) < (1 << 28) else _bytes_arr(text)
         doc_off = np.ascontiguousarray(doc_off, np.int64)
         self._lib.ref_add_many(self._h, _p(ids, C.c_int64), text.ctypes.data, _p(doc_off, C.c_int64), len(ids))
+
+    def add_many_borrowed(self, ids: np.ndarray, text: np.ndarray, doc_off: np.ndarray):
+        """add() for every document without copying the text (the arrays are kept alive by this object)."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        doc_off = np.ascontiguousarray(doc_off, np.int64)
+        assert text.dtype == np.uint8 and text.flags.c_contiguous
+        self._borrowed = (ids, text, doc_off)
+        self._lib.ref_add_many_borrowed(self._h, _p(ids, C.c_int64), text.ctypes.data, _p(doc_off, C.c_int64), len(ids))
+
+    def adopt_sa(self, sa: np.ndarray, bits1: int):
+        """Makes query() run on a caller-supplied packed suffix array (uint32 or uint64, kept alive here)."""
+        assert sa.dtype in (np.uint32, np.uint64) and sa.flags.c_contiguous
+        self._sa = sa
+        self._lib.ref_adopt_sa(self._h, sa.ctypes.data, sa.dtype.itemsize, bits1, len(sa))
 
     def build(self):
         err = C.create_string_buffer(512)

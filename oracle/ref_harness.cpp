@@ -29,6 +29,13 @@
 
 namespace {
 struct peek_tag {};
+struct adopt_tag {};
+struct adopt_in {
+    void* sa = nullptr;
+    int width = 4;
+    uint64_t bits = 1, size = 0;
+};
+thread_local adopt_in g_adopt;
 struct peek_out {
     int width = 0;
     uint64_t bits = 0, mask = 0, size = 0;
@@ -40,6 +47,7 @@ struct ref_handle {
     string_index idx;
     std::deque<std::string> owned;  // keeps the borrowed string_views alive (database.cpp:263-264)
     bool built = false;
+    bool adopted = false;  // sa points into caller memory: must be detached before ~string_index deletes it
 };
 
 void copy_err(const char* what, char* err, int errlen) {
@@ -63,11 +71,51 @@ void string_index::parallel_sort<peek_tag>() const {
         sa);
 }
 
+// Test-only: makes the reference's query() run on a suffix array supplied by the caller (bench.py injects the
+// array built on the GPU so that the CPU baseline can be timed on the full 10 GB configuration, whose
+// reference build would take tens of minutes).  Sets exactly the members build() sets (src/index.cpp:201-208).
+template <>
+void string_index::parallel_sort<adopt_tag>() const {
+    auto* self = const_cast<string_index*>(this);
+    self->bits = g_adopt.bits;
+    self->mask = (g_adopt.bits >= 64) ? ~0ull : ((1ull << g_adopt.bits) - 1);
+    self->size = g_adopt.size;
+    if (g_adopt.width == 4)
+        self->sa = static_cast<uint32_t*>(g_adopt.sa);
+    else
+        self->sa = static_cast<uint64_t*>(g_adopt.sa);
+}
+
 extern "C" {
 
 void* ref_create() { return new ref_handle(); }
 
-void ref_destroy(void* h) { delete static_cast<ref_handle*>(h); }
+void ref_destroy(void* h) {
+    auto* r = static_cast<ref_handle*>(h);
+    if (r && r->adopted) {
+        g_adopt = adopt_in{};
+        r->idx.parallel_sort<adopt_tag>();  // sa = nullptr: the destructor's delete[] becomes a no-op
+    }
+    delete r;
+}
+
+// add() without the owning copy: the views point into caller memory, exactly as the reference's own loader
+// hands views into ::data (database.cpp:263-264).  The caller keeps `text` alive.
+void ref_add_many_borrowed(void* h, const int64_t* ids, const char* text, const int64_t* off, int64_t nd) {
+    auto* r = static_cast<ref_handle*>(h);
+    for (int64_t d = 0; d < nd; ++d) r->idx.add(ids[d], std::string_view(text + off[d], (size_t)(off[d + 1] - off[d])));
+}
+
+void ref_adopt_sa(void* h, void* sa, int width, uint64_t bits, uint64_t size) {
+    auto* r = static_cast<ref_handle*>(h);
+    g_adopt.sa = sa;
+    g_adopt.width = width;
+    g_adopt.bits = bits;
+    g_adopt.size = size;
+    r->idx.parallel_sort<adopt_tag>();
+    r->adopted = true;
+    r->built = true;
+}
 
 void ref_add(void* h, int64_t id, const char* ptr, int64_t len) {
     auto* r = static_cast<ref_handle*>(h);
