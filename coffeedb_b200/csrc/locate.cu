@@ -5,11 +5,15 @@
 //                          (same midpoints, same predicates), so the interval is identical even on the
 //                          not-quite-sorted arrays of note N1.  Each probe = SA element -> doc_off pair ->
 //                          16 bytes of text, compared as big-endian integers (== unsigned memcmp).
-//   K5-K7 small path       one warp per pattern with occ <= kSmallCap: coalesced read of the SA interval,
-//                          doc = element & mask, sort in shared memory, run-length, ids[] gather, 16-byte
-//                          (id, count) stores.  Run twice: count rows -> exclusive scan -> emit (exact CSR).
+//   K5-K7 gather_kernel  ONE launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
+//                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, warp-level
+//                          LSD radix sort in shared memory (match_any multi-split, 9-bit digits), run-length,
+//                          then the tile's row count enters a decoupled look-back over per-tile status words,
+//                          which yields the exact CSR row offset without a second pass; finally the ids[] gather
+//                          and 16-byte (id, count) stores.
 //   K5-K7 large path       patterns with longer intervals are expanded into (entry << 32 | doc) keys, sorted by
-//                          the device radix sort (the same engine as the build) and run-length encoded.
+//                          the device radix sort (the same engine as the build) and run-length encoded; their
+//                          row counts are known before gather_kernel runs and take part in its scan.
 // All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
 #include <algorithm>
 
@@ -20,8 +24,11 @@
 
 namespace cdb {
 
-constexpr int kSmallCap = 1024;  // occurrences handled by one warp in shared memory
-constexpr int kSmallWarps = 4;   // warps per CTA in the small path
+constexpr int kWarpCap = 1024;    // occurrences one warp sorts in shared memory
+constexpr int kTileWarps = 8;     // patterns per CTA tile
+constexpr int kMaxDigitBits = 9;  // warp radix sort digit width (512 counters)
+constexpr int kCntWords = (1 << kMaxDigitBits) + ((1 << kMaxDigitBits) >> 5);  // padded against bank conflicts
+constexpr size_t kWarpSmemWords = 2 * kWarpCap + kCntWords;
 
 // ---- K4 ------------------------------------------------------------------------------------------------------
 struct SearchCtx {
@@ -67,19 +74,16 @@ __device__ __forceinline__ int compare_at(const SearchCtx& c, i64 M, const u8* _
 }
 
 template <typename SAT>
-__global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __restrict__ pat,
-                                                     const i64* __restrict__ pat_off, i64 npat,
-                                                     i64* __restrict__ left_out, i64* __restrict__ right_out,
-                                                     int* __restrict__ err) {
-    const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= npat) return;
+__device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restrict__ pat, const i64* __restrict__ pat_off,
+                                          i64 q, i64* __restrict__ left_out, i64* __restrict__ right_out,
+                                          int* __restrict__ err) {
     const i64 ps = pat_off[q];
     const i64 m = pat_off[q + 1] - ps;
     if (m <= 0) {  // src/index.cpp:239-241
         *err = 1;
         left_out[q] = 0;
         right_out[q] = 0;
-        return;
+        return 0;
     }
     const u8* kw = pat + ps;
     u64 p8 = 0;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __re
     if (c.n == 0) {
         left_out[q] = 0;
         right_out[q] = 0;
-        return;
+        return 0;
     }
     // src/index.cpp:262-274
     i64 L = 0, R = c.n - 1;
@@ -112,100 +116,193 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __re
         else
             R = M - 1;
     }
+    const i64 right = L + 1 > left ? L + 1 : left;
     left_out[q] = left;
-    right_out[q] = L + 1 > left ? L + 1 : left;
+    right_out[q] = right;
+    return right - left;
 }
 
-// ---- K5-K7 small path -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_bitonic_sort(u32* s, int N, int lane) {
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (N >> 1); t += 32) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                const bool up = (i & k) == 0;
-                const u32 a = s[i], b = s[l];
-                if ((a > b) == up) {
-                    s[i] = b;
-                    s[l] = a;
-                }
+template <typename SAT>
+__global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __restrict__ pat,
+                                                     const i64* __restrict__ pat_off, i64 npat,
+                                                     i64* __restrict__ left_out, i64* __restrict__ right_out,
+                                                     int* __restrict__ err, u32* __restrict__ large_list,
+                                                     unsigned long long* __restrict__ counters) {
+    const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 occ = 0;
+    if (q < npat) occ = search_one<SAT>(c, pat, pat_off, q, left_out, right_out, err);
+    if (counters == nullptr) return;
+    // classification: long intervals go to the large path; the rest is summed (capacity of the result buffer)
+    if (occ > kWarpCap) {
+        large_list[atomicAdd(counters + 0, 1ull)] = (u32)q;
+        occ = 0;
+    }
+    unsigned long long s = (unsigned long long)occ;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + 1, s);
+}
+
+// ---- K5-K7 fused gather ------------------------------------------------------------------------------------------
+constexpr u64 GS_LOCAL = 1ull << 62;
+constexpr u64 GS_INCL = 2ull << 62;
+constexpr u64 GS_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ int cnt_slot(int b) { return b + (b >> 5); }
+
+// Stable LSD radix sort of `occ` doc indices by one warp, A -> (A|B) ping-pong in shared memory; returns the
+// buffer holding the sorted keys.  Ranking is the match_any multi-split also used by the device-wide sort.
+__device__ __forceinline__ u32* warp_radix_sort(u32* A, u32* B, u32* cnt, int occ, int key_bits, int digit_bits,
+                                                int lane) {
+    const int nb = 1 << digit_bits;
+    const u32 dmask = (u32)nb - 1;
+    const u32 lt = lanemask_lt();
+    const int per = nb >> 5 ? nb >> 5 : 1;  // bins per lane in the scan (nb >= 32 guaranteed by the caller)
+    for (int shift = 0; shift < key_bits; shift += digit_bits) {
+        for (int b = lane; b < nb; b += 32) cnt[cnt_slot(b)] = 0;
+        __syncwarp();
+        for (int i = lane; i < occ; i += 32) atomicAdd(&cnt[cnt_slot((A[i] >> shift) & dmask)], 1u);
+        __syncwarp();
+        // exclusive scan over the bins: lane owns `per` consecutive bins
+        u32 s = 0;
+        const int b0 = lane * per;
+        for (int j = 0; j < per; ++j) {
+            const int slot = cnt_slot(b0 + j);
+            const u32 t = cnt[slot];
+            cnt[slot] = s;
+            s += t;
+        }
+        u32 incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const u32 base = incl - s;
+        for (int j = 0; j < per; ++j) cnt[cnt_slot(b0 + j)] += base;
+        __syncwarp();
+        // stable scatter
+        for (int r = 0; r < occ; r += 32) {
+            const int i = r + lane;
+            const bool valid = i < occ;
+            const u32 key = valid ? A[i] : 0u;
+            const u32 d = valid ? ((key >> shift) & dmask) : 0xffffffffu;
+            const u32 peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            u32 old = 0;
+            if (valid && lane == leader) {
+                const int slot = cnt_slot((int)d);
+                old = cnt[slot];
+                cnt[slot] = old + __popc(peers);
             }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            if (valid) B[old + __popc(peers & lt)] = key;
             __syncwarp();
         }
+        u32* t = A;
+        A = B;
+        B = t;
     }
+    return A;
 }
 
-// Loads the doc indices of SA[left, left+occ) into shared memory and sorts them.  Returns the padded size.
+// One CTA = one tile of kTileWarps consecutive patterns.  dlarge[q] holds the (already known) row count of the
+// patterns that took the large path; their rows are written later by large_emit_kernel at row_off[q].
 template <typename SAT>
-__device__ __forceinline__ void load_and_sort_docs(const SAT* __restrict__ sa, i64 left, int occ, u64 mask, u32* s, int lane) {
-    int N = 32;
-    while (N < occ) N <<= 1;
-    for (int i = lane; i < N; i += 32) s[i] = i < occ ? (u32)((u64)sa[left + i] & mask) : 0xffffffffu;
-    __syncwarp();
-    if (occ > 1) warp_bitonic_sort(s, N, lane);
-}
-
-// EMIT=false: dcount[q] = number of distinct docs, large patterns appended to large_list.
-// EMIT=true : rows written at row_off[q].
-template <typename SAT, bool EMIT>
-__global__ void __launch_bounds__(kSmallWarps * 32) small_path_kernel(const SAT* __restrict__ sa, u64 mask,
-                                                                      const i64* __restrict__ ids,
-                                                                      const i64* __restrict__ left,
-                                                                      const i64* __restrict__ right, i64 npat,
-                                                                      u64* __restrict__ dcount, u32* __restrict__ large_list,
-                                                                      unsigned long long* __restrict__ counters,
-                                                                      const u64* __restrict__ row_off,
-                                                                      i64* __restrict__ pairs) {
+__global__ void __launch_bounds__(kTileWarps * 32) gather_kernel(const SAT* __restrict__ sa, u64 mask, int key_bits,
+                                                                  int digit_bits, const i64* __restrict__ ids,
+                                                                  const i64* __restrict__ left,
+                                                                  const i64* __restrict__ right, i64 npat,
+                                                                  const u64* __restrict__ dlarge, u64* status,
+                                                                  u32* ticket, u64* __restrict__ row_off,
+                                                                  i64* __restrict__ pairs) {
     extern __shared__ u32 smem_u32[];
+    __shared__ u64 s_d[kTileWarps];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32* s = smem_u32 + (size_t)warp * (2 * kSmallCap);
-    u32* hp = s + kSmallCap;
-    const i64 q = (i64)blockIdx.x * kSmallWarps + warp;
-    if (q >= npat) return;
-    const i64 l = left[q];
-    const i64 occ64 = right[q] - l;
-    if (occ64 > kSmallCap) {
-        if (!EMIT && lane == 0) {
-            unsigned long long slot = atomicAdd(counters + 0, 1ull);
-            large_list[slot] = (u32)q;
-            dcount[q] = 0;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const i64 tile = s_tile;
+    const i64 q = tile * kTileWarps + warp;
+    u32* A = smem_u32 + (size_t)warp * kWarpSmemWords;
+    u32* B = A + kWarpCap;
+    u32* cnt = B + kWarpCap;
+    int occ = 0, nheads = 0;
+    u32* sorted = A;
+    u32* hp = B;
+    u64 d = 0;
+    if (q < npat) {
+        const i64 l = left[q];
+        const i64 occ64 = right[q] - l;
+        if (occ64 > kWarpCap) {
+            d = dlarge[q];
+        } else {
+            occ = (int)occ64;
+            for (int i = lane; i < occ; i += 32) A[i] = (u32)((u64)sa[l + i] & mask);
+            __syncwarp();
+            if (occ > 1) sorted = warp_radix_sort(A, B, cnt, occ, key_bits, digit_bits, lane);
+            hp = sorted == A ? B : A;
+            // run heads
+            for (int base = 0; base < occ; base += 32) {
+                const int t = base + lane;
+                const bool head = t < occ && (t == 0 || sorted[t] != sorted[t - 1]);
+                const u32 bal = __ballot_sync(0xffffffffu, head);
+                if (head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u32)t;
+                nheads += __popc(bal);
+            }
+            d = (u64)nheads;
         }
-        return;
     }
-    const int occ = (int)occ64;
-    if (occ == 0) {
-        if (!EMIT && lane == 0) dcount[q] = 0;
-        return;
-    }
-    load_and_sort_docs<SAT>(sa, l, occ, mask, s, lane);
-    // run heads
-    int nheads = 0;
-    for (int base = 0; base < occ; base += 32) {
-        const int t = base + lane;
-        const bool head = t < occ && (t == 0 || s[t] != s[t - 1]);
-        const u32 bal = __ballot_sync(0xffffffffu, head);
-        if (EMIT && head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u32)t;
-        nheads += __popc(bal);
-    }
-    if (!EMIT) {
+    if (lane == 0) s_d[warp] = d;
+    __syncthreads();
+    // tile aggregate -> decoupled look-back (warp 0, 32 predecessor tiles per round)
+    if (warp == 0) {
+        u64 agg = 0;
+#pragma unroll
+        for (int w = 0; w < kTileWarps; ++w) agg += s_d[w];
+        if (lane == 0) st_relaxed_u64(status + tile, (tile == 0 ? GS_INCL : GS_LOCAL) | agg);
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 t = tile - 1;
+            for (;;) {
+                const i64 idx = t - lane;
+                u64 v;
+                for (;;) {
+                    v = idx >= 0 ? ld_relaxed_u64(status + idx) : GS_INCL;
+                    if (__all_sync(0xffffffffu, (v >> 62) != 0)) break;
+                }
+                const u32 incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                u64 part = lane <= first ? (v & GS_MASK) : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
+                if (incl_mask) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(status + tile, GS_INCL | (excl + agg));
+        }
         if (lane == 0) {
-            dcount[q] = (u64)nheads;
-            atomicAdd(counters + 1, (unsigned long long)occ);
+            s_prefix = excl;
+            if ((tile + 1) * kTileWarps >= npat) row_off[npat] = excl + agg;
         }
-        return;
     }
-    __syncwarp();
-    const u64 row = row_off[q];
+    __syncthreads();
+    if (q >= npat) return;
+    u64 row = s_prefix;
+    for (int w = 0; w < warp; ++w) row += s_d[w];
+    if (lane == 0) row_off[q] = row;
     for (int r = lane; r < nheads; r += 32) {
         const int start = (int)hp[r];
         const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
-        const i64 id = __ldg(ids + s[start]);
         longlong2 v;
-        v.x = id;
+        v.x = __ldg(ids + sorted[start]);
         v.y = (i64)(end - start);
         *reinterpret_cast<longlong2*>(pairs + 2 * (row + r)) = v;
     }
 }
+
 
 // ---- K5-K7 large path -------------------------------------------------------------------------------------------
 __global__ void large_occ_kernel(const u32* __restrict__ list, u64 nl, const i64* __restrict__ left,
@@ -281,11 +378,15 @@ template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
                          cdb_device_result* out) {
     const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
+    const i64 ntiles = ceil_div(npat, kTileWarps);
     DevBuf<i64> left(npat, st), right(npat, st);
-    DevBuf<u64> dcount(npat + 1, st);      // becomes row_off after the in-place scan
-    DevBuf<unsigned long long> counters(4, st);  // [0] large patterns, [1] occurrences (small path), [2] err
+    DevBuf<u64> row_off(npat + 1, st);
+    DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
+    DevBuf<unsigned long long> counters(4, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] ticket
     DevBuf<u32> large_list(npat, st);
+    DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+    CDB_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), st));
     cudaEvent_t ev[6];
     for (auto& e : ev) CDB_CUDA(cudaEventCreate(&e));
     struct EvGuard {
@@ -297,26 +398,22 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaEventRecord(ev[0], st));
     SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
     int* err = reinterpret_cast<int*>(counters.p + 2);
-    search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, d_pat, d_pat_off, npat, left.p, right.p, err);
+    search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, d_pat, d_pat_off, npat, left.p, right.p, err,
+                                                                      large_list.p, counters.p);
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[1], st));
-    const size_t small_smem = (size_t)kSmallWarps * 2 * kSmallCap * sizeof(u32);
-    static_assert(kSmallWarps * 2 * kSmallCap * sizeof(u32) <= 48 * 1024, "small path uses static-limit shared memory");
-    const unsigned small_grid = (unsigned)ceil_div(npat, kSmallWarps);
-    small_path_kernel<SAT, false><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
-        sa, ix.mask, ix.d_ids, left.p, right.p, npat, dcount.p, large_list.p, counters.p, nullptr, nullptr);
-    CDB_LAUNCH_CHECK();
-    CDB_CUDA(cudaEventRecord(ev[2], st));
     unsigned long long hc[4];
     CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
     if ((int)(hc[2] & 0xffffffffu)) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
     const u64 nl = hc[0];
     u64 total_occ = hc[1];
-    // large path, phase 1
-    DevBuf<u64> ooff, lkeys, ukey, ustart, entry_first;
+    CDB_CUDA(cudaEventRecord(ev[2], st));
+    // large path, phase 1: exact row counts of the long intervals
+    DevBuf<u64> ooff, ukey, ustart, entry_first;
     u64 ltotal = 0, nu = 0;
     if (nl > 0) {
+        dlarge.alloc(npat, st);
         ooff.alloc(nl + 1, st);
         large_occ_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, left.p, right.p, ooff.p);
         CDB_LAUNCH_CHECK();
@@ -330,7 +427,6 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
         int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, ltotal, 0, 32 + bits_for_u64(nl - 1), st);
         u64* sorted = cbuf ? k1.p : k0.p;
-        u64* scratch = cbuf ? k0.p : k1.p;  // re-used for the positions of the unique keys
         DevBuf<u8> flags(ltotal, st);
         large_flag_kernel<<<grid, 256, 0, st>>>(sorted, ltotal, flags.p);
         CDB_LAUNCH_CHECK();
@@ -338,42 +434,47 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         prim::exclusive_scan<u8>(flags.p, pos.p, ltotal, st);
         CDB_CUDA(cudaMemcpyAsync(&nu, pos.p + ltotal, 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaStreamSynchronize(st));
-        (void)scratch;
         ukey.alloc(nu, st);
         ustart.alloc(nu, st);
         entry_first.alloc(nl + 1, st);
         large_unique_kernel<<<grid, 256, 0, st>>>(sorted, flags.p, pos.p, ltotal, ukey.p, ustart.p, entry_first.p);
         CDB_LAUNCH_CHECK();
         CDB_CUDA(cudaMemcpyAsync(entry_first.p + nl, pos.p + ltotal, 8, cudaMemcpyDeviceToDevice, st));
-        large_dcount_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, entry_first.p, dcount.p);
+        large_dcount_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, entry_first.p, dlarge.p);
         CDB_LAUNCH_CHECK();
     }
-    // exact CSR offsets
     CDB_CUDA(cudaEventRecord(ev[3], st));
-    prim::exclusive_scan<u64>(dcount.p, dcount.p, (u64)npat, st);
-    u64 total_pairs = 0;
-    CDB_CUDA(cudaMemcpyAsync(&total_pairs, dcount.p + npat, 8, cudaMemcpyDeviceToHost, st));
-    CDB_CUDA(cudaStreamSynchronize(st));
-    DevBuf<i64> pairs((size_t)total_pairs * 2, st);
-    CDB_CUDA(cudaEventRecord(ev[4], st));
-    small_path_kernel<SAT, true><<<small_grid, kSmallWarps * 32, small_smem, st>>>(
-        sa, ix.mask, ix.d_ids, left.p, right.p, npat, nullptr, nullptr, nullptr, dcount.p, pairs.p);
+    // fused gather: rows <= occurrences on the warp path + exact rows of the large path
+    const u64 cap_pairs = hc[1] + nu;
+    DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
+    int npass = (ix.bits1 + kMaxDigitBits - 1) / kMaxDigitBits;
+    int digit_bits = (ix.bits1 + npass - 1) / npass;
+    if (digit_bits < 5) digit_bits = 5;  // at least one bin per lane in the warp scan
+    const size_t smem = (size_t)kTileWarps * kWarpSmemWords * sizeof(u32);
+    CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, npass * digit_bits, digit_bits, ix.d_ids,
+                                                                       left.p, right.p, npat, dlarge.p, status.p,
+                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
+                                                                       pairs.p);
     CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaEventRecord(ev[4], st));
     if (nl > 0 && nu > 0) {
         const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
-        large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, dcount.p,
+        large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, row_off.p,
                                                 ix.d_ids, pairs.p);
         CDB_LAUNCH_CHECK();
     }
+    u64 total_pairs = 0;
+    CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(ev[5], st));
     CDB_CUDA(cudaStreamSynchronize(st));
     {
         LocateStats& ls = g_locate_stats;
         cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);
-        cudaEventElapsedTime(&ls.count_ms, ev[1], ev[2]);
+        ls.count_ms = 0;
         cudaEventElapsedTime(&ls.large_ms, ev[2], ev[3]);
-        cudaEventElapsedTime(&ls.scan_ms, ev[3], ev[4]);
-        cudaEventElapsedTime(&ls.emit_ms, ev[4], ev[5]);
+        cudaEventElapsedTime(&ls.scan_ms, ev[4], ev[5]);  // large-path emit + final read-back
+        cudaEventElapsedTime(&ls.emit_ms, ev[3], ev[4]);  // gather_kernel
         cudaEventElapsedTime(&ls.total_ms, ev[0], ev[5]);
         ls.npat = npat;
         ls.total_pairs = (long long)total_pairs;
@@ -383,12 +484,13 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     out->npat = npat;
     out->total_pairs = (i64)total_pairs;
     out->total_occurrences = (i64)total_occ;
-    out->row_off = reinterpret_cast<i64*>(dcount.detach());
+    out->row_off = reinterpret_cast<i64*>(row_off.detach());
     out->pairs = pairs.detach();
     out->left = left.detach();
     out->right = right.detach();
     out->_owner = (void*)st;
 }
+
 
 // ---- K8 highlight spans ----------------------------------------------------------------------------------------
 // Replaces the occurrence enumeration of ac_automaton::render (src/database.cpp:58-77): every occurrence of every
@@ -500,7 +602,7 @@ static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nk
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, 16, st));
     SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
     search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, d_kw.p, d_koff.p, nkw, left.p, right.p,
-                                                                      reinterpret_cast<int*>(counters.p + 1));
+                                                                      reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr);
     CDB_LAUNCH_CHECK();
     DevBuf<u64> ooff((size_t)nkw + 1, st);
     span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
