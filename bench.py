@@ -109,7 +109,7 @@ class DevArray:
 
 def make_patterns(w):
     from tests import corpora
-    return corpora.uniform_patterns(w["npat"], w["m"], seed=1000 + w["seed"])
+    return corpora.uniform_patterns(w["npat"], w["m"], seed=1000 + w["seed"], hi=ord("a") + w.get("sigma", 26) - 1)
 
 
 def make_shard(w, rank: int, world: int, device):
@@ -127,7 +127,8 @@ def make_shard(w, rank: int, world: int, device):
         g = torch.Generator(device=device)
         g.manual_seed(w["seed"] * 1000 + b)
         lo = (b - b0) * per * L
-        text[lo:lo + per * L] = torch.randint(97, 123, (per * L,), dtype=torch.uint8, device=device, generator=g)
+        text[lo:lo + per * L] = torch.randint(97, 97 + w.get("sigma", 26), (per * L,), dtype=torch.uint8, device=device,
+                                                   generator=g)
     doc_off = torch.arange(snd + 1, dtype=torch.int64, device=device) * L
     gdoc = torch.arange(b0 * per, b0 * per + snd, dtype=torch.int64, device=device)
     ids = (gdoc * 2654435761) % (1 << 40) + 10 ** 12  # unique, not in doc order
@@ -268,6 +269,9 @@ def run_ours(args):
     w = dict(WORKLOADS[wname])
     if args.npat:
         w["npat"] = args.npat
+    if args.sigma != 26:  # profiling aid only: smaller alphabet = longer intervals at a smaller corpus
+        w["sigma"] = args.sigma
+        wname += f"-sigma{args.sigma}"
     hbm_peak, peak_src = peaks()
 
     # ---- corpus shard + index build (setup; build throughput is reported, not part of the locate step)
@@ -466,6 +470,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--npat", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

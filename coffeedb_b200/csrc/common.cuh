@@ -108,6 +108,8 @@ __device__ __forceinline__ u32 ld_stream_u32(const u32* p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ u64 ld_stream(const u64* p) { return ld_stream_u64(p); }
+__device__ __forceinline__ u32 ld_stream(const u32* p) { return ld_stream_u32(p); }
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -6,8 +6,8 @@
 //                          not-quite-sorted arrays of note N1.  Each probe = SA element -> doc_off pair ->
 //                          16 bytes of text, compared as big-endian integers (== unsigned memcmp).
 //   K5-K7 gather_kernel  ONE launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
-//                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, warp-level
-//                          LSD radix sort in shared memory (match_any multi-split, 9-bit digits), run-length,
+//                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, bitonic
+//                          sorting network in registers (up to 32 keys per lane, SHFL for the lane strides), run-length,
 //                          then the tile's row count enters a decoupled look-back over per-tile status words,
 //                          which yields the exact CSR row offset without a second pass; finally the ids[] gather
 //                          and 16-byte (id, count) stores.
@@ -26,9 +26,7 @@ namespace cdb {
 
 constexpr int kWarpCap = 1024;    // occurrences one warp sorts in shared memory
 constexpr int kTileWarps = 8;     // patterns per CTA tile
-constexpr int kMaxDigitBits = 9;  // warp radix sort digit width (512 counters)
-constexpr int kCntWords = (1 << kMaxDigitBits) + ((1 << kMaxDigitBits) >> 5);  // padded against bank conflicts
-constexpr size_t kWarpSmemWords = 2 * kWarpCap + kCntWords;
+constexpr int kMlp = 4;  // independent global loads kept in flight per lane in the gather loops
 
 // ---- K4 ------------------------------------------------------------------------------------------------------
 struct SearchCtx {
@@ -148,75 +146,80 @@ constexpr u64 GS_LOCAL = 1ull << 62;
 constexpr u64 GS_INCL = 2ull << 62;
 constexpr u64 GS_MASK = (1ull << 62) - 1;
 
-__device__ __forceinline__ int cnt_slot(int b) { return b + (b >> 5); }
-
-// Stable LSD radix sort of `occ` doc indices by one warp, A -> (A|B) ping-pong in shared memory; returns the
-// buffer holding the sorted keys.  Ranking is the match_any multi-split also used by the device-wide sort.
-__device__ __forceinline__ u32* warp_radix_sort(u32* A, u32* B, u32* cnt, int occ, int key_bits, int digit_bits,
-                                                int lane) {
-    const int nb = 1 << digit_bits;
-    const u32 dmask = (u32)nb - 1;
-    const u32 lt = lanemask_lt();
-    const int per = nb >> 5 ? nb >> 5 : 1;  // bins per lane in the scan (nb >= 32 guaranteed by the caller)
-    for (int shift = 0; shift < key_bits; shift += digit_bits) {
-        for (int b = lane; b < nb; b += 32) cnt[cnt_slot(b)] = 0;
-        __syncwarp();
-        for (int i = lane; i < occ; i += 32) atomicAdd(&cnt[cnt_slot((A[i] >> shift) & dmask)], 1u);
-        __syncwarp();
-        // exclusive scan over the bins: lane owns `per` consecutive bins
-        u32 s = 0;
-        const int b0 = lane * per;
-        for (int j = 0; j < per; ++j) {
-            const int slot = cnt_slot(b0 + j);
-            const u32 t = cnt[slot];
-            cnt[slot] = s;
-            s += t;
-        }
-        u32 incl = s;
+// Bitonic sorting network over 32*R keys held in registers, R per lane, lane-blocked index i = lane*R + r.
+// Strides below R are register-to-register compare-exchanges (2 IMNMX), strides >= R are one SHFL + one IMNMX
+// per key; no shared memory, no divergence.  (MATCH.ANY-based multi-split radix sorting was measured first and
+// is XU-pipe bound on B200: profiles/README.md.)
+template <int R>
+__device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane) {
+    constexpr int N = 32 * R;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const u32 base = incl - s;
-        for (int j = 0; j < per; ++j) cnt[cnt_slot(b0 + j)] += base;
-        __syncwarp();
-        // stable scatter
-        for (int r = 0; r < occ; r += 32) {
-            const int i = r + lane;
-            const bool valid = i < occ;
-            const u32 key = valid ? A[i] : 0u;
-            const u32 d = valid ? ((key >> shift) & dmask) : 0xffffffffu;
-            const u32 peers = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs(peers) - 1;
-            u32 old = 0;
-            if (valid && lane == leader) {
-                const int slot = cnt_slot((int)d);
-                old = cnt[slot];
-                cnt[slot] = old + __popc(peers);
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= R) {
+                const int lj = j / R;
+                const bool asc = (k >= N) ? true : ((lane & (k / R)) == 0);
+                const bool keep_min = (((lane & lj) == 0) == asc);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const u32 o = __shfl_xor_sync(0xffffffffu, x[r], lj);
+                    x[r] = keep_min ? min(x[r], o) : max(x[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & j) == 0) {
+                        const bool asc = (k < R) ? ((r & k) == 0) : ((k >= N) ? true : ((lane & (k / R)) == 0));
+                        const u32 a = x[r], b = x[r ^ j];
+                        const u32 lo = min(a, b), hi = max(a, b);
+                        x[r] = asc ? lo : hi;
+                        x[r ^ j] = asc ? hi : lo;
+                    }
+                }
             }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            if (valid) B[old + __popc(peers & lt)] = key;
-            __syncwarp();
         }
-        u32* t = A;
-        A = B;
-        B = t;
     }
-    return A;
 }
+
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
+
+// Loads SA[l, l+occ) (coalesced, all R loads of a lane in flight at once), reduces to doc indices, sorts them in
+// registers and leaves them in shared memory at pad_idx(rank).
+template <typename SAT, int R>
+__device__ __forceinline__ void load_sort_store(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32* sorted, int lane) {
+    SAT v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        v[r] = i < occ ? ld_stream(sa + l + i) : (SAT)0;
+    }
+    u32 x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        x[r] = i < occ ? (u32)((u64)v[r] & mask) : 0xffffffffu;  // doc index <= 2^32-2 (bits1 <= 32)
+    }
+    warp_bitonic_regs<R>(x, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) sorted[pad_idx(lane * R + r)] = x[r];
+    __syncwarp();
+}
+
+constexpr int kSortedWords = kWarpCap + kWarpCap / 32;                 // padded keys
+constexpr size_t kWarpSmemBytes = (size_t)kSortedWords * 4 + kWarpCap * 2;  // + u16 run-head positions
 
 // One CTA = one tile of kTileWarps consecutive patterns.  dlarge[q] holds the (already known) row count of the
 // patterns that took the large path; their rows are written later by large_emit_kernel at row_off[q].
 template <typename SAT>
-__global__ void __launch_bounds__(kTileWarps * 32) gather_kernel(const SAT* __restrict__ sa, u64 mask, int key_bits,
-                                                                  int digit_bits, const i64* __restrict__ ids,
-                                                                  const i64* __restrict__ left,
-                                                                  const i64* __restrict__ right, i64 npat,
-                                                                  const u64* __restrict__ dlarge, u64* status,
-                                                                  u32* ticket, u64* __restrict__ row_off,
-                                                                  i64* __restrict__ pairs) {
-    extern __shared__ u32 smem_u32[];
+__global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
+                                                                     const i64* __restrict__ ids,
+                                                                     const i64* __restrict__ left,
+                                                                     const i64* __restrict__ right, i64 npat,
+                                                                     const u64* __restrict__ dlarge, u64* status,
+                                                                     u32* ticket, u64* __restrict__ row_off,
+                                                                     i64* __restrict__ pairs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u64 s_d[kTileWarps];
     __shared__ u64 s_prefix;
     __shared__ u32 s_tile;
@@ -225,30 +228,29 @@ __global__ void __launch_bounds__(kTileWarps * 32) gather_kernel(const SAT* __re
     __syncthreads();
     const i64 tile = s_tile;
     const i64 q = tile * kTileWarps + warp;
-    u32* A = smem_u32 + (size_t)warp * kWarpSmemWords;
-    u32* B = A + kWarpCap;
-    u32* cnt = B + kWarpCap;
+    u32* sorted = reinterpret_cast<u32*>(smem_raw + (size_t)warp * kWarpSmemBytes);
+    u16* hp = reinterpret_cast<u16*>(sorted + kSortedWords);
     int occ = 0, nheads = 0;
-    u32* sorted = A;
-    u32* hp = B;
     u64 d = 0;
     if (q < npat) {
         const i64 l = left[q];
         const i64 occ64 = right[q] - l;
         if (occ64 > kWarpCap) {
             d = dlarge[q];
-        } else {
+        } else if (occ64 > 0) {
             occ = (int)occ64;
-            for (int i = lane; i < occ; i += 32) A[i] = (u32)((u64)sa[l + i] & mask);
-            __syncwarp();
-            if (occ > 1) sorted = warp_radix_sort(A, B, cnt, occ, key_bits, digit_bits, lane);
-            hp = sorted == A ? B : A;
+            if (occ <= 32) load_sort_store<SAT, 1>(sa, l, occ, mask, sorted, lane);
+            else if (occ <= 64) load_sort_store<SAT, 2>(sa, l, occ, mask, sorted, lane);
+            else if (occ <= 128) load_sort_store<SAT, 4>(sa, l, occ, mask, sorted, lane);
+            else if (occ <= 256) load_sort_store<SAT, 8>(sa, l, occ, mask, sorted, lane);
+            else if (occ <= 512) load_sort_store<SAT, 16>(sa, l, occ, mask, sorted, lane);
+            else load_sort_store<SAT, 32>(sa, l, occ, mask, sorted, lane);
             // run heads
             for (int base = 0; base < occ; base += 32) {
                 const int t = base + lane;
-                const bool head = t < occ && (t == 0 || sorted[t] != sorted[t - 1]);
+                const bool head = t < occ && (t == 0 || sorted[pad_idx(t)] != sorted[pad_idx(t - 1)]);
                 const u32 bal = __ballot_sync(0xffffffffu, head);
-                if (head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u32)t;
+                if (head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u16)t;
                 nheads += __popc(bal);
             }
             d = (u64)nheads;
@@ -293,16 +295,26 @@ __global__ void __launch_bounds__(kTileWarps * 32) gather_kernel(const SAT* __re
     u64 row = s_prefix;
     for (int w = 0; w < warp; ++w) row += s_d[w];
     if (lane == 0) row_off[q] = row;
-    for (int r = lane; r < nheads; r += 32) {
-        const int start = (int)hp[r];
-        const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
-        longlong2 v;
-        v.x = __ldg(ids + sorted[start]);
-        v.y = (i64)(end - start);
-        *reinterpret_cast<longlong2*>(pairs + 2 * (row + r)) = v;
+    // ids[] gather (random 8-byte reads): kMlp independent loads in flight per lane, then 16-byte stores
+    for (int r0 = 0; r0 < nheads; r0 += 32 * kMlp) {
+        longlong2 v[kMlp];
+#pragma unroll
+        for (int u = 0; u < kMlp; ++u) {
+            const int r = r0 + u * 32 + lane;
+            if (r < nheads) {
+                const int start = (int)hp[r];
+                const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
+                v[u].x = __ldg(ids + sorted[pad_idx(start)]);
+                v[u].y = (i64)(end - start);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kMlp; ++u) {
+            const int r = r0 + u * 32 + lane;
+            if (r < nheads) *reinterpret_cast<longlong2*>(pairs + 2 * (row + r)) = v[u];
+        }
     }
 }
-
 
 // ---- K5-K7 large path -------------------------------------------------------------------------------------------
 __global__ void large_occ_kernel(const u32* __restrict__ list, u64 nl, const i64* __restrict__ left,
@@ -447,15 +459,11 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     // fused gather: rows <= occurrences on the warp path + exact rows of the large path
     const u64 cap_pairs = hc[1] + nu;
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
-    int npass = (ix.bits1 + kMaxDigitBits - 1) / kMaxDigitBits;
-    int digit_bits = (ix.bits1 + npass - 1) / npass;
-    if (digit_bits < 5) digit_bits = 5;  // at least one bin per lane in the warp scan
-    const size_t smem = (size_t)kTileWarps * kWarpSmemWords * sizeof(u32);
+    const size_t smem = (size_t)kTileWarps * kWarpSmemBytes;
     CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, npass * digit_bits, digit_bits, ix.d_ids,
-                                                                       left.p, right.p, npat, dlarge.p, status.p,
-                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
-                                                                       pairs.p);
+    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, ix.d_ids, left.p, right.p, npat, dlarge.p,
+                                                                       status.p, reinterpret_cast<u32*>(counters.p + 3),
+                                                                       row_off.p, pairs.p);
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[4], st));
     if (nl > 0 && nu > 0) {
