@@ -1,0 +1,47 @@
+"""The C++ adaptor over the C ABI (coffeedb_b200/host/string_index.hpp): compiles against the stand-alone base
+and — where the reference tree is present — against the reference's own abstract `index` (src/index.h:9-23),
+which is the drop-in arrangement INTEGRATION.md describes."""
+import os
+import subprocess
+
+import pytest
+
+import coffeedb_b200 as cdb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "test_adaptor.cpp")
+OUT = os.path.join(ROOT, "tests", "host", "_build")
+REF_INDEX_H = "/root/reference/src/index.h"
+
+
+def compile_adaptor(name, extra=()):
+    os.makedirs(OUT, exist_ok=True)
+    cdb.lib()  # fails loudly when the library has not been built
+    exe = os.path.join(OUT, name)
+    libdir = os.path.dirname(cdb.LIB_PATH)
+    cmd = ["g++", "-std=c++20", "-O1", "-w", *extra, SRC, "-o", exe, f"-L{libdir}", "-lcoffeedb_b200",
+           f"-Wl,-rpath,{libdir}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_adaptor_links_and_fails_loudly_without_device():
+    exe = compile_adaptor("test_adaptor")
+    r = subprocess.run([exe, "nogpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "adaptor nogpu ok" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(REF_INDEX_H), reason="reference tree absent (GPU box)")
+def test_adaptor_derives_from_reference_index_class():
+    exe = compile_adaptor("test_adaptor_refbase", [f'-DCDB_TEST_REFERENCE_BASE="{REF_INDEX_H}"'])
+    r = subprocess.run([exe, "nogpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_adaptor_on_device():
+    exe = compile_adaptor("test_adaptor")
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "adaptor gpu ok" in r.stdout
