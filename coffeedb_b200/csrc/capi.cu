@@ -23,6 +23,9 @@ void Index::free_device() {
     if (own_text) cudaFree(own_text);
     if (own_off) cudaFree(own_off);
     if (own_ids) cudaFree(own_ids);
+    if (d_ptab) cudaFree(d_ptab);
+    d_ptab = nullptr;
+    pt_k = pt_b = 0;
     d_sa = own_text = own_off = own_ids = nullptr;
     d_text = nullptr;
     d_off = nullptr;
@@ -98,6 +101,8 @@ static void keep_pool_memory(int dev) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    // experiment knob: L2 -> DRAM fetch granularity hint (bytes; 32/64/128) for the random-probe kernels
+    if (const char* e = getenv("CDB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
 }
 
 }  // namespace cdb

@@ -117,6 +117,30 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
                  : "l"(p));
     return v;
 }
+// L2 eviction-priority policies (createpolicy) and loads/stores that carry one: translate_kernel keeps the slice of
+// ids[] it is working on resident (evict_last) while rows stream through (evict_first).
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 ld_hint_u64(const u64* p, u64 policy) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_hint_v2(i64* p, longlong2 v, u64 policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
+}
+// streaming 8-byte store (written once, read by a later kernel)
+__device__ __forceinline__ void st_stream_u64(u64* p, u64 v) {
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // relaxed gpu-scope load/store of one 64-bit word: the decoupled look-back status words
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
     u64 v;

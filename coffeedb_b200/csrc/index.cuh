@@ -15,6 +15,12 @@ namespace cdb {
 
 constexpr i64 kTextPad = 64;  // bytes of zero padding after the text (16-byte window loads never fault)
 
+// Byte -> symbol re-coding of one corpus: 0 is reserved for end-of-document, the bytes that occur map to
+// 1..sigma in unsigned byte order (so symbol order == memcmp order, with "end" first as in src/index.h:66-73).
+struct SymTab {
+    u16 sym[256];
+};
+
 struct Index {
     cdb_options opt{};
     int device = 0;
@@ -36,6 +42,13 @@ struct Index {
     bool built = false;
     bool mixed = false;  // text holds bytes on both sides of 0x80 (note N1 applies when n > 4096)
     i64 chuck_size = 0;  // max(4096, n/256), src/index.cpp:218
+    // Prefix directory over the first pt_k symbols (pt_b bits each): ptab[c] = number of suffixes whose pt_k-symbol
+    // code is < c, for c = 0 .. 2^(pt_b*pt_k).  Resolves the SA interval of short patterns with two lookups and
+    // narrows the binary search of longer ones.  Only built when the array is sorted under one comparator
+    // (i.e. not in the note-N1 layout), see build_prefix_table().
+    SymTab symtab{};
+    int sigma = 0, pt_b = 0, pt_k = 0;
+    u64* d_ptab = nullptr;
     // build statistics
     double build_ms = 0, sort_ms = 0;
     i64 rounds = 0, chunks = 0;
@@ -45,5 +58,7 @@ struct Index {
 };
 
 void build_index(Index& ix, cudaStream_t st);
+// locate.cu: fills ix.d_ptab (after the suffix array is complete)
+void build_prefix_table(Index& ix, cudaStream_t st);
 
 }  // namespace cdb

@@ -16,6 +16,7 @@
 //                          row counts are known before gather_kernel runs and take part in its scan.
 // All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
 #include <algorithm>
+#include <cstdlib>
 
 #include "index.cuh"
 #include "locate.cuh"
@@ -26,7 +27,6 @@ namespace cdb {
 
 constexpr int kWarpCap = 1024;    // occurrences one warp sorts in shared memory
 constexpr int kTileWarps = 8;     // patterns per CTA tile
-constexpr int kMlp = 4;  // independent global loads kept in flight per lane in the gather loops
 
 // ---- K4 ------------------------------------------------------------------------------------------------------
 struct SearchCtx {
@@ -36,7 +36,13 @@ struct SearchCtx {
     u64 mask;
     const i64* doc_off;
     const u8* text;
+    const u64* ptab;  // prefix directory (Index::d_ptab) or nullptr
+    int pt_b, pt_k;
 };
+
+static SearchCtx make_ctx(const Index& ix) {
+    return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k};
+}
 
 // three-way comparison of keyword vs the suffix stored at SA rank M:
 //   -1: keyword <  suffix            0: keyword is a prefix of suffix (keyword <= suffix, starts_with)
@@ -74,7 +80,7 @@ __device__ __forceinline__ int compare_at(const SearchCtx& c, i64 M, const u8* _
 template <typename SAT>
 __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restrict__ pat, const i64* __restrict__ pat_off,
                                           i64 q, i64* __restrict__ left_out, i64* __restrict__ right_out,
-                                          int* __restrict__ err) {
+                                          int* __restrict__ err, const u16* s_tab) {
     const i64 ps = pat_off[q];
     const i64 m = pat_off[q + 1] - ps;
     if (m <= 0) {  // src/index.cpp:239-241
@@ -93,6 +99,49 @@ __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restri
         left_out[q] = 0;
         right_out[q] = 0;
         return 0;
+    }
+    if (c.ptab) {
+        // Sorted array (one comparator): the directory gives the interval of the first min(m, k) symbols with two
+        // lookups; longer keywords refine inside it with plain lower/upper bounds.  Same interval as the
+        // reference's recurrences whenever the array is sorted, which is the only case the directory exists in.
+        const int k = c.pt_k, b = c.pt_b;
+        const int kk = m < (i64)k ? (int)m : k;
+        u64 code = 0;
+        bool absent = false;
+        for (int i = 0; i < kk; ++i) {
+            const u32 sym = s_tab[kw[i]];
+            absent |= sym == 0;
+            code = (code << b) | sym;
+        }
+        i64 lo = 0, hi = 0;
+        if (!absent) {
+            const int sh = b * (k - kk);
+            lo = (i64)__ldg(c.ptab + (code << sh));
+            hi = (i64)__ldg(c.ptab + ((code + 1) << sh));
+            if (m > (i64)k && lo < hi) {
+                i64 L = lo, R = hi;
+                while (L < R) {
+                    const i64 M = L + (R - L) / 2;
+                    if (compare_at<SAT>(c, M, kw, m, p8) <= 0)
+                        R = M;
+                    else
+                        L = M + 1;
+                }
+                lo = L;
+                R = hi;
+                while (L < R) {
+                    const i64 M = L + (R - L) / 2;
+                    if (compare_at<SAT>(c, M, kw, m, p8) == 0)
+                        L = M + 1;
+                    else
+                        R = M;
+                }
+                hi = L;
+            }
+        }
+        left_out[q] = lo;
+        right_out[q] = hi;
+        return hi - lo;
     }
     // src/index.cpp:262-274
     i64 L = 0, R = c.n - 1;
@@ -121,14 +170,17 @@ __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restri
 }
 
 template <typename SAT>
-__global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __restrict__ pat,
+__global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, const u8* __restrict__ pat,
                                                      const i64* __restrict__ pat_off, i64 npat,
                                                      i64* __restrict__ left_out, i64* __restrict__ right_out,
                                                      int* __restrict__ err, u32* __restrict__ large_list,
                                                      unsigned long long* __restrict__ counters) {
+    __shared__ u16 s_tab[256];
+    s_tab[threadIdx.x] = tab.sym[threadIdx.x];
+    __syncthreads();
     const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 occ = 0;
-    if (q < npat) occ = search_one<SAT>(c, pat, pat_off, q, left_out, right_out, err);
+    if (q < npat) occ = search_one<SAT>(c, pat, pat_off, q, left_out, right_out, err, s_tab);
     if (counters == nullptr) return;
     // classification: long intervals go to the large path; the rest is summed (capacity of the result buffer)
     if (occ > kWarpCap) {
@@ -141,26 +193,118 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, const u8* __re
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + 1, s);
 }
 
-// ---- K5-K7 fused gather ------------------------------------------------------------------------------------------
+// ---- prefix directory ------------------------------------------------------------------------------------------
+// ptab[c] = first SA rank whose k-symbol code (end-of-document = 0 padding) is >= c; one thread per entry runs a
+// lower bound over the finished array.  Neighbouring entries follow almost the same path, so the probes hit L1/L2.
+template <typename SAT>
+__global__ void __launch_bounds__(256) ptab_kernel(SearchCtx c, SymTab tab, int b, int k, u64 nentries, u64* __restrict__ ptab) {
+    __shared__ u16 s_tab[256];
+    s_tab[threadIdx.x] = tab.sym[threadIdx.x];
+    __syncthreads();
+    const u64 code = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (code > nentries) return;
+    if (code == nentries) {
+        ptab[code] = (u64)c.n;
+        return;
+    }
+    i64 L = 0, R = c.n;
+    while (L < R) {
+        const i64 M = L + (R - L) / 2;
+        const u64 e = (u64) reinterpret_cast<const SAT*>(c.sa)[M];
+        const i64 doc = (i64)(e & c.mask);
+        const i64 s = __ldg(c.doc_off + doc) + (i64)(e >> c.bits1);
+        const i64 slen = __ldg(c.doc_off + doc + 1) - s;
+        const u64 t = load_be64(c.text, s);
+        u64 sc = 0;
+        for (int j = 0; j < k; ++j) sc = (sc << b) | (u64)((i64)j < slen ? s_tab[(t >> (56 - 8 * j)) & 255] : 0);
+        if (sc >= code)
+            R = M;
+        else
+            L = M + 1;
+    }
+    ptab[code] = (u64)L;
+}
+
+void build_prefix_table(Index& ix, cudaStream_t st) {
+    if (ix.d_ptab) cudaFree(ix.d_ptab);
+    ix.d_ptab = nullptr;
+    ix.pt_k = ix.pt_b = 0;
+    // note N1: on corpora mixing bytes < 0x80 and >= 0x80 the compat layout is not sorted under the comparator the
+    // search uses, and the reference's exact recurrences must run on it
+    if (ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size) return;
+    if (ix.n < 64 || ix.sigma == 0) return;
+    int budget = 0;
+    while (budget < 26 && ((i64)8 << (budget + 1)) <= ix.n) ++budget;  // <= n/8 entries, <= 512 MB
+    if (const char* e = getenv("CDB_PTAB_BITS")) budget = atoi(e);
+    int b = 1;
+    while ((1 << b) <= ix.sigma) ++b;  // symbols 0..sigma
+    int k = budget / b;
+    if (k > 8) k = 8;  // one 8-byte text window per probe
+    if (k < 1) return;
+    const u64 nentries = 1ull << (b * k);
+    CDB_CUDA(cudaMalloc(&ix.d_ptab, (nentries + 1) * 8));
+    SearchCtx c = make_ctx(ix);
+    c.ptab = nullptr;
+    const unsigned grid = (unsigned)ceil_div((i64)nentries + 1, 256);
+    if (ix.width == 4)
+        ptab_kernel<u32><<<grid, 256, 0, st>>>(c, ix.symtab, b, k, nentries, ix.d_ptab);
+    else
+        ptab_kernel<u64><<<grid, 256, 0, st>>>(c, ix.symtab, b, k, nentries, ix.d_ptab);
+    CDB_LAUNCH_CHECK();
+    ix.pt_b = b;
+    ix.pt_k = k;
+}
+
+// ---- K5-K7 gather (phase A) + translate (phase B) ---------------------------------------------------------------
 constexpr u64 GS_LOCAL = 1ull << 62;
 constexpr u64 GS_INCL = 2ull << 62;
 constexpr u64 GS_MASK = (1ull << 62) - 1;
+constexpr int kMaxRanges = 64;   // doc-range partitions of ids[] used by translate_kernel (each <= ~32 MB of ids)
 
-// Bitonic sorting network over 32*R keys held in registers, R per lane, lane-blocked index i = lane*R + r.
-// Strides below R are register-to-register compare-exchanges (2 IMNMX), strides >= R are one SHFL + one IMNMX
-// per key; no shared memory, no divergence.  (MATCH.ANY-based multi-split radix sorting was measured first and
-// is XU-pipe bound on B200: profiles/README.md.)
+// Bitonic sorting network over 32*R keys held in registers, R per lane, lane-blocked index i = lane*R + r, in the
+// all-ascending "flip + disperse" form: every compare-exchange puts the minimum at the lower index, so strides
+// below R are two VIMNMX per pair with no direction select, strides >= R are one SHFL + a min/max chosen by a lane
+// predicate per key.  No shared memory, no divergence.  (MATCH.ANY-based multi-split radix sorting was measured
+// first and is XU-pipe bound on B200: profiles/README.md.)
 template <int R>
 __device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane) {
     constexpr int N = 32 * R;
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int h = 2; h <= N; h <<= 1) {
+        // flip: i <-> i ^ (h-1)
+        if (h <= R) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int r = 0; r < R; ++r) {
+                const int p = r ^ (h - 1);
+                if (r < p) {
+                    const u32 a = x[r], b = x[p];
+                    x[r] = min(a, b);
+                    x[p] = max(a, b);
+                }
+            }
+        } else {
+            const int lm = h / R - 1;
+            const bool keep_min = (lane & (h / (2 * R))) == 0;
+            if (R == 1) {
+                const u32 o = __shfl_xor_sync(0xffffffffu, x[0], lm);
+                x[0] = keep_min ? min(x[0], o) : max(x[0], o);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const u32 a = x[r], b = x[R - 1 - r];
+                    const u32 oa = __shfl_xor_sync(0xffffffffu, b, lm);
+                    const u32 ob = __shfl_xor_sync(0xffffffffu, a, lm);
+                    x[r] = keep_min ? min(a, oa) : max(a, oa);
+                    x[R - 1 - r] = keep_min ? min(b, ob) : max(b, ob);
+                }
+            }
+        }
+        // disperse: i <-> i ^ j for j = h/4 ... 1
+#pragma unroll
+        for (int j = h >> 2; j > 0; j >>= 1) {
             if (j >= R) {
                 const int lj = j / R;
-                const bool asc = (k >= N) ? true : ((lane & (k / R)) == 0);
-                const bool keep_min = (((lane & lj) == 0) == asc);
+                const bool keep_min = (lane & lj) == 0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const u32 o = __shfl_xor_sync(0xffffffffu, x[r], lj);
@@ -170,11 +314,9 @@ __device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if ((r & j) == 0) {
-                        const bool asc = (k < R) ? ((r & k) == 0) : ((k >= N) ? true : ((lane & (k / R)) == 0));
-                        const u32 a = x[r], b = x[r ^ j];
-                        const u32 lo = min(a, b), hi = max(a, b);
-                        x[r] = asc ? lo : hi;
-                        x[r ^ j] = asc ? hi : lo;
+                        const u32 a = x[r], b = x[r | j];
+                        x[r] = min(a, b);
+                        x[r | j] = max(a, b);
                     }
                 }
             }
@@ -209,20 +351,25 @@ __device__ __forceinline__ void load_sort_store(const SAT* __restrict__ sa, i64 
 constexpr int kSortedWords = kWarpCap + kWarpCap / 32;                 // padded keys
 constexpr size_t kWarpSmemBytes = (size_t)kSortedWords * 4 + kWarpCap * 2;  // + u16 run-head positions
 
-// One CTA = one tile of kTileWarps consecutive patterns.  dlarge[q] holds the (already known) row count of the
-// patterns that took the large path; their rows are written later by large_emit_kernel at row_off[q].
+// Phase A.  One CTA = one tile of kTileWarps consecutive patterns, one warp each.  Per pattern: read the SA interval,
+// reduce to doc indices, sort, run-length encode; the tile's row count enters a decoupled look-back over per-tile
+// status words (exact CSR row offsets in the same pass); the row leaves as compact (count << 32 | doc) words plus
+// the row's split points at the doc-range boundaries (seg) that phase B iterates over.  dlarge[q] holds the
+// (already known) row count of the patterns that took the large path; their rows are written by large_emit_kernel.
+//   seg layout: [tile][r = 0..nranges][kTileWarps] u16, seg(q, r) = number of row entries with doc < (r << rshift)
 template <typename SAT>
 __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
-                                                                     const i64* __restrict__ ids,
                                                                      const i64* __restrict__ left,
                                                                      const i64* __restrict__ right, i64 npat,
                                                                      const u64* __restrict__ dlarge, u64* status,
                                                                      u32* ticket, u64* __restrict__ row_off,
-                                                                     i64* __restrict__ pairs) {
+                                                                     u64* __restrict__ cpairs, u16* __restrict__ seg,
+                                                                     int nranges, int rshift) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u64 s_d[kTileWarps];
     __shared__ u64 s_prefix;
     __shared__ u32 s_tile;
+    __shared__ u16 s_seg[(kMaxRanges + 1) * kTileWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -254,10 +401,29 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
                 nheads += __popc(bal);
             }
             d = (u64)nheads;
+            __syncwarp();
         }
+    }
+    // split points of the row at the doc-range boundaries (nheads == 0 for empty / large-path rows -> all zero)
+    for (int r = lane; r <= nranges; r += 32) {
+        const u64 bound = (u64)r << rshift;
+        int lo = 0, hi = nheads;  // first j with doc_j >= bound
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((u64)sorted[pad_idx((int)hp[mid])] < bound)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        s_seg[r * kTileWarps + warp] = (u16)lo;
     }
     if (lane == 0) s_d[warp] = d;
     __syncthreads();
+    {   // the tile's seg block leaves as one contiguous run
+        const int nseg = (nranges + 1) * kTileWarps;
+        u16* g = seg + (size_t)tile * nseg;
+        for (int i = threadIdx.x; i < nseg; i += kTileWarps * 32) g[i] = s_seg[i];
+    }
     // tile aggregate -> decoupled look-back (warp 0, 32 predecessor tiles per round)
     if (warp == 0) {
         u64 agg = 0;
@@ -295,23 +461,84 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
     u64 row = s_prefix;
     for (int w = 0; w < warp; ++w) row += s_d[w];
     if (lane == 0) row_off[q] = row;
-    // ids[] gather (random 8-byte reads): kMlp independent loads in flight per lane, then 16-byte stores
-    for (int r0 = 0; r0 < nheads; r0 += 32 * kMlp) {
-        longlong2 v[kMlp];
-#pragma unroll
-        for (int u = 0; u < kMlp; ++u) {
-            const int r = r0 + u * 32 + lane;
-            if (r < nheads) {
-                const int start = (int)hp[r];
-                const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
-                v[u].x = __ldg(ids + sorted[pad_idx(start)]);
-                v[u].y = (i64)(end - start);
-            }
+    // compact row: (count << 32 | doc), coalesced 8-byte stores
+    for (int r = lane; r < nheads; r += 32) {
+        const int start = (int)hp[r];
+        const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
+        st_stream_u64(cpairs + row + r, ((u64)(u32)(end - start) << 32) | (u64)sorted[pad_idx(start)]);
+    }
+}
+
+// Phase B.  pairs[i] = (ids[doc_i], count_i) for every compact entry i.  ids[] (8 bytes per document, 800 MB at the
+// 10 GB configuration) is read at random, so the work is ordered by doc range: item = (range r, block of 32
+// patterns), all warps of the grid walk the items in order and therefore look up the same <= 32 MB slice of ids[]
+// at the same time, which stays L2-resident (evict_last), while the compact rows and the result stream through
+// (evict_first).  One warp per item; the lanes are spread evenly over the concatenated row segments of the
+// item's 32 patterns (binary search over the segment prefix sums), kTrU independent lookups in flight per lane.
+constexpr int kTrU = 4;
+constexpr int kTrWarps = 8;
+
+__global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __restrict__ cpairs,
+                                                                  const u64* __restrict__ row_off,
+                                                                  const u16* __restrict__ seg,
+                                                                  const i64* __restrict__ ids, i64* __restrict__ pairs,
+                                                                  i64 npat, int nranges) {
+    __shared__ u32 s_excl[kTrWarps][33];
+    __shared__ u64 s_adj[kTrWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 ntile = (npat + 31) >> 5;
+    const i64 nitems = ntile * nranges;
+    const i64 nwarps = (i64)gridDim.x * kTrWarps;
+    const u64 pol_keep = l2_policy_evict_last();
+    const u64 pol_stream = l2_policy_evict_first();
+    for (i64 item = (i64)blockIdx.x * kTrWarps + warp; item < nitems; item += nwarps) {
+        const int r = (int)(item / ntile);
+        const i64 q = (item % ntile) * 32 + lane;
+        u32 len = 0;
+        u64 base = 0;
+        if (q < npat) {
+            const u16* sg = seg + ((size_t)(q / kTileWarps) * (nranges + 1) + r) * kTileWarps + (q % kTileWarps);
+            const u32 s = sg[0], e = sg[kTileWarps];
+            len = e - s;
+            if (len) base = row_off[q] + s;
         }
+        u32 incl = len;
 #pragma unroll
-        for (int u = 0; u < kMlp; ++u) {
-            const int r = r0 + u * 32 + lane;
-            if (r < nheads) *reinterpret_cast<longlong2*>(pairs + 2 * (row + r)) = v[u];
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot == 0) continue;
+        __syncwarp();
+        s_excl[warp][lane] = incl - len;
+        s_adj[warp][lane] = base - (incl - len);
+        __syncwarp();
+        for (u32 i0 = 0; i0 < tot; i0 += 32 * kTrU) {
+            u64 p[kTrU], cp[kTrU];
+            longlong2 v[kTrU];
+#pragma unroll
+            for (int u = 0; u < kTrU; ++u) {
+                const u32 idx = i0 + u * 32 + lane;
+                p[u] = ~0ull;
+                if (idx < tot) {
+                    int j = 0;  // largest j with excl[j] <= idx
+#pragma unroll
+                    for (int st = 16; st; st >>= 1)
+                        if (s_excl[warp][j + st] <= idx) j += st;
+                    p[u] = s_adj[warp][j] + idx;
+                    cp[u] = ld_hint_u64(cpairs + p[u], pol_stream);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kTrU; ++u)
+                if (p[u] != ~0ull) {
+                    v[u].x = (i64)ld_hint_u64(reinterpret_cast<const u64*>(ids) + (u32)cp[u], pol_keep);
+                    v[u].y = (i64)(cp[u] >> 32);
+                }
+#pragma unroll
+            for (int u = 0; u < kTrU; ++u)
+                if (p[u] != ~0ull) st_hint_v2(pairs + 2 * p[u], v[u], pol_stream);
         }
     }
 }
@@ -385,6 +612,17 @@ static int bits_for_u64(u64 v) {
     return b;
 }
 
+// Doc-range partition of ids[] for translate_kernel: ranges of 2^rshift documents (default 2^22 = 32 MB of ids,
+// CDB_RANGE_BITS overrides), at most kMaxRanges of them.
+static void ids_ranges(i64 nd, int* nranges, int* rshift) {
+    const char* e = getenv("CDB_RANGE_BITS");  // read per call: the tests switch it to exercise many ranges
+    const int env_bits = e ? atoi(e) : 22;
+    int sh = env_bits < 8 ? 8 : (env_bits > 40 ? 40 : env_bits);
+    while (ceil_div(nd > 0 ? nd : 1, (i64)1 << sh) > kMaxRanges) ++sh;
+    *rshift = sh;
+    *nranges = (int)ceil_div(nd > 0 ? nd : 1, (i64)1 << sh);
+}
+
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
@@ -399,18 +637,18 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
     CDB_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), st));
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     for (auto& e : ev) CDB_CUDA(cudaEventCreate(&e));
     struct EvGuard {
         cudaEvent_t* e;
         ~EvGuard() {
-            for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]);
+            for (int i = 0; i < 7; ++i) cudaEventDestroy(e[i]);
         }
     } ev_guard{ev};
     CDB_CUDA(cudaEventRecord(ev[0], st));
-    SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
+    SearchCtx c = make_ctx(ix);
     int* err = reinterpret_cast<int*>(counters.p + 2);
-    search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, d_pat, d_pat_off, npat, left.p, right.p, err,
+    search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, ix.symtab, d_pat, d_pat_off, npat, left.p, right.p, err,
                                                                       large_list.p, counters.p);
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[1], st));
@@ -456,16 +694,28 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[3], st));
-    // fused gather: rows <= occurrences on the warp path + exact rows of the large path
+    // phase A: rows <= occurrences on the warp path + exact rows of the large path
     const u64 cap_pairs = hc[1] + nu;
+    int nranges, rshift;
+    ids_ranges(ix.nd, &nranges, &rshift);
+    DevBuf<u64> cpairs((size_t)cap_pairs, st);
+    DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
     const size_t smem = (size_t)kTileWarps * kWarpSmemBytes;
     CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, ix.d_ids, left.p, right.p, npat, dlarge.p,
-                                                                       status.p, reinterpret_cast<u32*>(counters.p + 3),
-                                                                       row_off.p, pairs.p);
+    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p, status.p,
+                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
+                                                                       cpairs.p, seg.p, nranges, rshift);
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[4], st));
+    // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
+    {
+        const i64 nitems = ceil_div(npat, 32) * nranges;
+        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * 8);
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges);
+        CDB_LAUNCH_CHECK();
+    }
+    CDB_CUDA(cudaEventRecord(ev[5], st));
     if (nl > 0 && nu > 0) {
         const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
         large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, row_off.p,
@@ -474,16 +724,16 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     }
     u64 total_pairs = 0;
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
-    CDB_CUDA(cudaEventRecord(ev[5], st));
+    CDB_CUDA(cudaEventRecord(ev[6], st));
     CDB_CUDA(cudaStreamSynchronize(st));
     {
         LocateStats& ls = g_locate_stats;
         cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);
-        ls.count_ms = 0;
         cudaEventElapsedTime(&ls.large_ms, ev[2], ev[3]);
-        cudaEventElapsedTime(&ls.scan_ms, ev[4], ev[5]);  // large-path emit + final read-back
-        cudaEventElapsedTime(&ls.emit_ms, ev[3], ev[4]);  // gather_kernel
-        cudaEventElapsedTime(&ls.total_ms, ev[0], ev[5]);
+        cudaEventElapsedTime(&ls.count_ms, ev[3], ev[4]);  // gather_kernel (phase A)
+        cudaEventElapsedTime(&ls.emit_ms, ev[4], ev[5]);   // translate_kernel (phase B)
+        cudaEventElapsedTime(&ls.scan_ms, ev[5], ev[6]);   // large-path emit + final read-back
+        cudaEventElapsedTime(&ls.total_ms, ev[0], ev[6]);
         ls.npat = npat;
         ls.total_pairs = (long long)total_pairs;
         ls.total_occ = (long long)total_occ;
@@ -608,8 +858,8 @@ static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nk
     DevBuf<i64> left(nkw, st), right(nkw, st);
     DevBuf<unsigned long long> counters(2, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, 16, st));
-    SearchCtx c{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text};
-    search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, d_kw.p, d_koff.p, nkw, left.p, right.p,
+    SearchCtx c = make_ctx(ix);
+    search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, ix.symtab, d_kw.p, d_koff.p, nkw, left.p, right.p,
                                                                       reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr);
     CDB_LAUNCH_CHECK();
     DevBuf<u64> ooff((size_t)nkw + 1, st);

@@ -25,10 +25,6 @@
 
 namespace cdb {
 
-struct SymTab {
-    u16 sym[256];  // 0 is reserved for end-of-document; present bytes map to 1..sigma in unsigned order
-};
-
 // ---- corpus statistics ----------------------------------------------------------------------------------
 __global__ void doc_stats_kernel(const i64* __restrict__ doc_off, i64 nd, unsigned long long* maxlen) {
     u64 m = 0;
@@ -529,6 +525,108 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     ix.sort_ms = timers.total_ms();
 }
 
+// ---- note N1: the reference's signed-radix / unsigned-leaf layout ---------------------------------------------------
+// The reference splits a group of suffixes that share a d-byte prefix by the SIGNED value of byte d (end-of-document
+// first, then 0x80..0xFF, then 0x00..0x7F; src/index.h:66-73, src/index.cpp:97-125) as long as the group is larger
+// than chuck_size = max(4096, n/256), and sorts smaller groups by unsigned memcmp (src/index.cpp:86-94).  Relative to
+// the plainly (unsigned) sorted array this is, inside every such large group, a rotation of the block of suffixes
+// whose byte d is < 0x80 behind the block whose byte d is >= 0x80.  The groups are found level by level with
+// binary searches on the sorted array (<= 256 groups per level can exceed n/256), then the rotations are applied
+// parents first, each as three in-place reversals.
+struct N1Node {
+    i64 b, e, d;
+};
+
+template <typename P>
+__global__ void n1_bounds_kernel(const P* __restrict__ sa, u64 mask, int bits1, const i64* __restrict__ doc_off,
+                                 const u8* __restrict__ text, const N1Node* __restrict__ nodes, int nnodes,
+                                 i64* __restrict__ bounds) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nnodes * 257) return;
+    const N1Node nd = nodes[t / 257];
+    const int c = t % 257;  // bounds[c] = first rank in [b, e) whose suffix is longer than d bytes and has byte d >= c
+    i64 L = nd.b, R = nd.e;
+    if (c == 256) L = R;
+    while (L < R) {
+        const i64 M = L + (R - L) / 2;
+        const u64 x = (u64)sa[M];
+        const i64 doc = (i64)(x & mask);
+        const i64 pos = __ldg(doc_off + doc) + (i64)(x >> bits1) + nd.d;
+        const int key = pos >= __ldg(doc_off + doc + 1) ? -1 : (int)text[pos];
+        if (key >= c)
+            R = M;
+        else
+            L = M + 1;
+    }
+    bounds[t] = L;
+}
+
+template <typename P>
+__global__ void reverse_kernel(P* __restrict__ a, u64 len) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < len / 2; i += (u64)gridDim.x * blockDim.x) {
+        const P x = a[i], y = a[len - 1 - i];
+        a[i] = y;
+        a[len - 1 - i] = x;
+    }
+}
+
+template <typename P>
+static void reverse_range(P* a, u64 len, cudaStream_t st) {
+    if (len < 2) return;
+    const int grid = (int)std::min<i64>(ceil_div((i64)(len / 2), 256), kNumSMs * 16);
+    reverse_kernel<P><<<grid, 256, 0, st>>>(a, len);
+    CDB_LAUNCH_CHECK();
+}
+
+template <typename P>
+static void apply_signed_radix_layout(Index& ix, cudaStream_t st) {
+    P* sa = reinterpret_cast<P*>(ix.d_sa);
+    struct Pending {
+        N1Node node;
+        i64 shift;  // where the group sits now = node.b + shift (rotations of its ancestors)
+    };
+    struct Rot {
+        i64 at, lsize, hsize;
+    };
+    std::vector<Pending> level{{{0, ix.n, 0}, 0}}, next;
+    std::vector<Rot> rots;
+    std::vector<N1Node> hnodes;
+    std::vector<i64> hb;
+    while (!level.empty()) {
+        const int nn = (int)level.size();
+        hnodes.resize(nn);
+        for (int j = 0; j < nn; ++j) hnodes[j] = level[j].node;
+        DevBuf<N1Node> dn(nn, st);
+        DevBuf<i64> db((size_t)nn * 257, st);
+        CDB_CUDA(cudaMemcpyAsync(dn.p, hnodes.data(), sizeof(N1Node) * nn, cudaMemcpyHostToDevice, st));
+        n1_bounds_kernel<P><<<(unsigned)ceil_div((i64)nn * 257, 256), 256, 0, st>>>(sa, ix.mask, ix.bits1, ix.d_off, ix.d_text,
+                                                                                  dn.p, nn, db.p);
+        CDB_LAUNCH_CHECK();
+        hb.resize((size_t)nn * 257);
+        CDB_CUDA(cudaMemcpyAsync(hb.data(), db.p, hb.size() * 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        next.clear();
+        for (int j = 0; j < nn; ++j) {
+            const i64* B = hb.data() + (size_t)j * 257;
+            const i64 lsize = B[128] - B[0], hsize = B[256] - B[128];
+            const bool rotated = lsize > 0 && hsize > 0;
+            if (rotated) rots.push_back({B[0] + level[j].shift, lsize, hsize});
+            for (int c = 0; c < 256; ++c) {
+                if (B[c + 1] - B[c] <= ix.chuck_size) continue;
+                const i64 sh = level[j].shift + (rotated ? (c < 128 ? hsize : -lsize) : 0);
+                next.push_back({{B[c], B[c + 1], level[j].node.d + 1}, sh});
+            }
+        }
+        level.swap(next);
+    }
+    for (const Rot& r : rots) {  // [L][H] -> [H][L]
+        reverse_range<P>(sa + r.at, (u64)r.lsize, st);
+        reverse_range<P>(sa + r.at + r.lsize, (u64)r.hsize, st);
+        reverse_range<P>(sa + r.at, (u64)(r.lsize + r.hsize), st);
+    }
+    CDB_CUDA(cudaStreamSynchronize(st));
+}
+
 void build_index(Index& ix, cudaStream_t st) {
     cudaEvent_t e0, e1;
     CDB_CUDA(cudaEventCreate(&e0));
@@ -583,6 +681,8 @@ void build_index(Index& ix, cudaStream_t st) {
             }
         }
         ix.mixed = lo && hi;
+        ix.symtab = tab;
+        ix.sigma = sigma;
         int b = bits_for((u64)sigma);  // symbols 0..sigma
         int S = 64 / b;
         if (S > EX_MAXS) S = EX_MAXS;
@@ -590,6 +690,13 @@ void build_index(Index& ix, cudaStream_t st) {
             build_typed<u32>(ix, tab, b, S, st);
         else
             build_typed<u64>(ix, tab, b, S, st);
+        if (ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size) {
+            if (ix.width == 4)
+                apply_signed_radix_layout<u32>(ix, st);
+            else
+                apply_signed_radix_layout<u64>(ix, st);
+        }
+        build_prefix_table(ix, st);
     }
     CDB_CUDA(cudaEventRecord(e1, st));
     CDB_CUDA(cudaEventSynchronize(e1));

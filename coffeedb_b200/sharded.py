@@ -1,0 +1,219 @@
+"""Sharded string index: one doc-range shard per rank, one process per GPU (BASELINE config 4).
+
+The reference is a single process and has nothing like this; the contract comes from its result order.  A document
+lives in exactly one shard and ``string_index::query`` reports rows in ascending doc index (src/index.cpp:316-322),
+so when rank g indexes the documents ``[g*nd/W, (g+1)*nd/W)`` the full row of a pattern is the concatenation of the
+shard rows in rank order — per-document counts never need summing.  What the ranks exchange per batch is small:
+
+* the packed pattern batch, broadcast from the rank that received the request,
+* per-pattern row lengths of every shard (``all_gather``)  -> global CSR offsets by a scan in rank order,
+* per-pattern occurrence totals (``all_reduce``)           -> what the reference's ``count`` needs,
+* optionally the rows themselves, gathered to one rank (``gather_rows``), for callers that need the flat answer.
+
+Plumbing is ``torch.distributed`` (NCCL over NVLink on GPUs; the CPU tests run the same code over gloo with a fake
+local engine).  All device compute stays in the C-ABI library; this file moves no corpus bytes between ranks.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import StringIndex, pack
+
+
+def shard_range(nd: int, rank: int, world: int) -> tuple[int, int]:
+    """Documents [lo, hi) of shard `rank`: contiguous, ascending with rank, sizes differ by at most one."""
+    return rank * nd // world, (rank + 1) * nd // world
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of library-owned device memory (torch wraps it without a copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedResult:
+    """Result of one sharded batch on this rank.
+
+    row_off, pairs   this shard's CSR rows (torch tensors on the compute device; pairs is [total, 2])
+    shard_rows       int64 [world, npat]   row length of every pattern on every shard
+    global_row_off   int64 [npat + 1]      CSR offsets of the concatenated (rank-ordered) answer
+    rank_base        int64 [npat]          where this shard's part of row q starts inside global row q
+    occurrences      int64 [npat]          total occurrences of every pattern over all shards
+    """
+
+    def __init__(self, row_off, pairs, shard_rows, occurrences, rank, keep=None):
+        self.row_off, self.pairs, self.shard_rows, self.occurrences = row_off, pairs, shard_rows, occurrences
+        tot = shard_rows.sum(dim=0)
+        self.global_row_off = torch.zeros(tot.numel() + 1, dtype=torch.int64, device=tot.device)
+        torch.cumsum(tot, 0, out=self.global_row_off[1:])
+        self.rank_base = shard_rows[:rank].sum(dim=0)
+        self._keep = keep  # owner of the device buffers row_off / pairs alias
+
+    @property
+    def npat(self) -> int:
+        return self.row_off.numel() - 1
+
+
+class ShardedStringIndex:
+    """One shard of a doc-range-sharded ``string_index``.  Every rank of `group` constructs one, adds ITS documents
+    (in global doc order) and calls ``build()`` / ``locate_batch()`` collectively."""
+
+    def __init__(self, group=None, device: torch.device | None = None, index_factory=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+        make = index_factory or (lambda: StringIndex(device=device.index if device.type == "cuda" else -1))
+        self.local = make()
+        self.nd_local = 0
+        self.nd_global = None
+        self.doc_base = None
+
+    # -- corpus --------------------------------------------------------------------------------------------------
+    def add_many(self, ids, text, doc_off):
+        """This rank's documents (string_index::add, src/index.cpp:174-177, for every document of the shard)."""
+        self.local.add_many(ids, text, doc_off)
+        self.nd_local += len(ids)
+
+    def build_device(self, d_text_ptr, d_doc_off_ptr, d_ids_ptr, nd, stream=0, keep=()):
+        self.local.build_device(d_text_ptr, d_doc_off_ptr, d_ids_ptr, nd, stream, keep=keep)
+        self.nd_local = nd
+        self._exchange_sizes()
+
+    def build(self):
+        """Every shard builds its own suffix array; no communication (a suffix never leaves its document)."""
+        self.local.build()
+        self._exchange_sizes()
+
+    def _exchange_sizes(self):
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        mine = torch.tensor([self.nd_local], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_gather_into_tensor(sizes, mine, group=self.group)
+        else:
+            sizes.copy_(mine)
+        sizes = sizes.cpu()
+        self.nd_global = int(sizes.sum())
+        self.doc_base = int(sizes[: self.rank].sum())
+
+    # -- query ---------------------------------------------------------------------------------------------------
+    def broadcast_patterns(self, patterns=None, pat_off=None, src: int = 0):
+        """The rank that holds the request broadcasts the packed batch -> (pat uint8 tensor, pat_off int64 tensor)
+        on the compute device of every rank."""
+        hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if self.rank == src:
+            if pat_off is None:
+                pat, pat_off = pack(list(patterns))
+            else:
+                pat, pat_off = np.ascontiguousarray(patterns, np.uint8), np.ascontiguousarray(pat_off, np.int64)
+            hdr[0], hdr[1] = len(pat), len(pat_off) - 1
+        if self.world > 1:
+            dist.broadcast(hdr, src, group=self.group)
+        nbytes, npat = int(hdr[0]), int(hdr[1])
+        d_pat = torch.zeros(nbytes + 8, dtype=torch.uint8, device=self.device)
+        d_off = torch.zeros(npat + 1, dtype=torch.int64, device=self.device)
+        if self.rank == src:
+            d_pat[:nbytes].copy_(torch.from_numpy(pat))
+            d_off.copy_(torch.from_numpy(pat_off))
+        if self.world > 1:
+            dist.broadcast(d_pat, src, group=self.group)
+            dist.broadcast(d_off, src, group=self.group)
+        return d_pat, d_off
+
+    def locate_local(self, d_pat, d_off):
+        """This shard's rows for the batch -> (row_off, pairs[total,2], occ[npat], keep)."""
+        npat = d_off.numel() - 1
+        if self.device.type == "cuda":
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            res = self.local.locate_batch_device(d_pat.data_ptr(), d_off.data_ptr(), npat, stream)
+            row_off = torch.as_tensor(_DevArray(res.row_off, npat + 1), device=self.device)
+            tp = res.total_pairs
+            pairs = (torch.as_tensor(_DevArray(res.pairs, 2 * tp), device=self.device).view(tp, 2) if tp
+                     else torch.zeros((0, 2), dtype=torch.int64, device=self.device))
+            occ = (torch.as_tensor(_DevArray(res.right, npat), device=self.device)
+                   - torch.as_tensor(_DevArray(res.left, npat), device=self.device)) if npat else d_off[:0]
+            return row_off, pairs, occ, _ResultOwner(self.local, res)
+        # host engine (CPU tests inject one; the product StringIndex raises without a CUDA device)
+        nbytes = int(d_off[-1]) if npat else 0
+        ro, pr = self.local.locate_batch(d_pat[:nbytes].numpy(), d_off.numpy())
+        pr = np.asarray(pr, np.int64).reshape(-1, 2)
+        ro_t = torch.from_numpy(np.asarray(ro, np.int64))
+        occ = torch.zeros(npat, dtype=torch.int64)
+        if len(pr):
+            occ.index_add_(0, torch.repeat_interleave(torch.arange(npat), ro_t[1:] - ro_t[:-1]), torch.from_numpy(pr[:, 1].copy()))
+        return ro_t, torch.from_numpy(pr.copy()), occ, None
+
+    def locate_batch(self, patterns=None, pat_off=None, src: int = 0, device_patterns=None) -> ShardedResult:
+        """Collective.  `patterns` (list of bytes, or packed uint8 + offsets) is read on rank `src` only;
+        `device_patterns=(d_pat, d_off)` skips the packing when the batch is already on the device of rank `src`."""
+        if device_patterns is not None:
+            d_pat, d_off = device_patterns
+            if self.world > 1:
+                dist.broadcast(d_pat, src, group=self.group)
+                dist.broadcast(d_off, src, group=self.group)
+        else:
+            d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
+        npat = d_off.numel() - 1
+        row_off, pairs, occ, keep = self.locate_local(d_pat, d_off)
+        rows = (row_off[1:] - row_off[:-1]).contiguous()
+        shard_rows = torch.empty(self.world * npat, dtype=torch.int64, device=self.device)
+        occ = occ.clone()
+        if self.world > 1:
+            dist.all_gather_into_tensor(shard_rows, rows, group=self.group)
+            dist.all_reduce(occ, group=self.group)
+        else:
+            shard_rows.copy_(rows)
+        return ShardedResult(row_off, pairs, shard_rows.view(self.world, npat), occ, self.rank, keep)
+
+    def gather_rows(self, res: ShardedResult, dst: int = 0):
+        """Collective.  Assembles the flat answer on rank `dst`: (global_row_off, pairs) with row q = the shard rows of
+        q concatenated in rank order = string_index::query(q) on the whole corpus.  Other ranks get None."""
+        npat = res.npat
+        totals = res.shard_rows.sum(dim=1).cpu().tolist()
+        if self.rank == dst:
+            parts = []
+            for r in range(self.world):
+                if r == dst:
+                    parts.append(res.pairs)
+                else:
+                    buf = torch.empty((totals[r], 2), dtype=torch.int64, device=self.device)
+                    if totals[r]:
+                        dist.recv(buf, src=r, group=self.group)
+                    parts.append(buf)
+            out = torch.empty((int(res.global_row_off[-1]), 2), dtype=torch.int64, device=self.device)
+            # destination of entry j of shard r's row q: global_row_off[q] + sum_{r' < r} rows[r'][q] + j
+            base = torch.zeros(npat, dtype=torch.int64, device=self.device)
+            for r in range(self.world):
+                rows = res.shard_rows[r]
+                if totals[r]:
+                    starts = res.global_row_off[:-1] + base                   # per pattern
+                    local_off = torch.cumsum(rows, 0) - rows                  # this shard's own CSR offsets
+                    q_of = torch.repeat_interleave(torch.arange(npat, device=self.device), rows)
+                    pos = starts[q_of] + (torch.arange(totals[r], device=self.device) - local_off[q_of])
+                    out[pos] = parts[r]
+                base += rows
+            return res.global_row_off, out
+        if totals[self.rank]:
+            dist.send(res.pairs.contiguous(), dst=dst, group=self.group)
+        return None
+
+    def close(self):
+        self.local.close()
+
+
+class _ResultOwner:
+    """Frees the library-owned device result when the tensors that alias it go away."""
+
+    def __init__(self, index: StringIndex, res):
+        self.index, self.res = index, res
+
+    def __del__(self):
+        try:
+            self.index.device_result_free(self.res)
+        except Exception:
+            pass

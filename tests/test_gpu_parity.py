@@ -24,10 +24,10 @@ def build(text, off, ids, **kw):
     return ix
 
 
-PLAIN_CASES = [c for c in cases.CASES if c not in cases.N1_CASES]
+ALL_CASES = list(cases.CASES)  # including the note-N1 cases (signed-radix / unsigned-leaf layout)
 
 
-@pytest.mark.parametrize("name", PLAIN_CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_suffix_array_matches_reference(name, golden):
     text, off, ids, _ = cases.CASES[name]()
     ix = build(text, off, ids)
@@ -41,7 +41,7 @@ def test_suffix_array_matches_reference(name, golden):
     ix.close()
 
 
-@pytest.mark.parametrize("name", PLAIN_CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_locate_matches_reference(name, golden):
     text, off, ids, pats = cases.CASES[name]()
     ix = build(text, off, ids)
@@ -157,3 +157,67 @@ def test_highlight_spans_match_reference(golden):
     for d, sp in zip(docs, got):
         assert np.array_equal(sp, oracle.port.spans(kws, texts[d]))
     ix.close()
+
+
+def test_translate_many_doc_ranges(monkeypatch):
+    """translate_kernel walks ids[] by doc range (32 MB slices at production sizes); CDB_RANGE_BITS shrinks the
+    ranges so that a small corpus exercises the multi-range path, including rows that miss most ranges."""
+    text, off, ids = corpora.uniform(20000, 60, seed=51, lo=ord("a"), hi=ord("e"))
+    ix = build(text, off, ids)
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    pat, poff = corpora.uniform_patterns(300, 4, seed=52, lo=ord("a"), hi=ord("e"))
+    spat, soff = corpora.sampled_patterns(text, off, 100, 2, 9, seed=53)
+    pats = [bytes(pat[poff[i]:poff[i + 1]]) for i in range(300)] + [bytes(spat[soff[i]:soff[i + 1]]) for i in range(100)]
+    pats += [b"zzzz", b"a", b"ab"]  # no hit / large-path rows mixed into the batch
+    want = [oracle.port.query(text, off, ids, sa, b1, kw) for kw in pats]
+    for bits in ("8", "11", "22"):
+        monkeypatch.setenv("CDB_RANGE_BITS", bits)
+        row_off, pairs = ix.locate_batch(pats)
+        for q in range(len(pats)):
+            assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], want[q]), (bits, pats[q])
+    ix.close()
+
+
+def test_n1_layout_against_live_oracle():
+    """Note N1 at a size with several radix levels above chuck_size: the suffix array must equal the oracle's
+    signed-radix / unsigned-leaf layout and every query must return the reference's (sometimes non-brute-force)
+    answer, because the reference's own binary-search recurrences run on that layout."""
+    for seed, (text, off, ids) in enumerate([corpora.utf8ish(3000, 300, seed=61),
+                                             corpora.uniform(2000, 150, seed=62, lo=0x70, hi=0x90)]):
+        ix = build(text, off, ids)
+        sa, b1, _w = oracle.port.build_sa(text, off)
+        assert np.array_equal(ix.export_sa(), sa)
+        spat, soff = corpora.sampled_patterns(text, off, 300, 1, 6, seed=63 + seed)
+        row_off, pairs = ix.locate_batch(spat, soff)
+        nbrute = 0
+        for q in range(300):
+            kw = bytes(spat[soff[q]:soff[q + 1]])
+            got = pairs[row_off[q]:row_off[q + 1]]
+            assert np.array_equal(got, oracle.port.query(text, off, ids, sa, b1, kw)), kw
+            nbrute += int(not np.array_equal(got, corpora.brute_count(text, off, ids, kw))) if q < 60 else 0
+        ix.close()
+        # compat off: plain unsigned order, prefix directory on, brute-force answers
+        ix = build(text, off, ids, compat_signed=False)
+        row_off, pairs = ix.locate_batch(spat, soff)
+        for q in range(60):
+            kw = bytes(spat[soff[q]:soff[q + 1]])
+            assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], corpora.brute_count(text, off, ids, kw)), kw
+        ix.close()
+
+
+def test_prefix_directory_on_and_off(monkeypatch):
+    """Same answers with the prefix directory disabled (reference recurrences) and at several directory depths."""
+    text, off, ids = corpora.ragged(4000, 80, seed=71, alphabet=b"abcdefg")
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    spat, soff = corpora.sampled_patterns(text, off, 200, 1, 14, seed=72)
+    pat, poff = corpora.uniform_patterns(100, 3, seed=73, lo=ord("a"), hi=ord("i"))  # some bytes absent from the corpus
+    pats = [bytes(spat[soff[i]:soff[i + 1]]) for i in range(200)] + [bytes(pat[poff[i]:poff[i + 1]]) for i in range(100)]
+    want = [oracle.port.query(text, off, ids, sa, b1, kw) for kw in pats]
+    for bits in ("0", "3", "9", "16", "24"):
+        monkeypatch.setenv("CDB_PTAB_BITS", bits)
+        ix = build(text, off, ids)
+        assert np.array_equal(ix.export_sa(), sa)
+        row_off, pairs = ix.locate_batch(pats)
+        for q in range(len(pats)):
+            assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], want[q]), (bits, pats[q])
+        ix.close()
