@@ -103,6 +103,7 @@ static void keep_pool_memory(int dev) {
     }
     // experiment knob: L2 -> DRAM fetch granularity hint (bytes; 32/64/128) for the random-probe kernels
     if (const char* e = getenv("CDB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+    if (const char* e = getenv("CDB_L2_PERSIST_MB")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e) << 20);
 }
 
 }  // namespace cdb
@@ -254,6 +255,7 @@ cdb_status cdb_build_device(cdb_index* h, const void* d_text, const int64_t* d_d
     CDB_TRY
     Index* ix = reinterpret_cast<Index*>(h);
     if (!ix || nd < 0 || !d_doc_off) throw Error(CDB_ERR_ARG, "cdb_build_device: bad argument");
+    if (((uintptr_t)d_text & 15) != 0) throw Error(CDB_ERR_ARG, "cdb_build_device: d_text must be 16-byte aligned");
     require_device();
     if (ix->device < 0) CDB_CUDA(cudaGetDevice(&ix->device));
     DeviceSetter ds(ix->device);

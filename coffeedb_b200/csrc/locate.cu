@@ -482,16 +482,23 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
                                                                   const i64* __restrict__ ids, i64* __restrict__ pairs,
-                                                                  i64 npat, int nranges) {
+                                                                  i64 npat, int nranges, int mode,
+                                                                  unsigned long long* ticket) {
     __shared__ u32 s_excl[kTrWarps][33];
     __shared__ u64 s_adj[kTrWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 ntile = (npat + 31) >> 5;
     const i64 nitems = ntile * nranges;
-    const i64 nwarps = (i64)gridDim.x * kTrWarps;
     const u64 pol_keep = l2_policy_evict_last();
     const u64 pol_stream = l2_policy_evict_first();
-    for (i64 item = (i64)blockIdx.x * kTrWarps + warp; item < nitems; item += nwarps) {
+    // Items are handed out through one global ticket, in order: at any moment all warps of the grid are within a few
+    // thousand items of each other, i.e. inside one (at a range change: two) slices of ids[].  A static item
+    // stride lets warps drift several ranges apart and the slices in use no longer fit L2 together.
+    for (;;) {
+        i64 item = 0;
+        if (lane == 0) item = (i64)atomicAdd(ticket, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
         const int r = (int)(item / ntile);
         const i64 q = (item % ntile) * 32 + lane;
         u32 len = 0;
@@ -527,18 +534,26 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
                     for (int st = 16; st; st >>= 1)
                         if (s_excl[warp][j + st] <= idx) j += st;
                     p[u] = s_adj[warp][j] + idx;
-                    cp[u] = ld_hint_u64(cpairs + p[u], pol_stream);
+                    cp[u] = (mode & 4) ? ld_stream_u64(cpairs + p[u]) : ld_hint_u64(cpairs + p[u], pol_stream);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kTrU; ++u)
                 if (p[u] != ~0ull) {
-                    v[u].x = (i64)ld_hint_u64(reinterpret_cast<const u64*>(ids) + (u32)cp[u], pol_keep);
+                    const u64* ip = reinterpret_cast<const u64*>(ids) + (u32)cp[u];
+                    v[u].x = (mode & 3) == 0 ? (i64)ld_hint_u64(ip, pol_keep)
+                             : (mode & 3) == 1 ? (i64)__ldg(ip)
+                                               : (i64)ld_stream_u64(ip);
                     v[u].y = (i64)(cp[u] >> 32);
                 }
 #pragma unroll
             for (int u = 0; u < kTrU; ++u)
-                if (p[u] != ~0ull) st_hint_v2(pairs + 2 * p[u], v[u], pol_stream);
+                if (p[u] != ~0ull) {
+                    if (mode & 4)
+                        __stcs(reinterpret_cast<longlong2*>(pairs + 2 * p[u]), v[u]);
+                    else
+                        st_hint_v2(pairs + 2 * p[u], v[u], pol_stream);
+                }
         }
     }
 }
@@ -632,7 +647,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(4, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] ticket
+    DevBuf<unsigned long long> counters(5, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
     DevBuf<u32> large_list(npat, st);
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -711,8 +726,16 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     {
         const i64 nitems = ceil_div(npat, 32) * nranges;
-        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * 8);
-        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges);
+        static int per_sm = 0;  // resident CTAs per SM: the grid is exactly one wave
+        if (!per_sm) {
+            int v = 0;
+            CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
+            per_sm = v > 0 ? v : 1;
+        }
+        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
+        const char* em = getenv("CDB_TR_MODE");
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
+                                                         em ? atoi(em) : 1, counters.p + 4);
         CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[5], st));
@@ -794,6 +817,60 @@ __global__ void span_expand_kernel(const SAT* __restrict__ sa, u64 mask, int bit
     }
 }
 
+// Direct scan of the requested documents: one thread per (document, position) compares every keyword there.  Used
+// instead of the suffix-array enumeration (a) in the note-N1 layout, where the array is not sorted under the
+// comparator of the search and query() itself reproduces the reference's misses, while the reference's highlighter
+// scans the text and finds every occurrence (src/database.cpp:58-77), and (b) when the keywords occur far more often
+// in the whole corpus than the requested documents are long.
+__global__ void span_len_kernel(const i64* __restrict__ doc_off, const i64* __restrict__ udocs, u64 nu, u64* __restrict__ len) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nu) len[u] = (u64)(doc_off[udocs[u] + 1] - doc_off[udocs[u]]);
+}
+
+template <bool WRITE>
+__global__ void span_scan_kernel(const u8* __restrict__ text, const i64* __restrict__ doc_off, const i64* __restrict__ udocs,
+                                 u64 nu, const u64* __restrict__ pos_off, u64 total_pos, const u8* __restrict__ kw,
+                                 const i64* __restrict__ kw_off, u64 nkw, int bits2, u64* __restrict__ keys,
+                                 u64* __restrict__ ends, unsigned long long* __restrict__ cursor) {
+    unsigned long long found = 0;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total_pos; e += (u64)gridDim.x * blockDim.x) {
+        u64 lo = 0, hi = nu - 1;  // largest u with pos_off[u] <= e
+        while (lo < hi) {
+            const u64 mid = lo + (hi - lo + 1) / 2;
+            if (__ldg(pos_off + mid) <= e)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const u64 p = e - __ldg(pos_off + lo);
+        const i64 doc = udocs[lo];
+        const i64 ds = doc_off[doc];
+        const u64 len = (u64)(doc_off[doc + 1] - ds);
+        for (u64 k = 0; k < nkw; ++k) {
+            const u64 m = (u64)(kw_off[k + 1] - kw_off[k]);
+            if (p + m > len) continue;
+            const u8* a = text + ds + p;
+            const u8* b = kw + kw_off[k];
+            u64 i = 0;
+            while (i < m && a[i] == b[i]) ++i;
+            if (i == m) {
+                if (WRITE) {
+                    const u64 slot = atomicAdd(cursor, 1ull);
+                    keys[slot] = (lo << bits2) | p;
+                    ends[slot] = p + m - 1;
+                } else {
+                    ++found;
+                }
+            }
+        }
+    }
+    if (!WRITE) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
+        if ((threadIdx.x & 31) == 0 && found) atomicAdd(cursor, found);
+    }
+}
+
 // one thread per requested document: merge its records (sorted by begin).  WRITE=false counts spans.
 template <bool WRITE>
 __global__ void span_merge_kernel(const u64* __restrict__ keys, const u64* __restrict__ ends, u64 nrec, int bits2, u64 nu,
@@ -858,29 +935,61 @@ static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nk
     DevBuf<i64> left(nkw, st), right(nkw, st);
     DevBuf<unsigned long long> counters(2, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, 16, st));
-    SearchCtx c = make_ctx(ix);
-    search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, ix.symtab, d_kw.p, d_koff.p, nkw, left.p, right.p,
-                                                                      reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr);
-    CDB_LAUNCH_CHECK();
-    DevBuf<u64> ooff((size_t)nkw + 1, st);
-    span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
-    CDB_LAUNCH_CHECK();
-    prim::exclusive_scan<u64>(ooff.p, ooff.p, (u64)nkw, st);
-    u64 total = 0;
-    CDB_CUDA(cudaMemcpyAsync(&total, ooff.p + nkw, 8, cudaMemcpyDeviceToHost, st));
-    CDB_CUDA(cudaStreamSynchronize(st));
     uoff.assign(nu + 1, 0);
     uspans.clear();
-    if (total == 0) return;
-    DevBuf<u64> k0(total, st), k1(total, st), e0(total, st), e1(total, st);
-    const int grid = (int)std::min<i64>(ceil_div((i64)total, 256), kNumSMs * 16);
-    span_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, ix.bits1, ix.bits2, left.p, ooff.p, (u64)nkw, total, d_koff.p,
-                                                   d_udocs.p, nu, k0.p, e0.p, counters.p);
+    // size of the direct scan: positions of the requested documents
+    DevBuf<u64> pos_off(nu + 1, st);
+    span_len_kernel<<<(unsigned)ceil_div((i64)nu, 256), 256, 0, st>>>(ix.d_off, d_udocs.p, nu, pos_off.p);
     CDB_LAUNCH_CHECK();
-    unsigned long long nrec = 0;
-    CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
+    prim::exclusive_scan<u64>(pos_off.p, pos_off.p, nu, st);
+    u64 total_pos = 0;
+    CDB_CUDA(cudaMemcpyAsync(&total_pos, pos_off.p + nu, 8, cudaMemcpyDeviceToHost, st));
+    const bool n1_layout = ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size;
+    const char* force = getenv("CDB_SPANS_SCAN");
+    bool use_scan = n1_layout || (force && atoi(force) == 1);
+    u64 total = 0;
+    DevBuf<u64> ooff;
+    if (!use_scan) {
+        SearchCtx c = make_ctx(ix);
+        search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, ix.symtab, d_kw.p, d_koff.p, nkw, left.p, right.p,
+                                                                          reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr);
+        CDB_LAUNCH_CHECK();
+        ooff.alloc((size_t)nkw + 1, st);
+        span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
+        CDB_LAUNCH_CHECK();
+        prim::exclusive_scan<u64>(ooff.p, ooff.p, (u64)nkw, st);
+        CDB_CUDA(cudaMemcpyAsync(&total, ooff.p + nkw, 8, cudaMemcpyDeviceToHost, st));
+    }
     CDB_CUDA(cudaStreamSynchronize(st));
-    if (nrec == 0) return;
+    // enumerating every occurrence in the corpus costs `total`; scanning the requested documents costs positions x keywords
+    if (!use_scan && !(force && atoi(force) == 0) && total > total_pos * (u64)nkw) use_scan = true;
+    DevBuf<u64> k0, k1, e0, e1;
+    unsigned long long nrec = 0;
+    if (use_scan) {
+        if (total_pos == 0) return;
+        const int grid = (int)std::min<i64>(ceil_div((i64)total_pos, 256), kNumSMs * 16);
+        span_scan_kernel<false><<<grid, 256, 0, st>>>(ix.d_text, ix.d_off, d_udocs.p, nu, pos_off.p, total_pos, d_kw.p, d_koff.p,
+                                                      (u64)nkw, ix.bits2, nullptr, nullptr, counters.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        if (nrec == 0) return;
+        k0.alloc(nrec, st); k1.alloc(nrec, st); e0.alloc(nrec, st); e1.alloc(nrec, st);
+        CDB_CUDA(cudaMemsetAsync(counters.p, 0, 8, st));
+        span_scan_kernel<true><<<grid, 256, 0, st>>>(ix.d_text, ix.d_off, d_udocs.p, nu, pos_off.p, total_pos, d_kw.p, d_koff.p,
+                                                     (u64)nkw, ix.bits2, k0.p, e0.p, counters.p);
+        CDB_LAUNCH_CHECK();
+    } else {
+        if (total == 0) return;
+        k0.alloc(total, st); k1.alloc(total, st); e0.alloc(total, st); e1.alloc(total, st);
+        const int grid = (int)std::min<i64>(ceil_div((i64)total, 256), kNumSMs * 16);
+        span_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, ix.bits1, ix.bits2, left.p, ooff.p, (u64)nkw, total, d_koff.p,
+                                                       d_udocs.p, nu, k0.p, e0.p, counters.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        if (nrec == 0) return;
+    }
     int cb = rs::radix_sort_pairs<u64>(k0.p, k1.p, e0.p, e1.p, nrec, 0, ix.bits2 + bits_for_u64(nu - 1), st);
     const u64* ks = cb ? k1.p : k0.p;
     const u64* es = cb ? e1.p : e0.p;

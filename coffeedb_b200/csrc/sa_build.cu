@@ -17,6 +17,7 @@
 // The payload carried through every sort is the reference's own packed element (offset << bits1) | doc, so the
 // finished array is byte-for-byte what src/index.cpp:209-215 + the sort would hold (up to note N2 ties).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "index.cuh"
@@ -77,96 +78,173 @@ __device__ __forceinline__ i64 doc_of(const i64* __restrict__ doc_off, i64 lo, i
 }
 
 // ---- K1 + key extraction --------------------------------------------------------------------------------
-// One CTA handles 1024 consecutive text positions: the bytes (plus S-1 lookahead) are re-coded into shared
-// memory once, each thread then assembles the keys of 4 positions.  MODE 0: histogram of the top `cb` key bits
-// (chunk planning).  MODE 1: all positions, output index = position.  MODE 2: positions whose bucket lies in
-// [blo, bhi), appended through a CTA-aggregated atomic cursor.
+// tile_doc[t] = the document that holds text position t * EX_TILE (largest d with doc_off[d] <= position; empty
+// documents share an offset with their successor and are skipped this way), for t = 0 .. ntiles.  One parallel
+// lower bound per tile: neighbouring tiles follow the same path, the probes hit L1/L2.
 constexpr int EX_THREADS = 256;
 constexpr int EX_IPT = 4;
 constexpr int EX_TILE = EX_THREADS * EX_IPT;
 constexpr int EX_MAXS = 32;
+constexpr int EX_HIST = 4096;  // chunk planning histogram over the top 12 key bits
 
+__global__ void tile_doc_kernel(const i64* __restrict__ doc_off, i64 nd, i64 n, i64 ntiles, i64* __restrict__ tile_doc) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const i64 pos = t * EX_TILE;
+    tile_doc[t] = pos >= n ? nd - 1 : doc_of(doc_off, 0, nd - 1, pos);
+}
+
+// Persistent CTAs walk tiles of 1024 consecutive text positions.  Per tile: the bytes (plus S-1 lookahead) arrive as
+// 16-byte vector loads and are re-coded into shared memory once; the document of every position comes from a
+// block-wide scan over the document starts that fall into the tile (no per-position search); each thread then
+// assembles the keys of 4 positions.  MODE 0: histogram of the top key bits (chunk planning; shared-memory
+// histogram, flushed once per CTA).  MODE 1: all positions, output index = position.  MODE 2: positions whose
+// bucket lies in [blo, bhi): compacted in shared memory, appended through a CTA-aggregated atomic cursor and
+// written as contiguous runs.
 template <typename P, int MODE>
 __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restrict__ text, const i64* __restrict__ doc_off,
-                                                             i64 nd, i64 n, SymTab tab, int b, int S, int bits1,
-                                                             int cbshift, u32 blo, u32 bhi, u64* __restrict__ keys,
-                                                             P* __restrict__ vals, unsigned long long* cursor,
-                                                             unsigned long long* bucket_hist) {
+                                                             const i64* __restrict__ tile_doc, i64 nd, i64 n, i64 ntiles,
+                                                             SymTab tab, int b, int S, int bits1, int cbshift, u32 blo,
+                                                             u32 bhi, u64* __restrict__ keys, P* __restrict__ vals,
+                                                             unsigned long long* cursor, unsigned long long* bucket_hist) {
     __shared__ u16 s_tab[256];
-    __shared__ u16 s_sym[EX_TILE + EX_MAXS];
-    __shared__ i64 s_dlo, s_dhi;
+    __shared__ __align__(16) u16 s_sym[EX_TILE + 2 * EX_MAXS];
+    __shared__ u32 s_cnt[EX_TILE];
     __shared__ u64 s_ws[32];
     __shared__ u64 s_base;
+    __shared__ u64 s_key[MODE == 2 ? EX_TILE : 1];
+    __shared__ P s_val[MODE == 2 ? EX_TILE : 1];
+    __shared__ u32 s_hist[MODE == 0 ? EX_HIST : 1];
     const int tid = threadIdx.x;
     s_tab[tid] = tab.sym[tid];
-    const i64 t0 = (i64)blockIdx.x * EX_TILE;
-    if (tid == 0) s_dlo = doc_of(doc_off, 0, nd - 1, t0);
-    if (tid == 32) {
-        i64 last = t0 + EX_TILE - 1;
-        s_dhi = doc_of(doc_off, 0, nd - 1, last < n - 1 ? last : n - 1);
-    }
+    if (MODE == 0)
+        for (int i = tid; i < EX_HIST; i += EX_THREADS) s_hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < EX_TILE + S; i += EX_THREADS) {
-        i64 g = t0 + i;
-        s_sym[i] = g < n ? s_tab[text[g]] : 0;
-    }
-    __syncthreads();
-    const i64 dlo = s_dlo, dhi = s_dhi;
-    u64 key[EX_IPT];
-    P val[EX_IPT];
-    bool sel[EX_IPT];
-    u32 nsel = 0;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 t0 = tile * EX_TILE;
+        const i64 d0 = __ldg(tile_doc + tile), d1 = __ldg(tile_doc + tile + 1);
+        // symbols of text[t0, t0 + EX_TILE + S): 16-byte loads (text is 16-byte aligned and padded)
+        {
+            const int nvec = (EX_TILE + S + 15) >> 4;
+            if (tid < nvec) {
+                uint4 v = make_uint4(0, 0, 0, 0);  // bytes past the padded end are never part of a key
+                if (t0 + (i64)tid * 16 + 16 <= n + kTextPad) v = ld_stream_v4(reinterpret_cast<const uint4*>(text + t0) + tid);
+                const u32 w[4] = {v.x, v.y, v.z, v.w};
+                u16* dst = s_sym + tid * 16;
 #pragma unroll
-    for (int r = 0; r < EX_IPT; ++r) {
-        const int li = r * EX_THREADS + tid;
-        const i64 g = t0 + li;
-        sel[r] = false;
-        key[r] = 0;
-        val[r] = 0;
-        if (g < n) {
-            i64 d = doc_of(doc_off, dlo, dhi, g);
-            i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
-            i64 rem = de - g;
-            int lim = rem < (i64)S ? (int)rem : S;
-            u64 k = 0;
-            for (int j = 0; j < S; ++j) k = (k << b) | (u64)(j < lim ? s_sym[li + j] : 0);
-            key[r] = k;
-            val[r] = (P)(((u64)(g - ds) << bits1) | (u64)d);
-            if (MODE == 1) {
-                sel[r] = true;
-            } else {
-                u32 bucket = (u32)(k >> cbshift);
-                if (MODE == 0)
-                    atomicAdd(bucket_hist + bucket, 1ull);
-                else
-                    sel[r] = bucket >= blo && bucket < bhi;
-            }
-            nsel += sel[r] ? 1 : 0;
-        }
-    }
-    if (MODE == 1) {
-#pragma unroll
-        for (int r = 0; r < EX_IPT; ++r) {
-            const i64 g = t0 + r * EX_THREADS + tid;
-            if (sel[r]) {
-                keys[g] = key[r];
-                vals[g] = val[r];
+                for (int k = 0; k < 4; ++k) {
+                    dst[4 * k + 0] = s_tab[w[k] & 255];
+                    dst[4 * k + 1] = s_tab[(w[k] >> 8) & 255];
+                    dst[4 * k + 2] = s_tab[(w[k] >> 16) & 255];
+                    dst[4 * k + 3] = s_tab[w[k] >> 24];
+                }
             }
         }
-    } else if (MODE == 2) {
-        u64 tot;
-        u64 ex = prim::block_exclusive_scan_u64(nsel, &tot, s_ws);
-        if (tid == 0) s_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0;
+        *reinterpret_cast<uint4*>(&s_cnt[tid * EX_IPT]) = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        u64 o = s_base + ex;
+        // document starts inside (t0, t0 + EX_TILE): documents d0+1 .. d1
+        for (i64 d = d0 + 1 + tid; d <= d1; d += EX_THREADS) {
+            const i64 p = __ldg(doc_off + d) - t0;
+            if (p > 0 && p < EX_TILE) atomicAdd(&s_cnt[p], 1u);
+        }
+        __syncthreads();
+        // thread-contiguous scan: position li = tid * EX_IPT + r
+        u32 c[EX_IPT];
+        u32 csum = 0;
+        {
+            const uint4 cv = *reinterpret_cast<const uint4*>(&s_cnt[tid * EX_IPT]);
+            c[0] = cv.x;
+            c[1] = c[0] + cv.y;
+            c[2] = c[1] + cv.z;
+            c[3] = c[2] + cv.w;
+            csum = c[3];
+        }
+        u64 tot;
+        const u64 dbase = (u64)d0 + prim::block_exclusive_scan_u64((u64)csum, &tot, s_ws);
+        u64 key[EX_IPT];
+        P val[EX_IPT];
+        bool sel[EX_IPT];
+        u32 nsel = 0;
+        // sliding window over the thread's 4 consecutive positions: W = the S symbols from the position on, ignoring
+        // document ends; the key keeps the first min(S, remaining) of them
+        const u64 keymask = b * S >= 64 ? ~0ull : ((1ull << (b * S)) - 1);
+        u64 W = 0;
+        for (int j = 0; j < S - 1; ++j) W = (W << b) | (u64)s_sym[tid * EX_IPT + j];
 #pragma unroll
         for (int r = 0; r < EX_IPT; ++r) {
-            if (sel[r]) {
-                keys[o] = key[r];
-                vals[o] = val[r];
-                ++o;
+            const int li = tid * EX_IPT + r;
+            const i64 g = t0 + li;
+            W = ((W << b) | (u64)s_sym[li + S - 1]) & keymask;
+            sel[r] = false;
+            key[r] = 0;
+            val[r] = 0;
+            if (g < n) {
+                const i64 d = (i64)(dbase + c[r]);
+                const i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
+                const i64 rem = de - g;
+                const int sh = rem < (i64)S ? b * (S - (int)rem) : 0;
+                const u64 k = (W >> sh) << sh;
+                key[r] = k;
+                val[r] = (P)(((u64)(g - ds) << bits1) | (u64)d);
+                if (MODE == 1) {
+                    sel[r] = true;
+                } else {
+                    const u32 bucket = (u32)(k >> cbshift);
+                    if (MODE == 0)
+                        atomicAdd(&s_hist[bucket], 1u);
+                    else
+                        sel[r] = bucket >= blo && bucket < bhi;
+                }
+                nsel += sel[r] ? 1 : 0;
             }
         }
+        if (MODE == 1 && t0 + EX_TILE <= n) {
+            // thread-contiguous: 4 keys = 32 bytes, 4 values = 16/32 bytes per thread, 16-byte stores
+            ulonglong2* kd = reinterpret_cast<ulonglong2*>(keys + t0 + tid * EX_IPT);
+            kd[0] = make_ulonglong2(key[0], key[1]);
+            kd[1] = make_ulonglong2(key[2], key[3]);
+            if (sizeof(P) == 4) {
+                *reinterpret_cast<uint4*>(vals + t0 + tid * EX_IPT) = make_uint4((u32)val[0], (u32)val[1], (u32)val[2], (u32)val[3]);
+            } else {
+                ulonglong2* vd = reinterpret_cast<ulonglong2*>(vals + t0 + tid * EX_IPT);
+                vd[0] = make_ulonglong2((u64)val[0], (u64)val[1]);
+                vd[1] = make_ulonglong2((u64)val[2], (u64)val[3]);
+            }
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < EX_IPT; ++r) {
+                const i64 g = t0 + tid * EX_IPT + r;
+                if (sel[r]) {
+                    keys[g] = key[r];
+                    vals[g] = val[r];
+                }
+            }
+        } else if (MODE == 2) {
+            u64 stot;
+            const u64 ex = prim::block_exclusive_scan_u64(nsel, &stot, s_ws);
+            if (tid == 0) s_base = stot ? atomicAdd(cursor, (unsigned long long)stot) : 0;
+            u32 o = (u32)ex;
+#pragma unroll
+            for (int r = 0; r < EX_IPT; ++r) {
+                if (sel[r]) {
+                    s_key[o] = key[r];
+                    s_val[o] = val[r];
+                    ++o;
+                }
+            }
+            __syncthreads();
+            const u64 base = s_base;
+            for (u32 i = tid; i < (u32)stot; i += EX_THREADS) {
+                keys[base + i] = s_key[i];
+                vals[base + i] = s_val[i];
+            }
+        }
+        __syncthreads();  // s_sym / s_cnt / staging are re-used by the next tile
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (int i = tid; i < EX_HIST; i += EX_THREADS)
+            if (s_hist[i]) atomicAdd(bucket_hist + i, (unsigned long long)s_hist[i]);
     }
 }
 
@@ -346,7 +424,7 @@ template <typename P>
 struct ChunkSorter {
     Index& ix;
     const SymTab& tab;
-    int b, S;
+    int b, S0, S;  // S0 symbols in the round-0 key, S in every refinement key
     cudaStream_t st;
     BuildTimers& timers;
 
@@ -355,7 +433,7 @@ struct ChunkSorter {
     int run(u64* k[2], P* v[2], u64 m) {
         const int keybits = b * S;
         timers.begin(st);
-        int c = rs::radix_sort_pairs<P>(k[0], k[1], v[0], v[1], m, 0, keybits, st);
+        int c = rs::radix_sort_pairs<P>(k[0], k[1], v[0], v[1], m, 0, b * S0, st);
         timers.end(st);
         u64* keys = k[c];
         P* vals = v[c];
@@ -364,7 +442,7 @@ struct ChunkSorter {
         DevBuf<P> pay;
         u64 wm = 0, ngroups = 0;
         compact<false>(keys, nullptr, nullptr, vals, m, widx, pay, gid, wm, ngroups);
-        i64 depth = S;
+        i64 depth = S0;
         const int tiebits = ix.bits1 + ix.bits2;
         const int sortbits = keybits > tiebits ? keybits : tiebits;
         while (wm > 0) {
@@ -440,7 +518,19 @@ template <typename P>
 static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t st) {
     const i64 n = ix.n;
     BuildTimers timers;
-    const int keybits = b * S;
+    // Round-0 key length: enough symbols that random text is already (almost) tie-free, log2(n) + 10 bits, instead of
+    // all S that fit 64 bits — every 8 key bits saved is one full radix pass over the chunk.  Texts with long repeats
+    // just leave more suffixes to the refinement rounds (which always use S symbols).  CDB_SA_KEY_SLACK overrides.
+    int S0 = S;
+    {
+        int slack = 10;
+        if (const char* e = getenv("CDB_SA_KEY_SLACK")) slack = atoi(e);
+        int need = slack;
+        while (need - slack < 62 && ((i64)1 << (need - slack)) < n) ++need;
+        const int want = (need + b - 1) / b;
+        if (want < S0) S0 = want < 1 ? 1 : want;
+    }
+    const int keybits = b * S0;
     // workspace -> chunk capacity
     size_t free_b = 0, total_b = 0;
     CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -463,18 +553,22 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         if (n > cap && cap < 2 * rs::TILE)
             throw Error(CDB_ERR_NOMEM, "not enough device memory for the suffix-array build workspace");
     }
-    const unsigned ex_grid = (unsigned)ceil_div(n, EX_TILE);
+    const i64 ex_tiles = ceil_div(n, EX_TILE);
+    const unsigned ex_grid = (unsigned)std::min<i64>(ex_tiles, (i64)kNumSMs * 8);
+    DevBuf<i64> tile_doc((size_t)ex_tiles + 1, st);
+    tile_doc_kernel<<<(unsigned)ceil_div(ex_tiles + 1, 256), 256, 0, st>>>(ix.d_off, ix.nd, n, ex_tiles, tile_doc.p);
+    CDB_LAUNCH_CHECK();
     if (n <= cap) {
         // ---- one chunk: the sorted value buffer becomes the suffix array itself
         ix.chunks = 1;
         DevBuf<u64> k0(n, st), k1(n, st);
         DevBuf<P> v0(n, st), v1(n, st);
-        extract_kernel<P, 1><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, 0, 0, 0,
-                                                             k0.p, v0.p, nullptr, nullptr);
+        extract_kernel<P, 1><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, tile_doc.p, ix.nd, n, ex_tiles, tab, b, S0,
+                                                             ix.bits1, 0, 0, 0, k0.p, v0.p, nullptr, nullptr);
         CDB_LAUNCH_CHECK();
         u64* k[2] = {k0.p, k1.p};
         P* v[2] = {v0.p, v1.p};
-        ChunkSorter<P> cs{ix, tab, b, S, st, timers};
+        ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
         int c = cs.run(k, v, (u64)n);
         CDB_CUDA(cudaStreamSynchronize(st));
         ix.d_sa = c ? (void*)v1.detach() : (void*)v0.detach();
@@ -487,8 +581,8 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     const u32 nbuckets = 1u << cb;
     DevBuf<unsigned long long> d_hist(nbuckets + 1, st);
     CDB_CUDA(cudaMemsetAsync(d_hist.p, 0, d_hist.bytes(), st));
-    extract_kernel<P, 0><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, cbshift, 0, 0,
-                                                         nullptr, nullptr, nullptr, d_hist.p);
+    extract_kernel<P, 0><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, tile_doc.p, ix.nd, n, ex_tiles, tab, b, S0,
+                                                         ix.bits1, cbshift, 0, 0, nullptr, nullptr, nullptr, d_hist.p);
     CDB_LAUNCH_CHECK();
     std::vector<unsigned long long> hist(nbuckets);
     CDB_CUDA(cudaMemcpyAsync(hist.data(), d_hist.p, nbuckets * 8, cudaMemcpyDeviceToHost, st));
@@ -507,12 +601,12 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         if (cnt > 0) {
             ix.chunks++;
             CDB_CUDA(cudaMemsetAsync(cursor, 0, 8, st));
-            extract_kernel<P, 2><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, ix.nd, n, tab, b, S, ix.bits1, cbshift,
-                                                                 blo, bhi, k0.p, v0.p, cursor, nullptr);
+            extract_kernel<P, 2><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, tile_doc.p, ix.nd, n, ex_tiles, tab, b, S0,
+                                                                 ix.bits1, cbshift, blo, bhi, k0.p, v0.p, cursor, nullptr);
             CDB_LAUNCH_CHECK();
             u64* k[2] = {k0.p, k1.p};
             P* v[2] = {v0.p, v1.p};
-            ChunkSorter<P> cs{ix, tab, b, S, st, timers};
+            ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
             int c = cs.run(k, v, (u64)cnt);
             copy_kernel<P><<<kNumSMs * 8, 256, 0, st>>>(v[c], sa.p + sa_base, (u64)cnt);
             CDB_LAUNCH_CHECK();

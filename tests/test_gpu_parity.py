@@ -221,3 +221,23 @@ def test_prefix_directory_on_and_off(monkeypatch):
         for q in range(len(pats)):
             assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], want[q]), (bits, pats[q])
         ix.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "auto"])
+def test_highlight_spans_both_enumerations(mode, monkeypatch):
+    """Spans from suffix-array positions (CDB_SPANS_SCAN=0), from a direct scan of the requested documents (=1) and
+    with the cost-based choice must all equal the reference highlighter's spans (database.cpp:58-77)."""
+    if mode != "auto":
+        monkeypatch.setenv("CDB_SPANS_SCAN", mode)
+    text, off, ids = corpora.ragged(1500, 120, seed=81, alphabet=b"abc")
+    ix = build(text, off, ids)
+    kwsets = [[b"ab"], [b"a", b"bca"], [b"abc", b"cab", b"bb"], [b"c" * 5], [b"zz"], [b"abcabc", b"b"]]
+    docs = [0, 7, 7, 1499, 3, 250, 1000]
+    for kws in kwsets:
+        got = ix.spans(kws, docs)
+        for d, sp in zip(docs, got):
+            t = text[off[d]:off[d + 1]].tobytes()
+            assert np.array_equal(sp, oracle.port.spans(kws, t)), (kws, d)
+            if oracle.ref_available():
+                assert cdb.splice(t, sp, b"<", b">") == oracle.ref_render(kws, t, b"<", b">")
+    ix.close()
