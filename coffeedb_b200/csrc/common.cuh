@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -84,6 +85,36 @@ struct DevBuf {
     T* detach() { T* q = p; p = nullptr; n = 0; return q; }
     ~DevBuf() { release(); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// Large, long-lived or build-sized device buffer: plain cudaMalloc / cudaFree.  Growing the stream-ordered pool by
+// tens of gigabytes goes through the virtual-memory-management path and costs seconds at the 10 GB configuration;
+// it would also keep the build workspace inside the pool after the build.
+template <typename T>
+struct BigBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    BigBuf() {}
+    explicit BigBuf(size_t count) { alloc(count); }
+    BigBuf(const BigBuf&) = delete;
+    BigBuf& operator=(const BigBuf&) = delete;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (const char* e = getenv("CDB_BIGBUF_POOL")) pooled = atoi(e) != 0;  // experiment knob
+        if (pooled)
+            CDB_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), nullptr));
+        else
+            CDB_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    T* detach() { T* q = p; p = nullptr; n = 0; return q; }
+    ~BigBuf() { release(); }
+    bool pooled = false;
 };
 
 inline int ceil_div_i(i64 a, i64 b) { return (int)((a + b - 1) / b); }

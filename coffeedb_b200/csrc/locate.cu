@@ -16,6 +16,8 @@
 //                          row counts are known before gather_kernel runs and take part in its scan.
 // All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 
 #include "index.cuh"
@@ -478,29 +480,69 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
 constexpr int kTrU = 4;
 constexpr int kTrWarps = 8;
 
+// kTrU x 32 consecutive entries of the item, starting at flat index i0.  FULL: all of them exist.
+template <bool FULL>
+__device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs, const u64* __restrict__ ids,
+                                                 i64* __restrict__ pairs, const u32* s_excl, const u64* s_adj, u32 i0,
+                                                 u32 tot, int lane, u64 pol_keep, u64 pol_stream) {
+    u64 p[kTrU], cp[kTrU];
+#pragma unroll
+    for (int u = 0; u < kTrU; ++u) {
+        const u32 idx = i0 + u * 32 + lane;
+        if (FULL || idx < tot) {
+            int j = 0;  // largest j with excl[j] <= idx
+#pragma unroll
+            for (int st = 16; st; st >>= 1)
+                if (s_excl[j + st] <= idx) j += st;
+            p[u] = s_adj[j] + idx;
+            cp[u] = ld_hint_u64(cpairs + p[u], pol_stream);
+        }
+    }
+    // ptxas otherwise sinks every load next to its use and runs the kTrU chains one after another (one request in
+    // flight per lane); a warp barrier between the phases keeps the kTrU loads of a phase together
+    __syncwarp();
+    longlong2 v[kTrU];
+#pragma unroll
+    for (int u = 0; u < kTrU; ++u) {
+        const u32 idx = i0 + u * 32 + lane;
+        if (FULL || idx < tot) {
+            v[u].x = (i64)ld_hint_u64(ids + (u32)cp[u], pol_keep);
+            v[u].y = (i64)(cp[u] >> 32);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kTrU; ++u) {
+        const u32 idx = i0 + u * 32 + lane;
+        if (FULL || idx < tot) st_hint_v2(pairs + 2 * p[u], v[u], pol_stream);
+    }
+}
+
 __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __restrict__ cpairs,
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
                                                                   const i64* __restrict__ ids, i64* __restrict__ pairs,
-                                                                  i64 npat, int nranges, int mode,
+                                                                  i64 q_lo, i64 npat, int nranges,
                                                                   unsigned long long* ticket) {
-    __shared__ u32 s_excl[kTrWarps][33];
+    __shared__ u32 s_excl[kTrWarps][32];
     __shared__ u64 s_adj[kTrWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 ntile = (npat + 31) >> 5;
+    // this launch covers the patterns [q_lo, npat)
+    const i64 ntile = (npat - q_lo + 31) >> 5;
     const i64 nitems = ntile * nranges;
     const u64 pol_keep = l2_policy_evict_last();
     const u64 pol_stream = l2_policy_evict_first();
     // Items are handed out through one global ticket, in order: at any moment all warps of the grid are within a few
     // thousand items of each other, i.e. inside one (at a range change: two) slices of ids[].  A static item
-    // stride lets warps drift several ranges apart and the slices in use no longer fit L2 together.
+    // stride lets warps drift several ranges apart and the slices in use no longer fit L2 together (measured:
+    // 45.6 GB of DRAM reads per 10^6 patterns at cfg3 against 15.6 GB with the ticket).
     for (;;) {
         i64 item = 0;
         if (lane == 0) item = (i64)atomicAdd(ticket, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
         const int r = (int)(item / ntile);
-        const i64 q = (item % ntile) * 32 + lane;
+        const i64 q = q_lo + (item - (i64)r * ntile) * 32 + lane;
         u32 len = 0;
         u64 base = 0;
         if (q < npat) {
@@ -521,40 +563,11 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         s_excl[warp][lane] = incl - len;
         s_adj[warp][lane] = base - (incl - len);
         __syncwarp();
-        for (u32 i0 = 0; i0 < tot; i0 += 32 * kTrU) {
-            u64 p[kTrU], cp[kTrU];
-            longlong2 v[kTrU];
-#pragma unroll
-            for (int u = 0; u < kTrU; ++u) {
-                const u32 idx = i0 + u * 32 + lane;
-                p[u] = ~0ull;
-                if (idx < tot) {
-                    int j = 0;  // largest j with excl[j] <= idx
-#pragma unroll
-                    for (int st = 16; st; st >>= 1)
-                        if (s_excl[warp][j + st] <= idx) j += st;
-                    p[u] = s_adj[warp][j] + idx;
-                    cp[u] = (mode & 4) ? ld_stream_u64(cpairs + p[u]) : ld_hint_u64(cpairs + p[u], pol_stream);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kTrU; ++u)
-                if (p[u] != ~0ull) {
-                    const u64* ip = reinterpret_cast<const u64*>(ids) + (u32)cp[u];
-                    v[u].x = (mode & 3) == 0 ? (i64)ld_hint_u64(ip, pol_keep)
-                             : (mode & 3) == 1 ? (i64)__ldg(ip)
-                                               : (i64)ld_stream_u64(ip);
-                    v[u].y = (i64)(cp[u] >> 32);
-                }
-#pragma unroll
-            for (int u = 0; u < kTrU; ++u)
-                if (p[u] != ~0ull) {
-                    if (mode & 4)
-                        __stcs(reinterpret_cast<longlong2*>(pairs + 2 * p[u]), v[u]);
-                    else
-                        st_hint_v2(pairs + 2 * p[u], v[u], pol_stream);
-                }
-        }
+        const u64* idp = reinterpret_cast<const u64*>(ids);
+        u32 i0 = 0;
+        for (; i0 + 32 * kTrU <= tot; i0 += 32 * kTrU)
+            translate_rounds<true>(cpairs, idp, pairs, s_excl[warp], s_adj[warp], i0, tot, lane, pol_keep, pol_stream);
+        if (i0 < tot) translate_rounds<false>(cpairs, idp, pairs, s_excl[warp], s_adj[warp], i0, tot, lane, pol_keep, pol_stream);
     }
 }
 
@@ -638,6 +651,28 @@ static void ids_ranges(i64 nd, int* nranges, int* rshift) {
     *nranges = (int)ceil_div(nd > 0 ? nd : 1, (i64)1 << sh);
 }
 
+constexpr int kMaxChunks = 16;
+
+// side stream + events of one chunked locate call
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[kMaxChunks] = {};
+    cudaEvent_t done = nullptr;
+    void create() {
+        CDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto& e : ev) CDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CDB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    }
+    ~SideStream() {
+        if (!s) return;
+        cudaStreamSynchronize(s);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (done) cudaEventDestroy(done);
+        cudaStreamDestroy(s);
+    }
+};
+
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
@@ -647,7 +682,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(5, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
+    DevBuf<unsigned long long> counters(4 + kMaxChunks, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
     DevBuf<u32> large_list(npat, st);
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -713,32 +748,67 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     const u64 cap_pairs = hc[1] + nu;
     int nranges, rshift;
     ids_ranges(ix.nd, &nranges, &rshift);
+    const auto t_alloc0 = std::chrono::steady_clock::now();
     DevBuf<u64> cpairs((size_t)cap_pairs, st);
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
+    const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
+    cudaEvent_t dbg_ev = nullptr;
+    if (dbg) {
+        fprintf(stderr, "[cdb] locate: result/temporary allocation took %.3f ms on the host (%.2f GB)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc0).count(),
+                (double)cap_pairs * 24 / 1e9);
+        cudaEventCreate(&dbg_ev);
+        cudaEventRecord(dbg_ev, st);
+    }
     const size_t smem = (size_t)kTileWarps * kWarpSmemBytes;
     CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p, status.p,
-                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
-                                                                       cpairs.p, seg.p, nranges, rshift);
-    CDB_LAUNCH_CHECK();
-    CDB_CUDA(cudaEventRecord(ev[4], st));
-    // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
-    {
-        const i64 nitems = ceil_div(npat, 32) * nranges;
-        static int per_sm = 0;  // resident CTAs per SM: the grid is exactly one wave
-        if (!per_sm) {
-            int v = 0;
-            CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
-            per_sm = v > 0 ? v : 1;
+    static int per_sm = 0;  // resident translate CTAs per SM: its grid is exactly one wave
+    if (!per_sm) {
+        int v = 0;
+        CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
+        per_sm = v > 0 ? v : 1;
+    }
+    // The batch is cut into chunks of patterns: gather (ALU-bound: the sort) of chunk c+1 runs on `st` while translate
+    // (memory-bound) of chunk c runs on a side stream.  Look-back status words and the gather ticket run on across
+    // chunks (launches on one stream execute in order), so CSR offsets stay global.
+    int nchunks = 1;
+    if (const char* e = getenv("CDB_LOCATE_CHUNKS")) nchunks = atoi(e);
+    if (nchunks < 1 || npat < 65536) nchunks = 1;
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    const i64 chunk_pat = ceil_div(ceil_div(npat, nchunks), 32) * 32;
+    SideStream side;
+    if (nchunks > 1) side.create();
+    cudaStream_t sb = nchunks > 1 ? side.s : st;
+    float tr_ms = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const i64 q0 = (i64)c * chunk_pat, q1 = std::min<i64>(npat, q0 + chunk_pat);
+        if (q0 >= q1) break;
+        const i64 t0 = q0 / kTileWarps, t1 = ceil_div(q1, kTileWarps);
+        gather_kernel<SAT><<<(unsigned)(t1 - t0), kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
+                                                                              status.p, reinterpret_cast<u32*>(counters.p + 3),
+                                                                              row_off.p, cpairs.p, seg.p, nranges, rshift);
+        CDB_LAUNCH_CHECK();
+        if (nchunks > 1) {
+            CDB_CUDA(cudaEventRecord(side.ev[c], st));
+            CDB_CUDA(cudaStreamWaitEvent(sb, side.ev[c], 0));
+        } else {
+            CDB_CUDA(cudaEventRecord(ev[4], st));
         }
+        // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
+        const i64 nitems = ceil_div(q1 - q0, 32) * nranges;
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
-        const char* em = getenv("CDB_TR_MODE");
-        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
-                                                         em ? atoi(em) : 1, counters.p + 4);
+        translate_kernel<<<grid, kTrWarps * 32, 0, sb>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, q0, q1, nranges,
+                                                         counters.p + 4 + c);
         CDB_LAUNCH_CHECK();
     }
+    if (nchunks > 1) {
+        CDB_CUDA(cudaEventRecord(ev[4], st));  // end of the last gather
+        CDB_CUDA(cudaEventRecord(side.done, sb));
+        CDB_CUDA(cudaStreamWaitEvent(st, side.done, 0));
+    }
     CDB_CUDA(cudaEventRecord(ev[5], st));
+    (void)tr_ms;
     if (nl > 0 && nu > 0) {
         const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
         large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, row_off.p,
@@ -749,6 +819,15 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(ev[6], st));
     CDB_CUDA(cudaStreamSynchronize(st));
+    if (dbg) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ev[3], dbg_ev);
+        cudaEventElapsedTime(&b, dbg_ev, ev[4]);
+        size_t fr = 0, to = 0;
+        cudaMemGetInfo(&fr, &to);
+        fprintf(stderr, "[cdb] locate: device time ev3->after-alloc %.3f ms, after-alloc->gather-end %.3f ms; free %.1f GB\n", a, b, fr / 1e9);
+        cudaEventDestroy(dbg_ev);
+    }
     {
         LocateStats& ls = g_locate_stats;
         cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);

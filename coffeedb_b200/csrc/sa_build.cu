@@ -561,8 +561,8 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     if (n <= cap) {
         // ---- one chunk: the sorted value buffer becomes the suffix array itself
         ix.chunks = 1;
-        DevBuf<u64> k0(n, st), k1(n, st);
-        DevBuf<P> v0(n, st), v1(n, st);
+        BigBuf<u64> k0(n), k1(n);
+        BigBuf<P> v0(n), v1(n);
         extract_kernel<P, 1><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, tile_doc.p, ix.nd, n, ex_tiles, tab, b, S0,
                                                              ix.bits1, 0, 0, 0, k0.p, v0.p, nullptr, nullptr);
         CDB_LAUNCH_CHECK();
@@ -587,9 +587,9 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     std::vector<unsigned long long> hist(nbuckets);
     CDB_CUDA(cudaMemcpyAsync(hist.data(), d_hist.p, nbuckets * 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
-    DevBuf<P> sa(n, st);
-    DevBuf<u64> k0(cap, st), k1(cap, st);
-    DevBuf<P> v0(cap, st), v1(cap, st);
+    BigBuf<P> sa(n);
+    BigBuf<u64> k0(cap), k1(cap);
+    BigBuf<P> v0(cap), v1(cap);
     unsigned long long* cursor = d_hist.p + nbuckets;
     i64 sa_base = 0;
     u32 blo = 0;

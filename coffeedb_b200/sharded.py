@@ -46,11 +46,22 @@ class ShardedResult:
 
     def __init__(self, row_off, pairs, shard_rows, occurrences, rank, keep=None):
         self.row_off, self.pairs, self.shard_rows, self.occurrences = row_off, pairs, shard_rows, occurrences
-        tot = shard_rows.sum(dim=0)
-        self.global_row_off = torch.zeros(tot.numel() + 1, dtype=torch.int64, device=tot.device)
-        torch.cumsum(tot, 0, out=self.global_row_off[1:])
-        self.rank_base = shard_rows[:rank].sum(dim=0)
+        self.rank = rank
+        self._gro = None
         self._keep = keep  # owner of the device buffers row_off / pairs alias
+
+    @property
+    def global_row_off(self):
+        """Scan of the per-shard row lengths in rank order (computed on first use)."""
+        if self._gro is None:
+            tot = self.shard_rows.sum(dim=0)
+            self._gro = torch.zeros(tot.numel() + 1, dtype=torch.int64, device=tot.device)
+            torch.cumsum(tot, 0, out=self._gro[1:])
+        return self._gro
+
+    @property
+    def rank_base(self):
+        return self.shard_rows[: self.rank].sum(dim=0)
 
     @property
     def npat(self) -> int:
@@ -160,14 +171,14 @@ class ShardedStringIndex:
             d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
         npat = d_off.numel() - 1
         row_off, pairs, occ, keep = self.locate_local(d_pat, d_off)
-        rows = (row_off[1:] - row_off[:-1]).contiguous()
-        shard_rows = torch.empty(self.world * npat, dtype=torch.int64, device=self.device)
-        occ = occ.clone()
+        rows = row_off[1:] - row_off[:-1]
         if self.world > 1:
-            dist.all_gather_into_tensor(shard_rows, rows, group=self.group)
+            shard_rows = torch.empty(self.world * npat, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(shard_rows, rows.contiguous(), group=self.group)
+            occ = occ.clone()
             dist.all_reduce(occ, group=self.group)
         else:
-            shard_rows.copy_(rows)
+            shard_rows = rows
         return ShardedResult(row_off, pairs, shard_rows.view(self.world, npat), occ, self.rank, keep)
 
     def gather_rows(self, res: ShardedResult, dst: int = 0):

@@ -241,3 +241,47 @@ def test_highlight_spans_both_enumerations(mode, monkeypatch):
             if oracle.ref_available():
                 assert cdb.splice(t, sp, b"<", b">") == oracle.ref_render(kws, t, b"<", b">")
     ix.close()
+
+
+def test_concurrent_queries_and_rebuild():
+    """Boundary threading contract (test/test-concurrency.py): query() is re-entrant — several host
+    threads query one index at once while another index is being built (database.cpp builds the new index on locals
+    while queries run against the previous one)."""
+    import threading
+    text, off, ids = corpora.uniform(4000, 120, seed=95, lo=ord("a"), hi=ord("f"))
+    ix = build(text, off, ids)
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    pat, poff = corpora.uniform_patterns(64, 3, seed=96, lo=ord("a"), hi=ord("f"))
+    pats = [bytes(pat[poff[i]:poff[i + 1]]) for i in range(64)]
+    want = [oracle.port.query(text, off, ids, sa, b1, kw) for kw in pats]
+    errors = []
+
+    def querier(tid):
+        try:
+            for it in range(20):
+                q = (tid * 7 + it) % len(pats)
+                got = np.array(ix.query(pats[q]), np.int64).reshape(-1, 2)
+                assert np.array_equal(got, want[q]), pats[q]
+                ro, pr = ix.locate_batch(pats[q:q + 5])
+                for j in range(len(ro) - 1):
+                    assert np.array_equal(pr[ro[j]:ro[j + 1]], want[q + j])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def builder():
+        try:
+            for seed in range(3):
+                t2, o2, i2 = corpora.uniform(3000, 100, seed=200 + seed)
+                other = build(t2, o2, i2)
+                assert other.info()["n"] == 300000
+                other.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=querier, args=(t,)) for t in range(8)] + [threading.Thread(target=builder)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    ix.close()
