@@ -101,9 +101,6 @@ static void keep_pool_memory(int dev) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    // experiment knob: L2 -> DRAM fetch granularity hint (bytes; 32/64/128) for the random-probe kernels
-    if (const char* e = getenv("CDB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
-    if (const char* e = getenv("CDB_L2_PERSIST_MB")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e) << 20);
 }
 
 }  // namespace cdb

@@ -16,8 +16,6 @@
 //                          row counts are known before gather_kernel runs and take part in its scan.
 // All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
 #include <algorithm>
-#include <chrono>
-#include <cstdio>
 #include <cstdlib>
 
 #include "index.cuh"
@@ -522,13 +520,11 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
                                                                   const i64* __restrict__ ids, i64* __restrict__ pairs,
-                                                                  i64 q_lo, i64 npat, int nranges,
-                                                                  unsigned long long* ticket) {
+                                                                  i64 npat, int nranges, unsigned long long* ticket) {
     __shared__ u32 s_excl[kTrWarps][32];
     __shared__ u64 s_adj[kTrWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // this launch covers the patterns [q_lo, npat)
-    const i64 ntile = (npat - q_lo + 31) >> 5;
+    const i64 ntile = (npat + 31) >> 5;
     const i64 nitems = ntile * nranges;
     const u64 pol_keep = l2_policy_evict_last();
     const u64 pol_stream = l2_policy_evict_first();
@@ -542,7 +538,7 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
         const int r = (int)(item / ntile);
-        const i64 q = q_lo + (item - (i64)r * ntile) * 32 + lane;
+        const i64 q = (item - (i64)r * ntile) * 32 + lane;
         u32 len = 0;
         u64 base = 0;
         if (q < npat) {
@@ -651,28 +647,6 @@ static void ids_ranges(i64 nd, int* nranges, int* rshift) {
     *nranges = (int)ceil_div(nd > 0 ? nd : 1, (i64)1 << sh);
 }
 
-constexpr int kMaxChunks = 16;
-
-// side stream + events of one chunked locate call
-struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t ev[kMaxChunks] = {};
-    cudaEvent_t done = nullptr;
-    void create() {
-        CDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        for (auto& e : ev) CDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CDB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    }
-    ~SideStream() {
-        if (!s) return;
-        cudaStreamSynchronize(s);
-        for (auto& e : ev)
-            if (e) cudaEventDestroy(e);
-        if (done) cudaEventDestroy(done);
-        cudaStreamDestroy(s);
-    }
-};
-
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
@@ -682,7 +656,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(4 + kMaxChunks, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
+    DevBuf<unsigned long long> counters(5, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
     DevBuf<u32> large_list(npat, st);
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -748,67 +722,31 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     const u64 cap_pairs = hc[1] + nu;
     int nranges, rshift;
     ids_ranges(ix.nd, &nranges, &rshift);
-    const auto t_alloc0 = std::chrono::steady_clock::now();
     DevBuf<u64> cpairs((size_t)cap_pairs, st);
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
-    const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
-    cudaEvent_t dbg_ev = nullptr;
-    if (dbg) {
-        fprintf(stderr, "[cdb] locate: result/temporary allocation took %.3f ms on the host (%.2f GB)\n",
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc0).count(),
-                (double)cap_pairs * 24 / 1e9);
-        cudaEventCreate(&dbg_ev);
-        cudaEventRecord(dbg_ev, st);
-    }
     const size_t smem = (size_t)kTileWarps * kWarpSmemBytes;
     CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static int per_sm = 0;  // resident translate CTAs per SM: its grid is exactly one wave
-    if (!per_sm) {
-        int v = 0;
-        CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
-        per_sm = v > 0 ? v : 1;
-    }
-    // The batch is cut into chunks of patterns: gather (ALU-bound: the sort) of chunk c+1 runs on `st` while translate
-    // (memory-bound) of chunk c runs on a side stream.  Look-back status words and the gather ticket run on across
-    // chunks (launches on one stream execute in order), so CSR offsets stay global.
-    int nchunks = 1;
-    if (const char* e = getenv("CDB_LOCATE_CHUNKS")) nchunks = atoi(e);
-    if (nchunks < 1 || npat < 65536) nchunks = 1;
-    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
-    const i64 chunk_pat = ceil_div(ceil_div(npat, nchunks), 32) * 32;
-    SideStream side;
-    if (nchunks > 1) side.create();
-    cudaStream_t sb = nchunks > 1 ? side.s : st;
-    float tr_ms = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const i64 q0 = (i64)c * chunk_pat, q1 = std::min<i64>(npat, q0 + chunk_pat);
-        if (q0 >= q1) break;
-        const i64 t0 = q0 / kTileWarps, t1 = ceil_div(q1, kTileWarps);
-        gather_kernel<SAT><<<(unsigned)(t1 - t0), kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
-                                                                              status.p, reinterpret_cast<u32*>(counters.p + 3),
-                                                                              row_off.p, cpairs.p, seg.p, nranges, rshift);
-        CDB_LAUNCH_CHECK();
-        if (nchunks > 1) {
-            CDB_CUDA(cudaEventRecord(side.ev[c], st));
-            CDB_CUDA(cudaStreamWaitEvent(sb, side.ev[c], 0));
-        } else {
-            CDB_CUDA(cudaEventRecord(ev[4], st));
+    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p, status.p,
+                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
+                                                                       cpairs.p, seg.p, nranges, rshift);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaEventRecord(ev[4], st));
+    // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
+    {
+        static int per_sm = 0;  // resident translate CTAs per SM: its grid is exactly one wave
+        if (!per_sm) {
+            int v = 0;
+            CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
+            per_sm = v > 0 ? v : 1;
         }
-        // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
-        const i64 nitems = ceil_div(q1 - q0, 32) * nranges;
+        const i64 nitems = ceil_div(npat, 32) * nranges;
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
-        translate_kernel<<<grid, kTrWarps * 32, 0, sb>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, q0, q1, nranges,
-                                                         counters.p + 4 + c);
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
+                                                         counters.p + 4);
         CDB_LAUNCH_CHECK();
-    }
-    if (nchunks > 1) {
-        CDB_CUDA(cudaEventRecord(ev[4], st));  // end of the last gather
-        CDB_CUDA(cudaEventRecord(side.done, sb));
-        CDB_CUDA(cudaStreamWaitEvent(st, side.done, 0));
     }
     CDB_CUDA(cudaEventRecord(ev[5], st));
-    (void)tr_ms;
     if (nl > 0 && nu > 0) {
         const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
         large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, row_off.p,
@@ -819,15 +757,6 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(ev[6], st));
     CDB_CUDA(cudaStreamSynchronize(st));
-    if (dbg) {
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, ev[3], dbg_ev);
-        cudaEventElapsedTime(&b, dbg_ev, ev[4]);
-        size_t fr = 0, to = 0;
-        cudaMemGetInfo(&fr, &to);
-        fprintf(stderr, "[cdb] locate: device time ev3->after-alloc %.3f ms, after-alloc->gather-end %.3f ms; free %.1f GB\n", a, b, fr / 1e9);
-        cudaEventDestroy(dbg_ev);
-    }
     {
         LocateStats& ls = g_locate_stats;
         cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);

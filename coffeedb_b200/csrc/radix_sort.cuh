@@ -224,7 +224,7 @@ struct SortStats {
 // constant over all keys are skipped.  Synchronises the stream once (to read the histogram).
 template <typename V>
 int radix_sort_pairs(u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int end_bit, cudaStream_t st,
-                     SortStats* stats = nullptr) {
+                     SortStats* stats = nullptr, V* final_vout = nullptr, bool* used_final = nullptr) {
     if (n <= 1 || end_bit <= begin_bit) return 0;
     PassDesc pd;
     pd.npass = 0;
@@ -274,13 +274,20 @@ int radix_sort_pairs(u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int e
     int cur = 0;
     u64* kb[2] = {k0, k1};
     V* vb[2] = {v0, v1};
+    // final_vout: the last pass that runs scatters the values straight into the caller's destination (the suffix-array
+    // slice of a chunk) instead of the ping-pong buffer; *used_final tells whether any pass ran
+    int last_run = -1;
+    for (int p = 0; p < pd.npass; ++p)
+        if (run[p]) last_run = p;
+    if (used_final) *used_final = final_vout != nullptr && last_run >= 0;
     for (int p = 0; p < pd.npass; ++p) {
         if (!run[p]) {
             if (stats) stats->passes_skipped++;
             continue;
         }
         CDB_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), st));
-        onesweep_kernel<V><<<(unsigned)ntiles, THREADS, smem, st>>>(kb[cur], kb[cur ^ 1], vb[cur], vb[cur ^ 1], n,
+        V* vdst = (final_vout != nullptr && p == last_run) ? final_vout : vb[cur ^ 1];
+        onesweep_kernel<V><<<(unsigned)ntiles, THREADS, smem, st>>>(kb[cur], kb[cur ^ 1], vb[cur], vdst, n,
                                                                     pd.shift[p], pd.mask[p], dbase + (size_t)p * RADIX,
                                                                     status.p, counter.p + p);
         CDB_LAUNCH_CHECK();

@@ -428,15 +428,20 @@ struct ChunkSorter {
     cudaStream_t st;
     BuildTimers& timers;
 
-    // Sorts the m (key, packed) pairs in (k[0], v[0]) completely; returns the index of the buffer whose
-    // values hold the finished suffix-array slice.
-    int run(u64* k[2], P* v[2], u64 m) {
+    // Sorts the m (key, packed) pairs in (k[0], v[0]) completely; returns where the finished suffix-array slice is:
+    // `dest` when given (the last radix pass scatters straight into it), else one of v[0] / v[1].
+    P* run(u64* k[2], P* v[2], u64 m, P* dest = nullptr) {
         const int keybits = b * S;
         timers.begin(st);
-        int c = rs::radix_sort_pairs<P>(k[0], k[1], v[0], v[1], m, 0, b * S0, st);
+        bool used = false;
+        int c = rs::radix_sort_pairs<P>(k[0], k[1], v[0], v[1], m, 0, b * S0, st, nullptr, dest, &used);
         timers.end(st);
         u64* keys = k[c];
-        P* vals = v[c];
+        P* vals = used ? dest : v[c];
+        if (dest && !used && m) {  // no pass ran (a single distinct key): the input order is the result
+            CDB_CUDA(cudaMemcpyAsync(dest, v[c], m * sizeof(P), cudaMemcpyDeviceToDevice, st));
+            vals = dest;
+        }
         // round-0 ties -> worklist
         DevBuf<u32> widx, gid;
         DevBuf<P> pay;
@@ -484,7 +489,7 @@ struct ChunkSorter {
             ngroups = ng2;
             depth += S;
         }
-        return c;
+        return vals;
     }
 
     template <bool HasGid>
@@ -539,6 +544,7 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     i64 cap;
     {
         size_t ws = ix.opt.workspace_bytes > 0 ? (size_t)ix.opt.workspace_bytes : 0;
+        if (const char* e = getenv("CDB_BUILD_WORKSPACE_MB")) ws = (size_t)atoll(e) << 20;  // profiling aid: forces chunking
         if (ws == 0) {
             // single-chunk case re-uses the value buffer as the suffix array, so it needs no separate SA
             size_t single = (size_t)n * per_item;
@@ -569,9 +575,9 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         u64* k[2] = {k0.p, k1.p};
         P* v[2] = {v0.p, v1.p};
         ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
-        int c = cs.run(k, v, (u64)n);
+        P* fin = cs.run(k, v, (u64)n);
         CDB_CUDA(cudaStreamSynchronize(st));
-        ix.d_sa = c ? (void*)v1.detach() : (void*)v0.detach();
+        ix.d_sa = fin == v1.p ? (void*)v1.detach() : (void*)v0.detach();
         ix.sort_ms = timers.total_ms();
         return;
     }
@@ -607,9 +613,7 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
             u64* k[2] = {k0.p, k1.p};
             P* v[2] = {v0.p, v1.p};
             ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
-            int c = cs.run(k, v, (u64)cnt);
-            copy_kernel<P><<<kNumSMs * 8, 256, 0, st>>>(v[c], sa.p + sa_base, (u64)cnt);
-            CDB_LAUNCH_CHECK();
+            cs.run(k, v, (u64)cnt, sa.p + sa_base);  // the chunk lands in its final suffix-array range
             sa_base += cnt;
         }
         blo = bhi;

@@ -24,3 +24,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KE
     -f -o gpurun_out/${TAG}_locate_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 3 --no-cpu-baseline \
     > gpurun_out/${TAG}_locate_cfg2.bench.log 2>&1
 ls -la gpurun_out/
+# build kernels (--set full, with source) at the 1 GB configuration, chunked like the 10 GB one (workspace cap)
+CDB_BUILD_WORKSPACE_MB=8000 timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'extract_kernel|onesweep_kernel|ties_|hist_kernel' -c 14 \
+    -f -o gpurun_out/${TAG}_build_cfg2 python bench.py --workload cfg2 --steps 1 --warmup 3 --no-cpu-baseline \
+    > gpurun_out/${TAG}_build_cfg2.bench.log 2>&1
+ls -la gpurun_out/
