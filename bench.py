@@ -386,9 +386,16 @@ def run_ours(args):
     dom_ms, dom_bytes = kernels[dom]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = (alg["search"] + alg["gather"]) * npat
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of the same configuration
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_cfg3.json")
+    if world == 1 and wname == "cfg3" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj.get("kernels", {}):
+            traffic, traffic_src = tj["kernels"][dom]["traffic"], tj["source"]
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
         "phases_ms": phase,
         "kernels": {k: {"ms": v[0], "algorithmic_bytes": v[1],

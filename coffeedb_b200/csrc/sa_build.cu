@@ -17,6 +17,8 @@
 // The payload carried through every sort is the reference's own packed element (offset << bits1) | doc, so the
 // finished array is byte-for-byte what src/index.cpp:209-215 + the sort would hold (up to note N2 ties).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -123,22 +125,15 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 t0 = tile * EX_TILE;
         const i64 d0 = __ldg(tile_doc + tile), d1 = __ldg(tile_doc + tile + 1);
-        // symbols of text[t0, t0 + EX_TILE + S): 16-byte loads (text is 16-byte aligned and padded)
-        {
-            const int nvec = (EX_TILE + S + 15) >> 4;
-            if (tid < nvec) {
-                uint4 v = make_uint4(0, 0, 0, 0);  // bytes past the padded end are never part of a key
-                if (t0 + (i64)tid * 16 + 16 <= n + kTextPad) v = ld_stream_v4(reinterpret_cast<const uint4*>(text + t0) + tid);
-                const u32 w[4] = {v.x, v.y, v.z, v.w};
-                u16* dst = s_sym + tid * 16;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    dst[4 * k + 0] = s_tab[w[k] & 255];
-                    dst[4 * k + 1] = s_tab[(w[k] >> 8) & 255];
-                    dst[4 * k + 2] = s_tab[(w[k] >> 16) & 255];
-                    dst[4 * k + 3] = s_tab[w[k] >> 24];
-                }
-            }
+        // symbols of text[t0, t0 + EX_TILE + S): every thread re-codes one aligned 4-byte word (text is 16-byte aligned
+        // and padded) and stores its 4 symbols with one 8-byte shared store
+        for (int w = tid; w * 4 < EX_TILE + S; w += EX_THREADS) {
+            u32 v = 0;  // bytes past the padded end are never part of a key
+            if (t0 + (i64)w * 4 + 4 <= n + kTextPad) v = ld_stream_u32(reinterpret_cast<const u32*>(text + t0) + w);
+            uint2 o;
+            o.x = (u32)s_tab[v & 255] | ((u32)s_tab[(v >> 8) & 255] << 16);
+            o.y = (u32)s_tab[(v >> 16) & 255] | ((u32)s_tab[v >> 24] << 16);
+            *reinterpret_cast<uint2*>(&s_sym[w * 4]) = o;
         }
         *reinterpret_cast<uint4*>(&s_cnt[tid * EX_IPT]) = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -593,9 +588,14 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     std::vector<unsigned long long> hist(nbuckets);
     CDB_CUDA(cudaMemcpyAsync(hist.data(), d_hist.p, nbuckets * 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
+    const auto t_a0 = std::chrono::steady_clock::now();
     BigBuf<P> sa(n);
     BigBuf<u64> k0(cap), k1(cap);
     BigBuf<P> v0(cap), v1(cap);
+    if (getenv("CDB_DEBUG_TIMING"))
+        fprintf(stderr, "[cdb] build: cudaMalloc of SA (%.1f GB) + workspace (%.1f GB) took %.1f ms\n", n * sizeof(P) / 1e9,
+                cap * (16.0 + 2 * sizeof(P)) / 1e9,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
     unsigned long long* cursor = d_hist.p + nbuckets;
     i64 sa_base = 0;
     u32 blo = 0;
@@ -800,6 +800,7 @@ void build_index(Index& ix, cudaStream_t st) {
     CDB_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
+    if (getenv("CDB_DEBUG_TIMING")) fprintf(stderr, "[cdb] build: %.1f ms between the first and last event, sort %.1f ms\n", ms, ix.sort_ms);
     ix.build_ms = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
