@@ -86,13 +86,13 @@ constexpr size_t onesweep_smem_bytes() {
 
 // ---- one pass -----------------------------------------------------------------------------------------
 template <typename V>
-__global__ void __launch_bounds__(THREADS) onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
+__global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
                                                            const V* __restrict__ vin, V* __restrict__ vout, u64 n,
                                                            int shift, u32 dmask, const u64* __restrict__ digit_base,
                                                            u64* status, u32* tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* skeys = reinterpret_cast<u64*>(smem_raw);
-    __shared__ u32 wc[WARPS][RADIX];
+    __shared__ u16 wc[WARPS][RADIX];  // per-warp digit counts (<= 512), then exclusive offsets (<= 4096)
     __shared__ u32 bin_start[RADIX];
     __shared__ u64 gbase[RADIX];
     __shared__ u32 warp_tot[WARPS];
@@ -120,12 +120,20 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const u64* __restrict
 #pragma unroll
     for (int r = 0; r < IPT; ++r) {
         u32 d = (u32)(key[r] >> shift) & dmask;
-        u32 peers = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit: 8 ballots (ALU pipe).  MATCH.ANY does this in one instruction but runs on the
+        // ADU pipe, which the ncu capture showed 56 % busy and the kernel's limiter (profiles/README.md).
+        u32 peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < RADIX_BITS; ++bit) {
+            const bool one = (d >> bit) & 1u;
+            const u32 bal = __ballot_sync(0xffffffffu, one);
+            peers &= one ? bal : ~bal;
+        }
         int leader = __ffs(peers) - 1;
         u32 old = 0;
         if (lane == leader) {
             old = wc[warp][d];
-            wc[warp][d] = old + __popc(peers);
+            wc[warp][d] = (u16)(old + __popc(peers));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[r] = old + __popc(peers & lt);
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const u64* __restrict
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
         u32 c = wc[w][tid];
-        wc[w][tid] = run;
+        wc[w][tid] = (u16)run;
         run += c;
     }
     u64* my_status = status + tile * RADIX + tid;
@@ -276,10 +284,26 @@ int radix_sort_pairs(u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int e
     V* vb[2] = {v0, v1};
     // final_vout: the last pass that runs scatters the values straight into the caller's destination (the suffix-array
     // slice of a chunk) instead of the ping-pong buffer; *used_final tells whether any pass ran
-    int last_run = -1;
+    int last_run = -1, nrun = 0;
     for (int p = 0; p < pd.npass; ++p)
-        if (run[p]) last_run = p;
-    if (used_final) *used_final = final_vout != nullptr && last_run >= 0;
+        if (run[p]) {
+            last_run = p;
+            ++nrun;
+        }
+    // final_vout may be one of the two ping-pong buffers (a chunk sorts between its workspace and its suffix-array
+    // range).  If the natural ping-pong already ends there nothing special happens; if it ends in the other one the
+    // last pass would have to scatter in place, so the passes run naturally and one copy follows.
+    bool copy_after = false;
+    if (ValueTraits<V>::has && final_vout != nullptr && (final_vout == v0 || final_vout == v1)) {
+        V* natural_end = (nrun % 2) ? v1 : v0;
+        if (final_vout != natural_end) copy_after = nrun > 0;
+        if (used_final) *used_final = nrun > 0;
+        final_vout = nullptr;  // plain ping-pong
+        if (copy_after) final_vout = nullptr;
+    } else if (used_final) {
+        *used_final = final_vout != nullptr && last_run >= 0;
+    }
+    V* const alias_dest = copy_after ? ((nrun % 2) ? v0 : v1) : nullptr;
     for (int p = 0; p < pd.npass; ++p) {
         if (!run[p]) {
             if (stats) stats->passes_skipped++;
@@ -293,6 +317,10 @@ int radix_sort_pairs(u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int e
         CDB_LAUNCH_CHECK();
         cur ^= 1;
         if (stats) stats->passes_run++;
+    }
+    if (copy_after) {
+        if constexpr (ValueTraits<V>::has)
+            CDB_CUDA(cudaMemcpyAsync(alias_dest, vb[cur], n * sizeof(V), cudaMemcpyDeviceToDevice, st));
     }
     return cur;
 }

@@ -244,45 +244,83 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
 }
 
 // ---- tie detection + ordered compaction --------------------------------------------------------------------
+// An element is "tied" when its key (and group, in refinement rounds) equals a neighbour's; the first element of a
+// tied run is its head.  Tied elements are compacted in order into the next worklist.  A CTA covers 2048 consecutive
+// elements, warp w the 256 elements [w*256, (w+1)*256), lane l the elements r*32 + l of them (coalesced loads);
+// neighbours come from shuffles, positions from ballots.
 constexpr int TC_THREADS = 256;
 constexpr int TC_IPT = 8;
 constexpr int TC_TILE = TC_THREADS * TC_IPT;
 
 template <bool HasGid>
-__device__ __forceinline__ bool same_group(const u64* __restrict__ keys, const u32* __restrict__ gid, u64 i, u64 j) {
-    if (keys[i] != keys[j]) return false;
-    if (HasGid) return gid[i] == gid[j];
-    return true;
+__device__ __forceinline__ void tie_ballots(const u64* __restrict__ keys, const u32* __restrict__ gid, u64 m, u64 wbase,
+                                            int lane, u32 bt[TC_IPT], u32 bh[TC_IPT]) {
+    u64 k[TC_IPT];
+    u32 g[TC_IPT];
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) {
+        const u64 i = wbase + r * 32 + lane;
+        k[r] = i < m ? ld_stream_u64(keys + i) : 0;
+        g[r] = (HasGid && i < m) ? __ldg(gid + i) : 0;
+    }
+    // the elements just outside the warp's range
+    u64 kb = 0, ka = 0;
+    u32 gb = 0, ga = 0;
+    const bool has_b = wbase > 0 && wbase <= m, has_a = wbase + 32 * TC_IPT < m;
+    if (lane == 0 && has_b) {
+        kb = keys[wbase - 1];
+        gb = HasGid ? gid[wbase - 1] : 0;
+    }
+    if (lane == 31 && has_a) {
+        ka = keys[wbase + 32 * TC_IPT];
+        ga = HasGid ? gid[wbase + 32 * TC_IPT] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < TC_IPT; ++r) {
+        const u64 i = wbase + r * 32 + lane;
+        u64 kp = __shfl_up_sync(0xffffffffu, k[r], 1), kn = __shfl_down_sync(0xffffffffu, k[r], 1);
+        u32 gp = __shfl_up_sync(0xffffffffu, g[r], 1), gn = __shfl_down_sync(0xffffffffu, g[r], 1);
+        const u64 kp0 = r > 0 ? __shfl_sync(0xffffffffu, k[r > 0 ? r - 1 : 0], 31) : kb;
+        const u32 gp0 = r > 0 ? __shfl_sync(0xffffffffu, g[r > 0 ? r - 1 : 0], 31) : gb;
+        const u64 kn31 = r + 1 < TC_IPT ? __shfl_sync(0xffffffffu, k[r + 1 < TC_IPT ? r + 1 : r], 0) : ka;
+        const u32 gn31 = r + 1 < TC_IPT ? __shfl_sync(0xffffffffu, g[r + 1 < TC_IPT ? r + 1 : r], 0) : ga;
+        if (lane == 0) {
+            kp = kp0;
+            gp = gp0;
+        }
+        if (lane == 31) {
+            kn = kn31;
+            gn = gn31;
+        }
+        const bool valid = i < m;
+        const bool prev_ok = i > 0 && (r > 0 || lane > 0 || has_b);
+        const bool next_ok = i + 1 < m && (r + 1 < TC_IPT || lane < 31 || has_a);
+        const bool eq_prev = valid && prev_ok && kp == k[r] && (!HasGid || gp == g[r]);
+        const bool eq_next = valid && next_ok && kn == k[r] && (!HasGid || gn == g[r]);
+        const bool tied = eq_prev || eq_next;
+        bt[r] = __ballot_sync(0xffffffffu, tied);
+        bh[r] = __ballot_sync(0xffffffffu, tied && !eq_prev);
+    }
 }
 
 // packed count: low 32 bits = tied elements, high 32 bits = group heads among them
 template <bool HasGid>
-__device__ __forceinline__ void tie_flags(const u64* __restrict__ keys, const u32* __restrict__ gid, u64 m, u64 base,
-                                          bool tied[TC_IPT], bool head[TC_IPT]) {
-    bool eq_prev = base > 0 && base < m && same_group<HasGid>(keys, gid, base, base - 1);
-#pragma unroll
-    for (int r = 0; r < TC_IPT; ++r) {
-        u64 i = base + r;
-        bool eq_next = (i + 1 < m) && same_group<HasGid>(keys, gid, i + 1, i);
-        bool valid = i < m;
-        tied[r] = valid && (eq_prev || eq_next);
-        head[r] = tied[r] && !eq_prev;
-        eq_prev = eq_next;
-    }
-}
-
-template <bool HasGid>
 __global__ void __launch_bounds__(TC_THREADS) ties_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ gid,
                                                                 u64 m, u64* __restrict__ bsum) {
-    __shared__ u64 ws[32];
-    bool tied[TC_IPT], head[TC_IPT];
-    tie_flags<HasGid>(keys, gid, m, (u64)blockIdx.x * TC_TILE + (u64)threadIdx.x * TC_IPT, tied, head);
+    __shared__ u64 ws[TC_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 bt[TC_IPT], bh[TC_IPT];
+    tie_ballots<HasGid>(keys, gid, m, (u64)blockIdx.x * TC_TILE + (u64)warp * 32 * TC_IPT, lane, bt, bh);
     u64 s = 0;
 #pragma unroll
-    for (int r = 0; r < TC_IPT; ++r) s += (u64)tied[r] + ((u64)head[r] << 32);
-    u64 tot;
-    prim::block_exclusive_scan_u64(s, &tot, ws);
-    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+    for (int r = 0; r < TC_IPT; ++r) s += (u64)__popc(bt[r]) + ((u64)__popc(bh[r]) << 32);
+    if (lane == 0) ws[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int w = 0; w < TC_THREADS / 32; ++w) t += ws[w];
+        bsum[blockIdx.x] = t;
+    }
 }
 
 template <bool HasGid, typename P>
@@ -291,26 +329,32 @@ __global__ void __launch_bounds__(TC_THREADS) ties_write_kernel(const u64* __res
                                                                 u64 m, const u64* __restrict__ bsum,
                                                                 u32* __restrict__ widx_out, P* __restrict__ pay_out,
                                                                 u32* __restrict__ gid_out) {
-    __shared__ u64 ws[32];
-    bool tied[TC_IPT], head[TC_IPT];
-    const u64 base = (u64)blockIdx.x * TC_TILE + (u64)threadIdx.x * TC_IPT;
-    tie_flags<HasGid>(keys, gid, m, base, tied, head);
+    __shared__ u64 ws[TC_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 wbase = (u64)blockIdx.x * TC_TILE + (u64)warp * 32 * TC_IPT;
+    u32 bt[TC_IPT], bh[TC_IPT];
+    tie_ballots<HasGid>(keys, gid, m, wbase, lane, bt, bh);
     u64 s = 0;
 #pragma unroll
-    for (int r = 0; r < TC_IPT; ++r) s += (u64)tied[r] + ((u64)head[r] << 32);
-    u64 tot;
-    u64 ex = prim::block_exclusive_scan_u64(s, &tot, ws) + bsum[blockIdx.x];
+    for (int r = 0; r < TC_IPT; ++r) s += (u64)__popc(bt[r]) + ((u64)__popc(bh[r]) << 32);
+    if (lane == 0) ws[warp] = s;
+    __syncthreads();
+    u64 ex = bsum[blockIdx.x];
+    for (int w = 0; w < warp; ++w) ex += ws[w];
     u32 pos = (u32)ex, heads = (u32)(ex >> 32);
+    const u32 lt = lanemask_lt();
 #pragma unroll
     for (int r = 0; r < TC_IPT; ++r) {
-        if (tied[r]) {
-            heads += head[r] ? 1 : 0;
-            u64 i = base + r;
-            widx_out[pos] = HasGid ? widx_in[i] : (u32)i;
-            pay_out[pos] = pay_in[i];
-            gid_out[pos] = heads - 1;
-            ++pos;
+        if ((bt[r] >> lane) & 1u) {
+            const u64 i = wbase + r * 32 + lane;
+            const u32 o = pos + __popc(bt[r] & lt);
+            const u32 h = heads + __popc(bh[r] & (lt | (1u << lane)));  // heads up to and including this element
+            widx_out[o] = HasGid ? widx_in[i] : (u32)i;
+            pay_out[o] = pay_in[i];
+            gid_out[o] = h - 1;
         }
+        pos += __popc(bt[r]);
+        heads += __popc(bh[r]);
     }
 }
 
@@ -534,19 +578,27 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     // workspace -> chunk capacity
     size_t free_b = 0, total_b = 0;
     CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_item = 2 * (8 + sizeof(P)) + 1;  // ping-pong (key, packed) + look-back status share
+    // one chunk: ping-pong (key, packed) buffers, the value buffer that ends up sorted becomes the suffix array.
+    // several chunks: ping-pong keys + ONE value buffer — the chunk's own (still unused) suffix-array range is the
+    // other value buffer, and the last radix pass lands in it.
+    const size_t per_item_single = 2 * (8 + sizeof(P)) + 1;  // + look-back status share
+    const size_t per_item_chunk = 2 * 8 + sizeof(P) + 1;
     const size_t sa_bytes = (size_t)n * sizeof(P);
     i64 cap;
     {
         size_t ws = ix.opt.workspace_bytes > 0 ? (size_t)ix.opt.workspace_bytes : 0;
         if (const char* e = getenv("CDB_BUILD_WORKSPACE_MB")) ws = (size_t)atoll(e) << 20;  // profiling aid: forces chunking
+        size_t per_item = per_item_chunk;
         if (ws == 0) {
-            // single-chunk case re-uses the value buffer as the suffix array, so it needs no separate SA
-            size_t single = (size_t)n * per_item;
-            if (single < (size_t)(free_b * 0.85))
-                ws = single + per_item * rs::TILE;
-            else
+            size_t single = (size_t)n * per_item_single;
+            if (single < (size_t)(free_b * 0.85)) {
+                ws = single + per_item_single * rs::TILE;
+                per_item = per_item_single;
+            } else {
                 ws = free_b > sa_bytes ? (size_t)((free_b - sa_bytes) * 0.80) : 0;
+            }
+        } else if ((size_t)n * per_item_single <= ws) {
+            per_item = per_item_single;
         }
         cap = (i64)(ws / per_item);
         const i64 hard = ((i64)1 << 32) - 2 * rs::TILE;
@@ -591,10 +643,10 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     const auto t_a0 = std::chrono::steady_clock::now();
     BigBuf<P> sa(n);
     BigBuf<u64> k0(cap), k1(cap);
-    BigBuf<P> v0(cap), v1(cap);
+    BigBuf<P> v0(cap);
     if (getenv("CDB_DEBUG_TIMING"))
         fprintf(stderr, "[cdb] build: cudaMalloc of SA (%.1f GB) + workspace (%.1f GB) took %.1f ms\n", n * sizeof(P) / 1e9,
-                cap * (16.0 + 2 * sizeof(P)) / 1e9,
+                cap * (16.0 + sizeof(P)) / 1e9,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
     unsigned long long* cursor = d_hist.p + nbuckets;
     i64 sa_base = 0;
@@ -607,13 +659,17 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         if (cnt > 0) {
             ix.chunks++;
             CDB_CUDA(cudaMemsetAsync(cursor, 0, 8, st));
+            // values ping-pong between v0 and the chunk's final suffix-array range; they start in the one that makes an
+            // all-passes-run sort end in the range (a skipped pass costs one copy, see radix_sort_pairs)
+            P* slice = sa.p + sa_base;
+            const int planned = (keybits + rs::RADIX_BITS - 1) / rs::RADIX_BITS;
+            P* v[2] = {planned % 2 ? v0.p : slice, planned % 2 ? slice : v0.p};
             extract_kernel<P, 2><<<ex_grid, EX_THREADS, 0, st>>>(ix.d_text, ix.d_off, tile_doc.p, ix.nd, n, ex_tiles, tab, b, S0,
-                                                                 ix.bits1, cbshift, blo, bhi, k0.p, v0.p, cursor, nullptr);
+                                                                 ix.bits1, cbshift, blo, bhi, k0.p, v[0], cursor, nullptr);
             CDB_LAUNCH_CHECK();
             u64* k[2] = {k0.p, k1.p};
-            P* v[2] = {v0.p, v1.p};
             ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
-            cs.run(k, v, (u64)cnt, sa.p + sa_base);  // the chunk lands in its final suffix-array range
+            cs.run(k, v, (u64)cnt, slice);  // the chunk lands in its final suffix-array range
             sa_base += cnt;
         }
         blo = bhi;

@@ -116,3 +116,30 @@ def brute_count(text, doc_off, ids, kw: bytes):
         if c:
             out.append((int(ids[d]), c))
     return np.array(out, np.int64).reshape(-1, 2)
+
+
+def utf8_fast(char_lens, seed: int):
+    """Vectorised config-5 flavour corpus: document d holds char_lens[d] code points, 70 % one-byte (0x20..0x7E),
+    15 % two-byte, 15 % three-byte UTF-8 sequences (valid UTF-8; bytes on both sides of 0x80 -> note N1)."""
+    rng = np.random.default_rng(seed)
+    char_lens = np.asarray(char_lens, np.int64)
+    nchar = int(char_lens.sum())
+    cls = rng.choice(np.array([1, 2, 3], np.int64), size=nchar, p=[0.70, 0.15, 0.15])
+    start = np.zeros(nchar + 1, np.int64)
+    np.cumsum(cls, out=start[1:])
+    text = np.zeros(int(start[-1]), np.uint8)
+    s = start[:-1]
+    one, two, three = cls == 1, cls == 2, cls == 3
+    text[s[one]] = rng.integers(0x20, 0x7F, size=int(one.sum()), dtype=np.uint8)
+    cp2 = rng.integers(0x80, 0x800, size=int(two.sum()))
+    text[s[two]] = 0xC0 | (cp2 >> 6)
+    text[s[two] + 1] = 0x80 | (cp2 & 0x3F)
+    cp3 = rng.integers(0x800, 0xD800, size=int(three.sum()))
+    text[s[three]] = 0xE0 | (cp3 >> 12)
+    text[s[three] + 1] = 0x80 | ((cp3 >> 6) & 0x3F)
+    text[s[three] + 2] = 0x80 | (cp3 & 0x3F)
+    cend = np.zeros(len(char_lens) + 1, np.int64)
+    np.cumsum(char_lens, out=cend[1:])
+    off = start[cend]
+    ids = np.arange(len(char_lens), dtype=np.int64) * 5 + 3
+    return text, off, ids

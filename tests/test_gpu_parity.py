@@ -285,3 +285,29 @@ def test_concurrent_queries_and_rebuild():
         t.join()
     assert not errors, errors
     ix.close()
+
+
+def test_config5_flavour_utf8_long_documents():
+    """BASELINE configs[4] flavour at test scale: valid UTF-8, ragged documents up to ~70 KB among 40 000 short ones
+    (bits1 + bits2 = 33 -> 64-bit suffix-array elements), bytes on both sides of 0x80 with n >> 4096 -> several
+    signed-radix levels of the note-N1 layout.  Bit-exact suffix array and (id, count) rows against the oracle."""
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 40, size=40000)
+    lens[rng.integers(0, 40000, size=30)] = rng.integers(20000, 50000, size=30)
+    text, off, ids = corpora.utf8_fast(lens, seed=78)
+    ix = build(text, off, ids)
+    sa, b1, w = oracle.port.build_sa(text, off)
+    inf = ix.info()
+    assert (inf["bits"], inf["width"]) == (b1, w) and w == 8
+    assert np.array_equal(ix.export_sa(), sa)
+    spat, soff = corpora.sampled_patterns(text, off, 400, 1, 9, seed=79)
+    row_off, pairs = ix.locate_batch(spat, soff)
+    for q in range(400):
+        kw = bytes(spat[soff[q]:soff[q + 1]])
+        assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+    # highlight on this layout goes through the direct document scan and must find every occurrence
+    kws = [bytes(spat[soff[q]:soff[q + 1]]) for q in (3, 17, 101)]
+    docs = [int(d) for d in np.argsort(-np.diff(off))[:3]] + [0, 5]
+    for d, sp in zip(docs, ix.spans(kws, docs)):
+        assert np.array_equal(sp, oracle.port.spans(kws, text[off[d]:off[d + 1]].tobytes()))
+    ix.close()
