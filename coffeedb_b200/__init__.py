@@ -142,10 +142,11 @@ def pack(items) -> tuple[np.ndarray, np.ndarray]:
 class StringIndex:
     """Drop-in for the reference's ``string_index`` (src/index.h:54-86)."""
 
-    def __init__(self, device: int = -1, compat_signed: bool = True, workspace_bytes: int = 0):
+    def __init__(self, device: int = -1, compat_signed: bool = True, workspace_bytes: int = 0,
+                 keep_host_copy: bool = False):
         self._L = lib()
         self._h = C.c_void_p()
-        opt = Options(device, 1 if compat_signed else 0, workspace_bytes, 0, 0)
+        opt = Options(device, 1 if compat_signed else 0, workspace_bytes, 1 if keep_host_copy else 0, 0)
         _check(self._L.cdb_create(C.byref(opt), C.byref(self._h)))
         self._keep = []  # device tensors borrowed by build_device
 

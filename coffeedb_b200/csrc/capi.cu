@@ -85,6 +85,12 @@ struct DeviceSetter {
     }
 };
 
+// The reference never updates a built index either: a new one is filled and built, then swapped in
+// (src/database.cpp:170-172, 276-281).
+static const char* const kAfterBuild =
+    "the index has been built and its host staging copy released: add to a new index (or create this one with "
+    "keep_host_copy = 1)";
+
 static void require_device() {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -181,6 +187,7 @@ cdb_status cdb_add(cdb_index* h, int64_t id, const void* value, int64_t len) {
     CDB_TRY
     Index* ix = reinterpret_cast<Index*>(h);
     if (!ix || len < 0 || (len > 0 && !value)) throw Error(CDB_ERR_ARG, "cdb_add: bad argument");
+    if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
     ix->h_ids.push_back(id);
     const u8* p = static_cast<const u8*>(value);
     ix->h_text.insert(ix->h_text.end(), p, p + len);
@@ -193,6 +200,7 @@ cdb_status cdb_add_many(cdb_index* h, const int64_t* ids, const void* text, cons
     CDB_TRY
     Index* ix = reinterpret_cast<Index*>(h);
     if (!ix || nd < 0 || (nd > 0 && (!ids || !doc_off))) throw Error(CDB_ERR_ARG, "cdb_add_many: bad argument");
+    if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
     if (nd == 0) return CDB_OK;
     const u8* p = static_cast<const u8*>(text);
     const i64 base = (i64)ix->h_text.size() - doc_off[0];
@@ -211,6 +219,7 @@ cdb_status cdb_build(cdb_index* h) {
     CDB_TRY
     Index* ix = reinterpret_cast<Index*>(h);
     if (!ix) throw Error(CDB_ERR_ARG, "cdb_build: index is NULL");
+    if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
     require_device();
     if (ix->device < 0) CDB_CUDA(cudaGetDevice(&ix->device));
     DeviceSetter ds(ix->device);
@@ -242,6 +251,7 @@ cdb_status cdb_build(cdb_index* h) {
     cudaStreamDestroy(st);
     if (!ix->opt.keep_host_copy) {
         std::vector<u8>().swap(ix->h_text);
+        ix->host_dropped = true;
     }
     return CDB_OK;
     CDB_CATCH

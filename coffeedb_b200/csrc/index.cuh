@@ -28,6 +28,7 @@ struct Index {
     std::vector<u8> h_text;
     std::vector<i64> h_off{0};
     std::vector<i64> h_ids;
+    bool host_dropped = false;  // the staging copy was released after build (keep_host_copy == 0)
     // device corpus
     const u8* d_text = nullptr;
     const i64* d_off = nullptr;

@@ -5,7 +5,7 @@
 //                          (same midpoints, same predicates), so the interval is identical even on the
 //                          not-quite-sorted arrays of note N1.  Each probe = SA element -> doc_off pair ->
 //                          16 bytes of text, compared as big-endian integers (== unsigned memcmp).
-//   K5-K7 gather_kernel  ONE launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
+//   K5-K7 gather_kernel  one launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
 //                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, bitonic
 //                          sorting network in registers (up to 32 keys per lane, SHFL for the lane strides), run-length,
 //                          then the tile's row count enters a decoupled look-back over per-tile status words,
@@ -261,47 +261,102 @@ constexpr u64 GS_INCL = 2ull << 62;
 constexpr u64 GS_MASK = (1ull << 62) - 1;
 constexpr int kMaxRanges = 64;   // doc-range partitions of ids[] used by translate_kernel (each <= ~32 MB of ids)
 
-// Bitonic sorting network over 32*R keys held in registers, R per lane, lane-blocked index i = lane*R + r, in the
-// all-ascending "flip + disperse" form: every compare-exchange puts the minimum at the lower index, so strides
-// below R are two VIMNMX per pair with no direction select, strides >= R are one SHFL + a min/max chosen by a lane
-// predicate per key.  No shared memory, no divergence.  (MATCH.ANY-based multi-split radix sorting was measured
-// first and is XU-pipe bound on B200: profiles/README.md.)
+// Bitonic sorting network over 32*R keys held in registers, R per lane, in the all-ascending "flip + disperse"
+// form: every compare-exchange puts the minimum at the lower index.  Two register layouts are used:
+//   blocked  (B): lane holds ranks lane*R + r.  Strides below R are two VIMNMX per pair with no direction select,
+//                 strides >= R cost one SHFL + a min/max chosen by a lane predicate per key (3 issue slots).
+//   striped  (T): lane holds ranks r*32 + lane.  Strides >= 32 are register pairs, and a flip pairs register r of
+//                 lane l with register r ^ (h/32-1) of lane l ^ 31: one SHFL + ONE VIMNMX per key.
+// The merge phases with three or more lane-crossing strides (h >= 256) switch to T through shared memory (padded,
+// conflict-free), do those strides there and come back for the strides below R.  The kernel is bound by the ALU pipe,
+// and the round trip trades 2 ALU instructions per key and stride for 4 LDS/STS per key and phase.
+// (MATCH.ANY-based multi-split radix sorting was measured first and is slower on B200: profiles/README.md.)
 template <int R>
-__device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane) {
+__device__ __forceinline__ int tr_addr(int i) { return (i / R) * (R + 1) + (i % R); }
+
+template <int R>
+__device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane, u32* tbuf) {
     constexpr int N = 32 * R;
 #pragma unroll
     for (int h = 2; h <= N; h <<= 1) {
-        // flip: i <-> i ^ (h-1)
-        if (h <= R) {
+        const bool striped = R >= 16 && h >= 256;  // this phase does its strides >= 32 in layout T
+        if (striped) {
+            // ---- B -> T
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int p = r ^ (h - 1);
-                if (r < p) {
-                    const u32 a = x[r], b = x[p];
-                    x[r] = min(a, b);
-                    x[p] = max(a, b);
+            for (int r = 0; r < R; ++r) tbuf[lane * (R + 1) + r] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[r] = tbuf[tr_addr<R>(r * 32 + lane)];
+            __syncwarp();
+            // flip: (r, lane) <-> (r ^ (h/32-1), lane ^ 31); the lower rank is the one with the smaller register
+            {
+                const int rm = h / 32 - 1;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int rp = r ^ rm;
+                    if (r < rp) {
+                        const u32 a = x[r], b = x[rp];
+                        const u32 ob = __shfl_xor_sync(0xffffffffu, b, 31);
+                        const u32 oa = __shfl_xor_sync(0xffffffffu, a, 31);
+                        x[r] = min(a, ob);
+                        x[rp] = max(b, oa);
+                    }
                 }
             }
-        } else {
-            const int lm = h / R - 1;
-            const bool keep_min = (lane & (h / (2 * R))) == 0;
-            if (R == 1) {
-                const u32 o = __shfl_xor_sync(0xffffffffu, x[0], lm);
-                x[0] = keep_min ? min(x[0], o) : max(x[0], o);
-            } else {
+            // disperse strides h/4 .. 32: register pairs
 #pragma unroll
-                for (int r = 0; r < R / 2; ++r) {
-                    const u32 a = x[r], b = x[R - 1 - r];
-                    const u32 oa = __shfl_xor_sync(0xffffffffu, b, lm);
-                    const u32 ob = __shfl_xor_sync(0xffffffffu, a, lm);
-                    x[r] = keep_min ? min(a, oa) : max(a, oa);
-                    x[R - 1 - r] = keep_min ? min(b, ob) : max(b, ob);
+            for (int j = h >> 2; j >= 32; j >>= 1) {
+                const int rj = j / 32;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const u32 a = x[r], b = x[r | rj];
+                        x[r] = min(a, b);
+                        x[r | rj] = max(a, b);
+                    }
+                }
+            }
+            // ---- T -> B
+#pragma unroll
+            for (int r = 0; r < R; ++r) tbuf[tr_addr<R>(r * 32 + lane)] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[r] = tbuf[lane * (R + 1) + r];
+            __syncwarp();
+        } else {
+            // flip: i <-> i ^ (h-1)
+            if (h <= R) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int p = r ^ (h - 1);
+                    if (r < p) {
+                        const u32 a = x[r], b = x[p];
+                        x[r] = min(a, b);
+                        x[p] = max(a, b);
+                    }
+                }
+            } else {
+                const int lm = h / R - 1;
+                const bool keep_min = (lane & (h / (2 * R))) == 0;
+                if (R == 1) {
+                    const u32 o = __shfl_xor_sync(0xffffffffu, x[0], lm);
+                    x[0] = keep_min ? min(x[0], o) : max(x[0], o);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R / 2; ++r) {
+                        const u32 a = x[r], b = x[R - 1 - r];
+                        const u32 oa = __shfl_xor_sync(0xffffffffu, b, lm);
+                        const u32 ob = __shfl_xor_sync(0xffffffffu, a, lm);
+                        x[r] = keep_min ? min(a, oa) : max(a, oa);
+                        x[R - 1 - r] = keep_min ? min(b, ob) : max(b, ob);
+                    }
                 }
             }
         }
-        // disperse: i <-> i ^ j for j = h/4 ... 1
+        // disperse: i <-> i ^ j for the remaining strides, layout B
 #pragma unroll
         for (int j = h >> 2; j > 0; j >>= 1) {
+            if (striped && j >= 32) continue;  // done above
             if (j >= R) {
                 const int lj = j / R;
                 const bool keep_min = (lane & lj) == 0;
@@ -327,9 +382,12 @@ __device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane) {
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 
 // Loads SA[l, l+occ) (coalesced, all R loads of a lane in flight at once), reduces to doc indices, sorts them in
-// registers and leaves them in shared memory at pad_idx(rank).
+// registers and run-length encodes them straight from the registers: the distinct docs go to s_doc[0 .. nheads) in
+// ascending order, the rank of each run's first element to s_pos (s_pos[nheads] = occ), both indexed through
+// pad_idx.  Returns nheads.
 template <typename SAT, int R>
-__device__ __forceinline__ void load_sort_store(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32* sorted, int lane) {
+__device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32* s_doc, u32* s_pos,
+                                             int lane) {
     SAT v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -342,14 +400,42 @@ __device__ __forceinline__ void load_sort_store(const SAT* __restrict__ sa, i64 
         const int i = r * 32 + lane;
         x[r] = i < occ ? (u32)((u64)v[r] & mask) : 0xffffffffu;  // doc index <= 2^32-2 (bits1 <= 32)
     }
-    warp_bitonic_regs<R>(x, lane);
+    warp_bitonic_regs<R>(x, lane, s_doc);  // s_doc doubles as the transpose buffer (33*R words) before it is filled
+    // lane holds ranks lane*R .. lane*R + R-1; a rank is a run head when its doc differs from the previous rank's
+    const u32 prev_last = __shfl_up_sync(0xffffffffu, x[R - 1], 1);
+    u32 hm = 0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) sorted[pad_idx(lane * R + r)] = x[r];
+    for (int r = 0; r < R; ++r) {
+        const int idx = lane * R + r;
+        const u32 pk = r ? x[r > 0 ? r - 1 : 0] : prev_last;
+        const bool head = idx < occ && (idx == 0 || x[r] != pk);
+        hm |= head ? (1u << r) : 0u;
+    }
+    const int nh = __popc(hm);
+    int incl = nh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int nheads = __shfl_sync(0xffffffffu, incl, 31);
+    // compact list index j lives at pad_idx(j): when there are no repeats lane l writes j = l*R + r, and without the
+    // padding all lanes of one store would hit the same bank
+    int o = incl - nh;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if ((hm >> r) & 1u) {
+            s_doc[pad_idx(o)] = x[r];
+            s_pos[pad_idx(o)] = (u32)(lane * R + r);
+            ++o;
+        }
+    }
+    if (lane == 0) s_pos[pad_idx(nheads)] = (u32)occ;
     __syncwarp();
+    return nheads;
 }
 
-constexpr int kSortedWords = kWarpCap + kWarpCap / 32;                 // padded keys
-constexpr size_t kWarpSmemBytes = (size_t)kSortedWords * 4 + kWarpCap * 2;  // + u16 run-head positions
+constexpr size_t kWarpSmemBytes = ((size_t)kWarpCap + 32) * 4 + ((size_t)kWarpCap + 64) * 4;  // s_doc, s_pos: u32, padded
 
 // Phase A.  One CTA = one tile of kTileWarps consecutive patterns, one warp each.  Per pattern: read the SA interval,
 // reduce to doc indices, sort, run-length encode; the tile's row count enters a decoupled look-back over per-tile
@@ -375,8 +461,8 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
     __syncthreads();
     const i64 tile = s_tile;
     const i64 q = tile * kTileWarps + warp;
-    u32* sorted = reinterpret_cast<u32*>(smem_raw + (size_t)warp * kWarpSmemBytes);
-    u16* hp = reinterpret_cast<u16*>(sorted + kSortedWords);
+    u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * kWarpSmemBytes);
+    u32* s_pos = s_doc + kWarpCap + 32;
     int occ = 0, nheads = 0;
     u64 d = 0;
     if (q < npat) {
@@ -386,22 +472,13 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
             d = dlarge[q];
         } else if (occ64 > 0) {
             occ = (int)occ64;
-            if (occ <= 32) load_sort_store<SAT, 1>(sa, l, occ, mask, sorted, lane);
-            else if (occ <= 64) load_sort_store<SAT, 2>(sa, l, occ, mask, sorted, lane);
-            else if (occ <= 128) load_sort_store<SAT, 4>(sa, l, occ, mask, sorted, lane);
-            else if (occ <= 256) load_sort_store<SAT, 8>(sa, l, occ, mask, sorted, lane);
-            else if (occ <= 512) load_sort_store<SAT, 16>(sa, l, occ, mask, sorted, lane);
-            else load_sort_store<SAT, 32>(sa, l, occ, mask, sorted, lane);
-            // run heads
-            for (int base = 0; base < occ; base += 32) {
-                const int t = base + lane;
-                const bool head = t < occ && (t == 0 || sorted[pad_idx(t)] != sorted[pad_idx(t - 1)]);
-                const u32 bal = __ballot_sync(0xffffffffu, head);
-                if (head) hp[nheads + __popc(bal & ((1u << lane) - 1))] = (u16)t;
-                nheads += __popc(bal);
-            }
+            if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 256) nheads = load_sort_rle<SAT, 8>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 512) nheads = load_sort_rle<SAT, 16>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else nheads = load_sort_rle<SAT, 32>(sa, l, occ, mask, s_doc, s_pos, lane);
             d = (u64)nheads;
-            __syncwarp();
         }
     }
     // split points of the row at the doc-range boundaries (nheads == 0 for empty / large-path rows -> all zero)
@@ -410,7 +487,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
         int lo = 0, hi = nheads;  // first j with doc_j >= bound
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if ((u64)sorted[pad_idx((int)hp[mid])] < bound)
+            if ((u64)s_doc[pad_idx(mid)] < bound)
                 lo = mid + 1;
             else
                 hi = mid;
@@ -462,11 +539,9 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
     for (int w = 0; w < warp; ++w) row += s_d[w];
     if (lane == 0) row_off[q] = row;
     // compact row: (count << 32 | doc), coalesced 8-byte stores
-    for (int r = lane; r < nheads; r += 32) {
-        const int start = (int)hp[r];
-        const int end = r + 1 < nheads ? (int)hp[r + 1] : occ;
-        st_stream_u64(cpairs + row + r, ((u64)(u32)(end - start) << 32) | (u64)sorted[pad_idx(start)]);
-    }
+    for (int r = lane; r < nheads; r += 32)
+        st_stream_u64(cpairs + row + r,
+                      ((u64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]) << 32) | (u64)s_doc[pad_idx(r)]);
 }
 
 // Phase B.  pairs[i] = (ids[doc_i], count_i) for every compact entry i.  ids[] (8 bytes per document, 800 MB at the

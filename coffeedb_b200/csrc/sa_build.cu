@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
     __shared__ u16 s_tab[256];
     __shared__ __align__(16) u16 s_sym[EX_TILE + 2 * EX_MAXS];
     __shared__ u32 s_cnt[EX_TILE];
+    __shared__ u32 s_bits[(EX_TILE + 2 * EX_MAXS) / 32 + 2];  // bit p: a document (or the text) ends right before t0 + p
     __shared__ u64 s_ws[32];
     __shared__ u64 s_base;
     __shared__ u64 s_key[MODE == 2 ? EX_TILE : 1];
@@ -136,11 +137,18 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
             *reinterpret_cast<uint2*>(&s_sym[w * 4]) = o;
         }
         *reinterpret_cast<uint4*>(&s_cnt[tid * EX_IPT]) = make_uint4(0, 0, 0, 0);
+        if (tid < (int)(sizeof(s_bits) / 4)) s_bits[tid] = 0;
         __syncthreads();
-        // document starts inside (t0, t0 + EX_TILE): documents d0+1 .. d1
-        for (i64 d = d0 + 1 + tid; d <= d1; d += EX_THREADS) {
+        // document starts inside (t0, t0 + EX_TILE + S): documents d0+1 .. (doc_off is non-decreasing; entry nd = n is
+        // the end of the text).  Counts feed the doc-index scan, the bit mask tells every position how far its
+        // document reaches without touching global memory again.
+        for (i64 d = d0 + 1 + tid; d <= nd; d += EX_THREADS) {
             const i64 p = __ldg(doc_off + d) - t0;
-            if (p > 0 && p < EX_TILE) atomicAdd(&s_cnt[p], 1u);
+            if (p >= EX_TILE + S) break;
+            if (p > 0) {
+                if (p < EX_TILE && d <= d1) atomicAdd(&s_cnt[p], 1u);
+                atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+            }
         }
         __syncthreads();
         // thread-contiguous scan: position li = tid * EX_IPT + r
@@ -174,13 +182,13 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
             key[r] = 0;
             val[r] = 0;
             if (g < n) {
-                const i64 d = (i64)(dbase + c[r]);
-                const i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
-                const i64 rem = de - g;
-                const int sh = rem < (i64)S ? b * (S - (int)rem) : 0;
+                // remaining length of the document from here, capped at 33: first set bit among positions li+1 .. li+32
+                const int p1 = li + 1;
+                const u32 win = __funnelshift_r(s_bits[p1 >> 5], s_bits[(p1 >> 5) + 1], p1 & 31);
+                const int rem = win ? __ffs(win) : 33;
+                const int sh = rem < S ? b * (S - rem) : 0;
                 const u64 k = (W >> sh) << sh;
                 key[r] = k;
-                val[r] = (P)(((u64)(g - ds) << bits1) | (u64)d);
                 if (MODE == 1) {
                     sel[r] = true;
                 } else {
@@ -190,7 +198,11 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
                     else
                         sel[r] = bucket >= blo && bucket < bhi;
                 }
-                nsel += sel[r] ? 1 : 0;
+                if (sel[r]) {  // the packed element needs the document's start: only selected positions load it
+                    const i64 d = (i64)(dbase + c[r]);
+                    val[r] = (P)(((u64)(g - __ldg(doc_off + d)) << bits1) | (u64)d);
+                    ++nsel;
+                }
             }
         }
         if (MODE == 1 && t0 + EX_TILE <= n) {

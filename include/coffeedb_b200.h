@@ -42,7 +42,10 @@ typedef struct cdb_options {
     int32_t compat_signed;     /* 1 (default) = reproduce the reference's signed-radix / unsigned-leaf order on
                                   corpora mixing bytes <0x80 and >=0x80 (SURVEY.md §8 note N1); 0 = plain unsigned */
     int64_t workspace_bytes;   /* cap on temporary device memory used by build (0 = 60 % of free memory) */
-    int32_t keep_host_copy;    /* 1 = keep the host staging copy of the text after build (needed for re-build) */
+    int32_t keep_host_copy;    /* 1 = keep the host staging copy of the text after build: cdb_add + cdb_build may then be
+                                  repeated on the same handle; 0 (default) = release it, later cdb_add / cdb_build
+                                  fail with CDB_ERR_STATE (the reference fills and builds a NEW index every time,
+                                  src/database.cpp:170-172, 276-281) */
     int32_t reserved;
 } cdb_options;
 

@@ -311,3 +311,24 @@ def test_config5_flavour_utf8_long_documents():
     for d, sp in zip(docs, ix.spans(kws, docs)):
         assert np.array_equal(sp, oracle.port.spans(kws, text[off[d]:off[d + 1]].tobytes()))
     ix.close()
+
+
+def test_add_after_build_and_rebuild():
+    """keep_host_copy = 0 (default): the staging copy is released by build(), later add()/build() fail loudly.
+    keep_host_copy = 1: documents can be appended and the index rebuilt on the same handle."""
+    ix = cdb.StringIndex()
+    ix.add(1, b"abcabc")
+    ix.build()
+    with pytest.raises(RuntimeError, match="has been built"):
+        ix.add(2, b"abc")
+    with pytest.raises(RuntimeError, match="has been built"):
+        ix.build()
+    assert ix.query(b"abc") == [(1, 2)]
+    ix.close()
+    ix = cdb.StringIndex(keep_host_copy=True)
+    ix.add(1, b"abcabc")
+    ix.build()
+    ix.add(2, b"xabc")
+    ix.build()
+    assert ix.query(b"abc") == [(1, 2), (2, 1)]
+    ix.close()
