@@ -31,6 +31,28 @@ __device__ __forceinline__ u64 block_exclusive_scan_u64(u64 v, u64* total, u64* 
     return woff + incl - v;
 }
 
+// 32-bit variant (counts inside one tile)
+__device__ __forceinline__ u32 block_exclusive_scan_u32(u32 v, u32* total, u32* warp_sums /* [32] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // protects warp_sums against a previous use
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    u32 woff = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        u32 s = warp_sums[w];
+        if (w < warp) woff += s;
+        tot += s;
+    }
+    *total = tot;
+    return woff + incl - v;
+}
+
 template <typename Tin>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const Tin* __restrict__ in, u64 n, u64* __restrict__ bsum) {
     __shared__ u64 ws[32];

@@ -84,7 +84,7 @@ __device__ __forceinline__ i64 doc_of(const i64* __restrict__ doc_off, i64 lo, i
 // documents share an offset with their successor and are skipped this way), for t = 0 .. ntiles.  One parallel
 // lower bound per tile: neighbouring tiles follow the same path, the probes hit L1/L2.
 constexpr int EX_THREADS = 256;
-constexpr int EX_IPT = 4;
+constexpr int EX_IPT = 8;
 constexpr int EX_TILE = EX_THREADS * EX_IPT;
 constexpr int EX_MAXS = 32;
 constexpr int EX_HIST = 4096;  // chunk planning histogram over the top 12 key bits
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
     __shared__ __align__(16) u16 s_sym[EX_TILE + 2 * EX_MAXS];
     __shared__ u32 s_cnt[EX_TILE];
     __shared__ u32 s_bits[(EX_TILE + 2 * EX_MAXS) / 32 + 2];  // bit p: a document (or the text) ends right before t0 + p
-    __shared__ u64 s_ws[32];
+    __shared__ u32 s_ws[32];
     __shared__ u64 s_base;
     __shared__ u64 s_key[MODE == 2 ? EX_TILE : 1];
     __shared__ P s_val[MODE == 2 ? EX_TILE : 1];
@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
             o.y = (u32)s_tab[(v >> 16) & 255] | ((u32)s_tab[v >> 24] << 16);
             *reinterpret_cast<uint2*>(&s_sym[w * 4]) = o;
         }
-        *reinterpret_cast<uint4*>(&s_cnt[tid * EX_IPT]) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < EX_IPT; r += 4) *reinterpret_cast<uint4*>(&s_cnt[tid * EX_IPT + r]) = make_uint4(0, 0, 0, 0);
         if (tid < (int)(sizeof(s_bits) / 4)) s_bits[tid] = 0;
         __syncthreads();
         // document starts inside (t0, t0 + EX_TILE + S): documents d0+1 .. (doc_off is non-decreasing; entry nd = n is
@@ -154,16 +155,17 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
         // thread-contiguous scan: position li = tid * EX_IPT + r
         u32 c[EX_IPT];
         u32 csum = 0;
-        {
-            const uint4 cv = *reinterpret_cast<const uint4*>(&s_cnt[tid * EX_IPT]);
-            c[0] = cv.x;
-            c[1] = c[0] + cv.y;
-            c[2] = c[1] + cv.z;
-            c[3] = c[2] + cv.w;
-            csum = c[3];
+#pragma unroll
+        for (int r = 0; r < EX_IPT; r += 4) {
+            const uint4 cv = *reinterpret_cast<const uint4*>(&s_cnt[tid * EX_IPT + r]);
+            c[r] = csum + cv.x;
+            c[r + 1] = c[r] + cv.y;
+            c[r + 2] = c[r + 1] + cv.z;
+            c[r + 3] = c[r + 2] + cv.w;
+            csum = c[r + 3];
         }
-        u64 tot;
-        const u64 dbase = (u64)d0 + prim::block_exclusive_scan_u64((u64)csum, &tot, s_ws);
+        u32 tot;
+        const u64 dbase = (u64)d0 + prim::block_exclusive_scan_u32(csum, &tot, s_ws);
         u64 key[EX_IPT];
         P val[EX_IPT];
         bool sel[EX_IPT];
@@ -186,8 +188,11 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
                 const int p1 = li + 1;
                 const u32 win = __funnelshift_r(s_bits[p1 >> 5], s_bits[(p1 >> 5) + 1], p1 & 31);
                 const int rem = win ? __ffs(win) : 33;
-                const int sh = rem < S ? b * (S - rem) : 0;
-                const u64 k = (W >> sh) << sh;
+                u64 k = W;
+                if (rem < S) {  // the document ends inside the window (rare): drop the symbols past its end
+                    const int sh = b * (S - rem);
+                    k = (W >> sh) << sh;
+                }
                 key[r] = k;
                 if (MODE == 1) {
                     sel[r] = true;
@@ -206,16 +211,18 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
             }
         }
         if (MODE == 1 && t0 + EX_TILE <= n) {
-            // thread-contiguous: 4 keys = 32 bytes, 4 values = 16/32 bytes per thread, 16-byte stores
+            // thread-contiguous: 8 keys = 64 bytes, 8 values = 32/64 bytes per thread, 16-byte stores
             ulonglong2* kd = reinterpret_cast<ulonglong2*>(keys + t0 + tid * EX_IPT);
-            kd[0] = make_ulonglong2(key[0], key[1]);
-            kd[1] = make_ulonglong2(key[2], key[3]);
+#pragma unroll
+            for (int r = 0; r < EX_IPT; r += 2) kd[r / 2] = make_ulonglong2(key[r], key[r + 1]);
             if (sizeof(P) == 4) {
-                *reinterpret_cast<uint4*>(vals + t0 + tid * EX_IPT) = make_uint4((u32)val[0], (u32)val[1], (u32)val[2], (u32)val[3]);
+                uint4* vd = reinterpret_cast<uint4*>(vals + t0 + tid * EX_IPT);
+#pragma unroll
+                for (int r = 0; r < EX_IPT; r += 4) vd[r / 4] = make_uint4((u32)val[r], (u32)val[r + 1], (u32)val[r + 2], (u32)val[r + 3]);
             } else {
                 ulonglong2* vd = reinterpret_cast<ulonglong2*>(vals + t0 + tid * EX_IPT);
-                vd[0] = make_ulonglong2((u64)val[0], (u64)val[1]);
-                vd[1] = make_ulonglong2((u64)val[2], (u64)val[3]);
+#pragma unroll
+                for (int r = 0; r < EX_IPT; r += 2) vd[r / 2] = make_ulonglong2((u64)val[r], (u64)val[r + 1]);
             }
         } else if (MODE == 1) {
 #pragma unroll
@@ -227,10 +234,10 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
                 }
             }
         } else if (MODE == 2) {
-            u64 stot;
-            const u64 ex = prim::block_exclusive_scan_u64(nsel, &stot, s_ws);
+            u32 stot;
+            const u32 ex = prim::block_exclusive_scan_u32(nsel, &stot, s_ws);
             if (tid == 0) s_base = stot ? atomicAdd(cursor, (unsigned long long)stot) : 0;
-            u32 o = (u32)ex;
+            u32 o = ex;
 #pragma unroll
             for (int r = 0; r < EX_IPT; ++r) {
                 if (sel[r]) {
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(EX_THREADS) extract_kernel(const u8* __restric
             }
             __syncthreads();
             const u64 base = s_base;
-            for (u32 i = tid; i < (u32)stot; i += EX_THREADS) {
+            for (u32 i = tid; i < stot; i += EX_THREADS) {
                 keys[base + i] = s_key[i];
                 vals[base + i] = s_val[i];
             }
