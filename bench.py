@@ -135,10 +135,15 @@ def make_shard(w, rank: int, world: int, device):
     return text, doc_off, ids, snd
 
 
-def algorithmic_bytes_per_pattern(n, w, occ, d):
-    """64*S + w*occ + 24*d with S = 2*ceil(log2 n) probes."""
+def algorithmic_bytes_per_pattern(n, w, occ, d, m=0, directory_symbols=0):
+    """64*S + w*occ + 24*d with S = 2*ceil(log2 n) probes.  When the prefix directory resolves the
+    keyword (m <= its symbols) no probe is made: the search then reads the keyword and its offset, two directory
+    entries, and writes the interval."""
     S = 2 * int(np.ceil(np.log2(max(n, 2))))
-    return {"search": 64.0 * S, "gather": float(w) * occ + 24.0 * d, "S": S}
+    search = 64.0 * S
+    if directory_symbols and 0 < m <= directory_symbols:
+        search, S = float(m + 8 + 2 * 8 + 2 * 8), 0
+    return {"search": search, "gather": float(w) * occ + 24.0 * d, "S": S}
 
 
 def pick_workload(name, world):
@@ -372,7 +377,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (CUDA-event phase times measured inside the library on `stream`)
     occ_pp = occs / npat
     d_pp = pairs / npat
-    alg = algorithmic_bytes_per_pattern(n_shard, width, occ_pp, d_pp)
+    alg = algorithmic_bytes_per_pattern(n_shard, width, occ_pp, d_pp, w["m"], ix.prefix_directory()["symbols"])
     # algorithmic bytes per launch, split over the kernels of the path: the search reads 64*S per
     # pattern; gather_kernel (phase A) reads the SA interval (w*occ); translate_kernel (phase B) reads ids[] and
     # writes the (id, count) pairs (24*d).  The compact intermediate rows between A and B (8*d written, 8*d read)
@@ -403,9 +408,9 @@ def run_ours(args):
                         "frac": (v[1] / (v[0] / 1e3) / 1e9 / hbm_peak if v[0] > 0 else 0.0)} for k, v in kernels.items()},
         "path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (phase["total_ms"] / 1e3) / 1e9,
                  "frac": path_bytes / (phase["total_ms"] / 1e3) / 1e9 / hbm_peak,
-                 "note": "SURVEY.md 8d formula 64*S + w*occ + 24*d per pattern over the whole locate; the prefix "
-                         "directory makes the search read far fewer than 64*S bytes, so also see frac_gather_only",
-                 "frac_gather_only": alg["gather"] * npat / (phase["total_ms"] / 1e3) / 1e9 / hbm_peak},
+                 "note": "w*occ + 24*d per pattern (SURVEY.md 8d) plus the search's bytes: 64*S probes, or 45 B when the "
+                         "prefix directory resolves the keyword without probing",
+                 "probes_per_pattern": alg["S"]},
     }
 
     # ---- CPU baseline: the reference's query() on this box's host cores, same index, bounded sample

@@ -25,7 +25,7 @@ CSRC = os.path.join(HERE, "csrc")
 # every symbol include/coffeedb_b200.h declares
 EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
-    "cdb_build", "cdb_build_device", "cdb_info", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
+    "cdb_build", "cdb_build_device", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
     "cdb_splice", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count",
 ]
@@ -86,6 +86,7 @@ def lib():
         L.cdb_build.argtypes = [vp]
         L.cdb_build_device.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.cdb_info.argtypes = [vp, i64p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.cdb_prefix_directory.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i64p]
         L.cdb_export_sa.argtypes = [vp, vp, C.c_int64]
         L.cdb_sa_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.cdb_locate_batch.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Result)]
@@ -219,6 +220,11 @@ class StringIndex:
         n, nd, w, bits, mask = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_uint64()
         _check(self._L.cdb_info(self._h, C.byref(n), C.byref(nd), C.byref(w), C.byref(bits), C.byref(mask)))
         return {"n": n.value, "nd": nd.value, "width": w.value, "bits": bits.value, "mask": mask.value}
+
+    def prefix_directory(self) -> dict:
+        k, b, e = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(self._L.cdb_prefix_directory(self._h, C.byref(k), C.byref(b), C.byref(e)))
+        return {"symbols": k.value, "bits_per_symbol": b.value, "entries": e.value}
 
     def build_stats(self) -> dict:
         t, s, r, c = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()

@@ -296,6 +296,18 @@ cdb_status cdb_info(const cdb_index* h, int64_t* n, int64_t* nd, int32_t* width,
     CDB_CATCH
 }
 
+cdb_status cdb_prefix_directory(const cdb_index* h, int32_t* symbols, int32_t* bits_per_symbol, int64_t* entries) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    const bool on = ix->d_ptab != nullptr;
+    if (symbols) *symbols = on ? ix->pt_k : 0;
+    if (bits_per_symbol) *bits_per_symbol = on ? ix->pt_b : 0;
+    if (entries) *entries = on ? ((i64)1 << (ix->pt_b * ix->pt_k)) : 0;
+    return CDB_OK;
+    CDB_CATCH
+}
+
 cdb_status cdb_export_sa(const cdb_index* h, void* buf, int64_t buf_bytes) {
     CDB_TRY
     const Index* ix = reinterpret_cast<const Index*>(h);

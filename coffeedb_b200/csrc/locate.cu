@@ -187,10 +187,17 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, co
         large_list[atomicAdd(counters + 0, 1ull)] = (u32)q;
         occ = 0;
     }
-    unsigned long long s = (unsigned long long)occ;
+    unsigned long long s = (unsigned long long)occ, mx = s;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + 1, s);
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = t > mx ? t : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && s) {
+        atomicAdd(counters + 1, s);
+        atomicMax(counters + 5, mx);  // longest interval on the warp path: picks the gather_kernel variant
+    }
 }
 
 // ---- prefix directory ------------------------------------------------------------------------------------------
@@ -435,7 +442,11 @@ __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, 
     return nheads;
 }
 
-constexpr size_t kWarpSmemBytes = ((size_t)kWarpCap + 32) * 4 + ((size_t)kWarpCap + 64) * 4;  // s_doc, s_pos: u32, padded
+// s_doc and s_pos of one warp (u32, padded) for intervals of up to 32 * MAXR occurrences
+template <int MAXR>
+constexpr size_t warp_smem_bytes() {
+    return ((size_t)32 * MAXR + 32) * 4 + ((size_t)32 * MAXR + 64) * 4;
+}
 
 // Phase A.  One CTA = one tile of kTileWarps consecutive patterns, one warp each.  Per pattern: read the SA interval,
 // reduce to doc indices, sort, run-length encode; the tile's row count enters a decoupled look-back over per-tile
@@ -443,8 +454,12 @@ constexpr size_t kWarpSmemBytes = ((size_t)kWarpCap + 32) * 4 + ((size_t)kWarpCa
 // the row's split points at the doc-range boundaries (seg) that phase B iterates over.  dlarge[q] holds the
 // (already known) row count of the patterns that took the large path; their rows are written by large_emit_kernel.
 //   seg layout: [tile][r = 0..nranges][kTileWarps] u16, seg(q, r) = number of row entries with doc < (r << rshift)
-template <typename SAT>
-__global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
+// MAXR = 32: intervals up to kWarpCap, 3 CTAs per SM.  MAXR = 4: batches whose longest warp-path interval is <= 128
+// occurrences (short rows: sharded corpora, long keywords) — the same code with the long sorting networks compiled
+// out, a third of the registers and a tenth of the shared memory, so twice as many CTAs per SM hide the per-tile
+// latency (ticket, look-back) that dominates there.
+template <typename SAT, int MAXR>
+__global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
                                                                      const i64* __restrict__ left,
                                                                      const i64* __restrict__ right, i64 npat,
                                                                      const u64* __restrict__ dlarge, u64* status,
@@ -461,8 +476,8 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
     __syncthreads();
     const i64 tile = s_tile;
     const i64 q = tile * kTileWarps + warp;
-    u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * kWarpSmemBytes);
-    u32* s_pos = s_doc + kWarpCap + 32;
+    u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<MAXR>());
+    u32* s_pos = s_doc + 32 * MAXR + 32;
     int occ = 0, nheads = 0;
     u64 d = 0;
     if (q < npat) {
@@ -474,10 +489,10 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3) gather_kernel(const SAT* _
             occ = (int)occ64;
             if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane);
             else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 256) nheads = load_sort_rle<SAT, 8>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 512) nheads = load_sort_rle<SAT, 16>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else nheads = load_sort_rle<SAT, 32>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+            else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
             d = (u64)nheads;
         }
     }
@@ -731,7 +746,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(5, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket
+    DevBuf<unsigned long long> counters(6, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket, [5] longest warp-path interval
     DevBuf<u32> large_list(npat, st);
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -751,7 +766,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
                                                                       large_list.p, counters.p);
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[1], st));
-    unsigned long long hc[4];
+    unsigned long long hc[6];
     CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
     if ((int)(hc[2] & 0xffffffffu)) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
@@ -800,11 +815,18 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u64> cpairs((size_t)cap_pairs, st);
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
-    const size_t smem = (size_t)kTileWarps * kWarpSmemBytes;
-    CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gather_kernel<SAT><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p, status.p,
-                                                                       reinterpret_cast<u32*>(counters.p + 3), row_off.p,
-                                                                       cpairs.p, seg.p, nranges, rshift);
+    if (hc[5] <= 128) {
+        const size_t smem = (size_t)kTileWarps * warp_smem_bytes<4>();
+        gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
+                                                                              status.p, reinterpret_cast<u32*>(counters.p + 3),
+                                                                              row_off.p, cpairs.p, seg.p, nranges, rshift);
+    } else {
+        const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
+        CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
+                                                                               status.p, reinterpret_cast<u32*>(counters.p + 3),
+                                                                               row_off.p, cpairs.p, seg.p, nranges, rshift);
+    }
     CDB_LAUNCH_CHECK();
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident

@@ -110,6 +110,10 @@ cdb_status cdb_build_device(cdb_index* idx, const void* d_text, const int64_t* d
 /* Index geometry after build: SA length n, element width (4|8), doc-index field width and mask
  * (src/index.h:56-58). */
 cdb_status cdb_info(const cdb_index* idx, int64_t* n, int64_t* nd, int32_t* width, int32_t* bits, uint64_t* mask);
+/* The prefix directory built beside the suffix array (no reference counterpart): `symbols` leading symbols of
+ * `bits_per_symbol` bits each index `entries` + 1 interval boundaries; symbols = 0 when the index has none (tiny
+ * corpora, or the note-N1 layout where the reference's exact binary search must run). */
+cdb_status cdb_prefix_directory(const cdb_index* idx, int32_t* symbols, int32_t* bits_per_symbol, int64_t* entries);
 /* Copies the packed suffix array to host memory (n*width bytes), for parity checks. */
 cdb_status cdb_export_sa(const cdb_index* idx, void* buf, int64_t buf_bytes);
 /* Device pointer of the packed suffix array (borrowed). */
