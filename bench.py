@@ -374,6 +374,17 @@ def run_ours(args):
     e2e_val = npat * e2e_steps / float(e2e_s.item())
     h2d_bytes = int(pat.nbytes + poff.nbytes)
 
+    # ---- latency of ONE keyword through the host ABI (the reference's own calling pattern: query() per request)
+    one_pat = np.ascontiguousarray(pat[: poff[1]])
+    one_off = np.ascontiguousarray(poff[:2])
+    for _ in range(20):
+        ix.result_free(ix.locate_batch_raw(one_pat, one_off))
+    t0 = time.perf_counter()
+    nlat = 200
+    for _ in range(nlat):
+        ix.result_free(ix.locate_batch_raw(one_pat, one_off))
+    single_us = (time.perf_counter() - t0) / nlat * 1e6
+
     # ---- roofline of the dominant kernel (CUDA-event phase times measured inside the library on `stream`)
     occ_pp = occs / npat
     d_pp = pairs / npat
@@ -434,6 +445,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "single_query_latency_us": single_us,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -91,6 +91,17 @@ static const char* const kAfterBuild =
     "the index has been built and its host staging copy released: add to a new index (or create this one with "
     "keep_host_copy = 1)";
 
+ThreadCtx& thread_ctx(int device) {
+    static thread_local std::map<int, ThreadCtx> ctxs;
+    ThreadCtx& c = ctxs[device];
+    if (!c.stream) {
+        c.device = device;
+        CDB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (auto& e : c.ev) CDB_CUDA(cudaEventCreate(&e));
+    }
+    return c;
+}
+
 static void require_device() {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -383,8 +394,7 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
     // the reference rejects an empty keyword before touching the index (src/index.cpp:239-241)
     for (i64 q = 0; q < npat; ++q)
         if (pat_off[q + 1] <= pat_off[q]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
-    cudaStream_t st;
-    CDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = thread_ctx(ix->device).stream;
     HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
     cdb_device_result dr;
     std::memset(&dr, 0, sizeof(dr));
@@ -414,7 +424,6 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
     } catch (...) {
         cdb_device_result_free(&dr);
         cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
         if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
         if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
         delete own;
@@ -426,9 +435,7 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
     out->row_off = (const i64*)own->row_off;
     out->pairs = (const i64*)own->pairs;
     out->_owner = own;
-    cdb_device_result_free(&dr);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
+    cdb_device_result_free(&dr);  // stream-ordered frees on the thread's own stream: nothing to wait for
     return CDB_OK;
     CDB_CATCH
 }

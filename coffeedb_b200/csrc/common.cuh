@@ -117,6 +117,26 @@ struct BigBuf {
     bool pooled = false;
 };
 
+// Per host thread and device: one non-blocking stream and a set of timing events, created on first use and kept (a
+// query() per request must not pay stream and event creation every time).
+struct ThreadCtx {
+    static constexpr int kEvents = 8;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kEvents] = {};
+    ~ThreadCtx() {
+        if (!stream) return;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(stream);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+ThreadCtx& thread_ctx(int device);  // capi.cu; the device must be current
+
 inline int ceil_div_i(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 

@@ -751,14 +751,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
     CDB_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), st));
-    cudaEvent_t ev[7];
-    for (auto& e : ev) CDB_CUDA(cudaEventCreate(&e));
-    struct EvGuard {
-        cudaEvent_t* e;
-        ~EvGuard() {
-            for (int i = 0; i < 7; ++i) cudaEventDestroy(e[i]);
-        }
-    } ev_guard{ev};
+    cudaEvent_t* ev = thread_ctx(ix.device).ev;  // 7 of the thread's cached timing events
     CDB_CUDA(cudaEventRecord(ev[0], st));
     SearchCtx c = make_ctx(ix);
     int* err = reinterpret_cast<int*>(counters.p + 2);

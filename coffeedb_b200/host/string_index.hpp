@@ -21,6 +21,7 @@
 //                          ac_automaton::render, src/database.cpp:58-77); render() splices the markers
 //                          (src/database.cpp:78-90)
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -139,5 +140,68 @@ private:
 };
 
 using string_index = basic_string_index<index_base>;
+
+// $correlation composition over (id, count) lists, as filter() does it on the host (src/interface.cpp:79-146).  The
+// device delivers exact per-(keyword, document) counts; these helpers are the reference-shaped integer adds on top.
+namespace correlation {
+using list = std::vector<std::pair<int64_t, int64_t>>;
+
+// OR of two keyword lists of one key: union by id, counts added (src/interface.cpp:87-113).  Inputs sorted by (id, count).
+inline list or_merge(const list& now, const list& result) {
+    list tmp;
+    size_t i = 0, j = 0;
+    while (i < now.size() && j < result.size()) {
+        if (now[i].first == result[j].first) {
+            tmp.push_back(now[i]);
+            tmp.back().second += result[j].second;
+            ++i, ++j;
+        } else if (now[i] < result[j]) {
+            tmp.push_back(now[i++]);
+        } else {
+            tmp.push_back(result[j++]);
+        }
+    }
+    while (i < now.size()) tmp.push_back(now[i++]);
+    while (j < result.size()) tmp.push_back(result[j++]);
+    return tmp;
+}
+
+// AND across keys: intersection by id, counts added (src/interface.cpp:118-135).
+inline list and_merge(const list& result, const list& answer) {
+    list tmp;
+    for (size_t i = 0, j = 0; i < result.size() && j < answer.size();) {
+        if (result[i].first == answer[j].first) {
+            tmp.push_back(result[i]);
+            tmp.back().second += answer[j].second;
+            ++i, ++j;
+        } else if (result[i] < answer[j]) {
+            ++i;
+        } else {
+            ++j;
+        }
+    }
+    return tmp;
+}
+
+// The keyword list of ONE key (src/interface.cpp:79-113) from the rows of one batched device pass: every row is
+// sorted by (id, count) first, as filter() does on arrival (:81-82, :86-87), then OR-merged in keyword order.
+inline list or_of_rows(std::vector<list> rows) {
+    list result;
+    for (size_t k = 0; k < rows.size(); ++k) {
+        std::sort(rows[k].begin(), rows[k].end());
+        result = k == 0 ? std::move(rows[k]) : or_merge(rows[k], result);
+    }
+    return result;
+}
+
+// $correlation range [L, R) and the final descending sort (src/interface.cpp:137-146; std::sort with the same
+// comparator on the same input order gives the same permutation for a given libstdc++).
+inline void finish(list& answer, bool has_range, int64_t L, int64_t R) {
+    if (has_range)
+        answer.erase(std::remove_if(answer.begin(), answer.end(), [L, R](auto p) { return !(p.second >= L && p.second < R); }),
+                     answer.end());
+    std::sort(answer.begin(), answer.end(), [](auto x, auto y) { return x.second > y.second; });
+}
+}  // namespace correlation
 
 }  // namespace coffeedb_b200

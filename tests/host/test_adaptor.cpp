@@ -100,6 +100,39 @@ int main(int argc, char** argv) {
             REQUIRE(rows[t] == want);
         }
     }
+    {  // $correlation composition (src/interface.cpp:79-146): OR of three keywords of one key, AND with a second key
+        namespace cor = coffeedb_b200::correlation;
+        std::mt19937_64 rng(11);
+        std::vector<std::string> title(400), body(400);
+        for (size_t i = 0; i < title.size(); ++i) {
+            title[i].resize(40);
+            body[i].resize(200);
+            for (auto& c : title[i]) c = (char)('a' + rng() % 4);
+            for (auto& c : body[i]) c = (char)('a' + rng() % 4);
+        }
+        sindex t, b;
+        for (size_t i = 0; i < title.size(); ++i) {
+            t.add(5000 - (int64_t)i, title[i]);  // ids descend: list order (doc index) != id order
+            b.add(5000 - (int64_t)i, body[i]);
+        }
+        t.build();
+        b.build();
+        const std::vector<std::string> kws = {"abc", "ca", "dddd"};
+        cor::list got = cor::and_merge(cor::or_of_rows(b.query_batch(kws)), cor::or_of_rows(t.query_batch({"ab"})));
+        cor::list want;
+        for (size_t i = title.size(); i-- > 0;) {  // ascending id
+            int64_t cb = 0;
+            for (auto& k : kws) cb += brute(body[i], k);
+            const int64_t ct = brute(title[i], "ab");
+            if (cb && ct) want.emplace_back(5000 - (int64_t)i, cb + ct);
+        }
+        REQUIRE(got == want);
+        cor::finish(got, true, 3, 6);
+        for (size_t i = 0; i < got.size(); ++i) {
+            REQUIRE(got[i].second >= 3 && got[i].second < 6);
+            REQUIRE(i == 0 || got[i - 1].second >= got[i].second);
+        }
+    }
     std::puts("adaptor gpu ok");
     return 0;
 }
