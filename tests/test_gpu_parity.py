@@ -332,3 +332,62 @@ def test_add_after_build_and_rebuild():
     ix.build()
     assert ix.query(b"abc") == [(1, 2), (2, 1)]
     ix.close()
+
+
+def _fuzz_corpus(rng):
+    """Small adversarial corpora: tiny alphabets, empty and one-byte documents, repeated documents, NUL and 0xFF
+    bytes, documents shorter than a radix key, a few long runs."""
+    kind = int(rng.integers(0, 6))
+    nd = int(rng.integers(1, 400))
+    if kind == 0:    # binary alphabet, many ties
+        alpha = np.frombuffer(b"ab", np.uint8)
+    elif kind == 1:  # bytes around the sign boundary and the extremes
+        alpha = np.array([0x00, 0x01, 0x7F, 0x80, 0xFE, 0xFF], np.uint8)
+    elif kind == 2:  # single symbol
+        alpha = np.frombuffer(b"z", np.uint8)
+    elif kind == 3:
+        alpha = np.arange(97, 123, dtype=np.uint8)
+    elif kind == 4:  # high bytes only
+        alpha = np.arange(0x80, 0x90, dtype=np.uint8)
+    else:
+        alpha = np.frombuffer(b"acgt", np.uint8)
+    maxlen = int(rng.choice([1, 2, 9, 13, 40, 300]))
+    docs = []
+    for _ in range(nd):
+        ln = int(rng.integers(0, maxlen + 1)) if rng.random() > 0.15 else 0
+        docs.append(bytes(alpha[rng.integers(0, len(alpha), size=ln)]))
+    if nd > 3 and rng.random() < 0.5:  # exact duplicates of whole documents
+        for _ in range(int(rng.integers(1, 10))):
+            docs[int(rng.integers(0, nd))] = docs[int(rng.integers(0, nd))]
+    if rng.random() < 0.3:
+        docs[int(rng.integers(0, nd))] = bytes(alpha[:1]) * int(rng.integers(300, 3000))
+    return corpora.from_docs(docs, id_base=int(rng.integers(-1000, 1000)))
+
+
+def test_fuzz_small_corpora():
+    rng = np.random.default_rng(20261017)
+    for case in range(60):
+        text, off, ids = _fuzz_corpus(rng)
+        ix = build(text, off, ids)
+        sa, b1, w = oracle.port.build_sa(text, off)
+        inf = ix.info()
+        assert (inf["n"], inf["bits"], inf["width"]) == (len(sa), b1, w), case
+        assert np.array_equal(ix.export_sa(), sa), case
+        pats = []
+        if len(text):
+            spat, soff = corpora.sampled_patterns(text, off, 30, 1, 12, seed=case)
+            pats = [bytes(spat[soff[i]:soff[i + 1]]) for i in range(30)]
+        alpha = np.unique(text) if len(text) else np.array([97], np.uint8)
+        for _ in range(20):  # random keywords over (alphabet + one byte that may be absent)
+            m = int(rng.integers(1, 6))
+            pool = np.concatenate([alpha, np.array([int(rng.integers(0, 256))], np.uint8)])
+            pats.append(bytes(pool[rng.integers(0, len(pool), size=m)]))
+        row_off, pairs = ix.locate_batch(pats)
+        for q, kw in enumerate(pats):
+            assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), (case, kw)
+        nd = len(ids)
+        docs = [int(d) for d in rng.integers(0, nd, size=min(nd, 5))]
+        kws = pats[:3] if pats else [b"a"]
+        for d, sp in zip(docs, ix.spans(kws, docs)):
+            assert np.array_equal(sp, oracle.port.spans(kws, text[off[d]:off[d + 1]].tobytes())), (case, d)
+        ix.close()
