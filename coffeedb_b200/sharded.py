@@ -6,8 +6,8 @@ so when rank g indexes the documents ``[g*nd/W, (g+1)*nd/W)`` the full row of a 
 shard rows in rank order — per-document counts never need summing.  What the ranks exchange per batch is small:
 
 * the packed pattern batch, broadcast from the rank that received the request,
-* per-pattern row lengths of every shard (``all_gather``)  -> global CSR offsets by a scan in rank order,
-* per-pattern occurrence totals (``all_reduce``)           -> what the reference's ``count`` needs,
+* per-pattern (row length, occurrences) of every shard, one ``all_gather`` -> global CSR offsets by a scan in rank
+  order, and the occurrence totals the reference's ``count`` needs as column sums,
 * optionally the rows themselves, gathered to one rank (``gather_rows``), for callers that need the flat answer.
 
 Plumbing is ``torch.distributed`` (NCCL over NVLink on GPUs; the CPU tests run the same code over gloo with a fake
@@ -173,13 +173,17 @@ class ShardedStringIndex:
         row_off, pairs, occ, keep = self.locate_local(d_pat, d_off)
         rows = row_off[1:] - row_off[:-1]
         if self.world > 1:
-            shard_rows = torch.empty(self.world * npat, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(shard_rows, rows.contiguous(), group=self.group)
-            occ = occ.clone()
-            dist.all_reduce(occ, group=self.group)
+            # ONE collective per batch: every shard's (row lengths, occurrences) per pattern.  The occurrence totals the
+            # reference's `count` needs are the column sums, so no separate all_reduce.
+            mine = torch.stack([rows, occ]).reshape(-1)                       # [2 * npat]
+            allst = torch.empty(self.world * 2 * npat, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allst, mine, group=self.group)
+            allst = allst.view(self.world, 2, npat)
+            shard_rows = allst[:, 0, :]
+            occ = allst[:, 1, :].sum(dim=0)
         else:
-            shard_rows = rows
-        return ShardedResult(row_off, pairs, shard_rows.view(self.world, npat), occ, self.rank, keep)
+            shard_rows = rows.view(1, npat)
+        return ShardedResult(row_off, pairs, shard_rows, occ, self.rank, keep)
 
     def gather_rows(self, res: ShardedResult, dst: int = 0):
         """Collective.  Assembles the flat answer on rank `dst`: (global_row_off, pairs) with row q = the shard rows of
