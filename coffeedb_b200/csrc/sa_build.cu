@@ -696,6 +696,15 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
     CDB_CUDA(cudaStreamSynchronize(st));
     ix.d_sa = (void*)sa.detach();
     ix.sort_ms = timers.total_ms();
+    if (getenv("CDB_DEBUG_TIMING")) {
+        const auto t_f0 = std::chrono::steady_clock::now();
+        k0.release();
+        k1.release();
+        v0.release();
+        fprintf(stderr, "[cdb] build: cudaFree of the workspace took %.1f ms; %.1f ms since the allocations\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
+    }
 }
 
 // ---- note N1: the reference's signed-radix / unsigned-leaf layout ---------------------------------------------------
