@@ -299,6 +299,19 @@ def run_ours(args):
     # ---- patterns: pinned host copy (e2e) and device copy (value)
     pat, poff = make_patterns(w)
     npat = w["npat"]
+    if args.patterns == "w8s":
+        # secondary workload W8s: 8-byte substrings sampled from the corpus (every pattern hits; on this
+        # rank's shard when sharded).  Keywords longer than the prefix directory: the search refines by binary search.
+        g = torch.Generator(device=dev)
+        g.manual_seed(4242)
+        L = w["doclen"]
+        docs_s = torch.randint(0, snd, (npat,), device=dev, generator=g)
+        offs_s = torch.randint(0, L - 8 + 1, (npat,), device=dev, generator=g)
+        idx = (docs_s * L + offs_s).unsqueeze(1) + torch.arange(8, device=dev).unsqueeze(0)
+        pat = text[idx.reshape(-1)].cpu().numpy()
+        poff = np.arange(npat + 1, dtype=np.int64) * 8
+        w["m"] = 8
+        wname += "-w8s"
     h_pat = torch.from_numpy(pat).pin_memory()
     h_poff = torch.from_numpy(poff).pin_memory()
     d_pat = torch.zeros(len(pat) + 8, dtype=torch.uint8, device=dev)
@@ -509,6 +522,8 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--npat", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--patterns", default="w5", choices=["w5", "w8s"],
+                    help="w5 = uniform 5-byte keywords (the metric's workload); w8s = sampled 8-byte substrings")
     ap.add_argument("--no-rebuild", dest="rebuild", action="store_false",
                     help="skip the second (warm) build of the same corpus (build.rebuild_ms)")
     ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")

@@ -17,6 +17,7 @@
 // All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "index.cuh"
 #include "locate.cuh"
@@ -766,45 +767,77 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     const u64 nl = hc[0];
     u64 total_occ = hc[1];
     CDB_CUDA(cudaEventRecord(ev[2], st));
-    // large path, phase 1: exact row counts of the long intervals
-    DevBuf<u64> ooff, ukey, ustart, entry_first;
-    u64 ltotal = 0, nu = 0;
+    // large path, phase 1: exact row counts of the long intervals.  The occurrences of the large patterns are
+    // expanded, sorted and run-length encoded in sub-batches of bounded size (25 bytes of temporaries per occurrence);
+    // what is kept until the rows can be emitted is 16 bytes per (pattern, document) pair.
+    struct LargeChunk {
+        u64 j0 = 0, nlc = 0, nu = 0, ltotal = 0;
+        DevBuf<u64> ukey, ustart, entry_first;
+    };
+    std::vector<LargeChunk> lchunks;
+    u64 nu = 0;
     if (nl > 0) {
         dlarge.alloc(npat, st);
-        ooff.alloc(nl + 1, st);
+        DevBuf<u64> ooff(nl + 1, st);
         large_occ_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, left.p, right.p, ooff.p);
         CDB_LAUNCH_CHECK();
         prim::exclusive_scan<u64>(ooff.p, ooff.p, nl, st);
-        CDB_CUDA(cudaMemcpyAsync(&ltotal, ooff.p + nl, 8, cudaMemcpyDeviceToHost, st));
+        std::vector<u64> h_ooff(nl + 1);
+        CDB_CUDA(cudaMemcpyAsync(h_ooff.data(), ooff.p, (nl + 1) * 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaStreamSynchronize(st));
-        total_occ += ltotal;
-        DevBuf<u64> k0(ltotal, st), k1(ltotal, st);
-        const int grid = (int)std::min<i64>(ceil_div((i64)ltotal, 256), kNumSMs * 16);
-        large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p, nl, left.p, ooff.p, ltotal, k0.p);
-        CDB_LAUNCH_CHECK();
-        int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, ltotal, 0, 32 + bits_for_u64(nl - 1), st);
-        u64* sorted = cbuf ? k1.p : k0.p;
-        DevBuf<u8> flags(ltotal, st);
-        large_flag_kernel<<<grid, 256, 0, st>>>(sorted, ltotal, flags.p);
-        CDB_LAUNCH_CHECK();
-        DevBuf<u64> pos(ltotal + 1, st);
-        prim::exclusive_scan<u8>(flags.p, pos.p, ltotal, st);
-        CDB_CUDA(cudaMemcpyAsync(&nu, pos.p + ltotal, 8, cudaMemcpyDeviceToHost, st));
-        CDB_CUDA(cudaStreamSynchronize(st));
-        ukey.alloc(nu, st);
-        ustart.alloc(nu, st);
-        entry_first.alloc(nl + 1, st);
-        large_unique_kernel<<<grid, 256, 0, st>>>(sorted, flags.p, pos.p, ltotal, ukey.p, ustart.p, entry_first.p);
-        CDB_LAUNCH_CHECK();
-        CDB_CUDA(cudaMemcpyAsync(entry_first.p + nl, pos.p + ltotal, 8, cudaMemcpyDeviceToDevice, st));
-        large_dcount_kernel<<<(unsigned)ceil_div((i64)nl, 256), 256, 0, st>>>(large_list.p, nl, entry_first.p, dlarge.p);
-        CDB_LAUNCH_CHECK();
+        total_occ += h_ooff[nl];
+        u64 limit = 1ull << 28;
+        if (const char* e = getenv("CDB_LARGE_LIMIT")) limit = (u64)atoll(e);
+        for (u64 j0 = 0; j0 < nl;) {
+            u64 j1 = j0 + 1;  // at least one pattern, then as many as fit the limit
+            while (j1 < nl && h_ooff[j1 + 1] - h_ooff[j0] <= limit) ++j1;
+            lchunks.emplace_back();
+            LargeChunk& lc = lchunks.back();
+            lc.j0 = j0;
+            lc.nlc = j1 - j0;
+            lc.ltotal = h_ooff[j1] - h_ooff[j0];
+            std::vector<u64> h_loff(lc.nlc + 1);
+            for (u64 j = 0; j <= lc.nlc; ++j) h_loff[j] = h_ooff[j0 + j] - h_ooff[j0];
+            DevBuf<u64> loff(lc.nlc + 1, st);
+            CDB_CUDA(cudaMemcpyAsync(loff.p, h_loff.data(), (lc.nlc + 1) * 8, cudaMemcpyHostToDevice, st));
+            DevBuf<u64> k0(lc.ltotal, st), k1(lc.ltotal, st);
+            const int grid = (int)std::min<i64>(ceil_div((i64)lc.ltotal, 256), kNumSMs * 16);
+            large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal, k0.p);
+            CDB_LAUNCH_CHECK();
+            int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, lc.ltotal, 0,
+                                                         32 + bits_for_u64(lc.nlc - 1), st);
+            u64* sorted = cbuf ? k1.p : k0.p;
+            DevBuf<u8> flags(lc.ltotal, st);
+            large_flag_kernel<<<grid, 256, 0, st>>>(sorted, lc.ltotal, flags.p);
+            CDB_LAUNCH_CHECK();
+            DevBuf<u64> pos(lc.ltotal + 1, st);
+            prim::exclusive_scan<u8>(flags.p, pos.p, lc.ltotal, st);
+            CDB_CUDA(cudaMemcpyAsync(&lc.nu, pos.p + lc.ltotal, 8, cudaMemcpyDeviceToHost, st));
+            CDB_CUDA(cudaStreamSynchronize(st));  // also: h_loff must stay alive until its upload has happened
+            lc.ukey.alloc(lc.nu, st);
+            lc.ustart.alloc(lc.nu, st);
+            lc.entry_first.alloc(lc.nlc + 1, st);
+            large_unique_kernel<<<grid, 256, 0, st>>>(sorted, flags.p, pos.p, lc.ltotal, lc.ukey.p, lc.ustart.p, lc.entry_first.p);
+            CDB_LAUNCH_CHECK();
+            CDB_CUDA(cudaMemcpyAsync(lc.entry_first.p + lc.nlc, pos.p + lc.ltotal, 8, cudaMemcpyDeviceToDevice, st));
+            large_dcount_kernel<<<(unsigned)ceil_div((i64)lc.nlc, 256), 256, 0, st>>>(large_list.p + j0, lc.nlc, lc.entry_first.p,
+                                                                                      dlarge.p);
+            CDB_LAUNCH_CHECK();
+            nu += lc.nu;
+            j0 = j1;
+        }
     }
     CDB_CUDA(cudaEventRecord(ev[3], st));
     // phase A: rows <= occurrences on the warp path + exact rows of the large path
     const u64 cap_pairs = hc[1] + nu;
     int nranges, rshift;
     ids_ranges(ix.nd, &nranges, &rshift);
+    // Few lookups compared with the size of ids[] (short rows, e.g. long keywords): one pass over all rows costs less
+    // than nranges sparse ones, and there is nothing for L2 to keep.
+    if (nranges > 1 && cap_pairs * 8 < (u64)ix.nd && !getenv("CDB_RANGE_BITS")) {
+        nranges = 1;
+        rshift = 40;
+    }
     DevBuf<u64> cpairs((size_t)cap_pairs, st);
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
@@ -837,10 +870,11 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[5], st));
-    if (nl > 0 && nu > 0) {
-        const int grid = (int)std::min<i64>(ceil_div((i64)nu, 256), kNumSMs * 16);
-        large_emit_kernel<<<grid, 256, 0, st>>>(ukey.p, ustart.p, nu, ltotal, large_list.p, entry_first.p, row_off.p,
-                                                ix.d_ids, pairs.p);
+    for (LargeChunk& lc : lchunks) {
+        if (lc.nu == 0) continue;
+        const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), kNumSMs * 16);
+        large_emit_kernel<<<grid, 256, 0, st>>>(lc.ukey.p, lc.ustart.p, lc.nu, lc.ltotal, large_list.p + lc.j0, lc.entry_first.p,
+                                                row_off.p, ix.d_ids, pairs.p);
         CDB_LAUNCH_CHECK();
     }
     u64 total_pairs = 0;

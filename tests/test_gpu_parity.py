@@ -113,12 +113,16 @@ def test_chunked_build_equals_single_chunk():
     b.close()
 
 
-def test_large_interval_path():
-    """Intervals longer than the warp path's capacity go through the device radix sort."""
+@pytest.mark.parametrize("limit", [None, "40000", "1"])
+def test_large_interval_path(limit, monkeypatch):
+    """Intervals longer than the warp path's capacity go through the device radix sort, in sub-batches of bounded
+    size (CDB_LARGE_LIMIT occurrences; "1" = one pattern per sub-batch)."""
+    if limit:
+        monkeypatch.setenv("CDB_LARGE_LIMIT", limit)
     text, off, ids = corpora.uniform(20000, 50, seed=43, lo=ord("a"), hi=ord("c"))
     ix = build(text, off, ids)
     sa, b1, _w = oracle.port.build_sa(text, off)
-    pats = [b"a", b"ab", b"abc", b"abca", b"c", b"cc", b"abcabcabc", b"bbbbbbbbbbbbbbbbbbbbbbbb"]
+    pats = [b"a", b"ab", b"abc", b"abca", b"c", b"cc", b"abcabcabc", b"bbbbbbbbbbbbbbbbbbbbbbbb", b"ba", b"cab", b"bcb"]
     row_off, pairs = ix.locate_batch(pats)
     for q, kw in enumerate(pats):
         assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
