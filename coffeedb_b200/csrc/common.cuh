@@ -137,7 +137,6 @@ struct ThreadCtx {
 };
 ThreadCtx& thread_ctx(int device);  // capi.cu; the device must be current
 
-inline int ceil_div_i(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------- device side

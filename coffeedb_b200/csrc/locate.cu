@@ -1,20 +1,27 @@
 // Batched substring locate — replaces string_index::query() (src/index.cpp:237-326; kernels K4-K7 of
 // SURVEY.md §2a) for a whole batch of patterns at once.
 //
-//   K4  search_kernel      one thread per pattern runs the reference's two binary-search recurrences verbatim
-//                          (same midpoints, same predicates), so the interval is identical even on the
-//                          not-quite-sorted arrays of note N1.  Each probe = SA element -> doc_off pair ->
-//                          16 bytes of text, compared as big-endian integers (== unsigned memcmp).
-//   K5-K7 gather_kernel  one launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
+//   K4  search_kernel      one thread per pattern.  Sorted array: the prefix directory (first k symbols -> SA
+//                          interval) answers keywords of <= k symbols with two lookups and narrows longer ones to one
+//                          bucket, refined by lower/upper bounds.  Note-N1 layout: the reference's two binary-search
+//                          recurrences verbatim (same midpoints, same predicates), so the interval is identical on
+//                          that not-quite-sorted array.  A probe = SA element -> doc_off pair -> 16 bytes of text,
+//                          compared as big-endian integers (== unsigned memcmp).
+//   K5-K7 gather_kernel    phase A, one launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
 //                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, bitonic
-//                          sorting network in registers (up to 32 keys per lane, SHFL for the lane strides), run-length,
-//                          then the tile's row count enters a decoupled look-back over per-tile status words,
-//                          which yields the exact CSR row offset without a second pass; finally the ids[] gather
-//                          and 16-byte (id, count) stores.
+//                          sorting network in registers, run-length encoding, then the tile's row count enters a
+//                          decoupled look-back over per-tile status words, which yields the exact CSR row offset
+//                          without a second pass; rows leave as compact (count << 32 | doc) words.
+//         translate_kernel phase B: pairs = (ids[doc], count), ordered by doc range so that the slice of ids[] in use
+//                          stays in L2 (a fused gather spent 99 GB of DRAM reads on 25.8 GB of algorithmic bytes).
 //   K5-K7 large path       patterns with longer intervals are expanded into (entry << 32 | doc) keys, sorted by
-//                          the device radix sort (the same engine as the build) and run-length encoded; their
-//                          row counts are known before gather_kernel runs and take part in its scan.
-// All integer work; bounded by HBM sector traffic (64*S + w*occ + 24*d bytes per pattern).
+//                          the device radix sort (the same engine as the build) and run-length encoded, in
+//                          sub-batches of bounded size; their row counts are known before gather_kernel runs and
+//                          take part in its look-back.
+//   K8  span_* kernels     highlight spans from suffix-array positions or from a direct scan of the requested
+//                          documents.
+// All integer work; bounded by HBM traffic and, in gather_kernel, by the ALU pipe (64*S + w*occ + 24*d
+// algorithmic bytes per pattern).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>

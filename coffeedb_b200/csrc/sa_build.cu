@@ -2,18 +2,22 @@
 // (src/index.cpp:178-236, 75-128; kernels K1-K3 of SURVEY.md §2a).
 //
 // Algorithm (B200-first, not the reference's work-queue MSD radix):
-//   round 0   every suffix gets a 64-bit key holding its first S symbols; the alphabet is re-coded to
-//             b = ceil(log2(sigma+1)) bits with 0 = end-of-document, so S = 64/b (12 symbols for a-z).  The
-//             reference's 257-symbol order "end-of-document < every byte" (src/index.h:66-73) is exactly
-//             integer order of these keys.  (key, packed) pairs are sorted by the onesweep radix sort.
+//   round 0   every suffix gets a key holding its first S0 symbols; the alphabet is re-coded to
+//             b = ceil(log2(sigma+1)) bits with 0 = end-of-document, and S0 = ceil((log2 n + 10) / b) symbols make
+//             random text already almost tie-free (9 symbols = 45 bits = 6 radix passes for a-z at n = 10^10; at most
+//             S = 64/b).  The reference's 257-symbol order "end-of-document < every byte" (src/index.h:66-73) is
+//             exactly integer order of these keys.  (key, packed) pairs are sorted by the onesweep radix sort.
 //   round r   only suffixes still tied with a neighbour stay on a worklist.  A tied group whose members have
 //             ended (their remaining length < compared depth) consists of byte-identical suffixes: their
 //             final order is ascending packed value (the canonical order of note N2).  Every other tied
 //             suffix gets the next S symbols as its key.  The worklist is sorted by key, then stably by
 //             group number, and written back in place; new ties form the next worklist.
 //   chunks    when 2*(8+w) bytes per suffix do not fit the workspace, suffixes are partitioned by the top
-//             12 bits of their round-0 key and the partitions are sorted one after another straight into
-//             their final suffix-array range (a 10 GB corpus needs ~8 chunks on one 180 GB B200).
+//             12 bits of their round-0 key and the partitions are sorted one after another; keys ping-pong
+//             between two buffers, values between one buffer and the partition's own range of the suffix array,
+//             where the last radix pass lands (a 10 GB corpus takes 4 chunks on one 180 GB B200).
+//   note N1   on corpora mixing bytes < 0x80 and >= 0x80 the sorted array is then rotated into the reference's
+//             signed-radix / unsigned-leaf layout (apply_signed_radix_layout).
 // The payload carried through every sort is the reference's own packed element (offset << bits1) | doc, so the
 // finished array is byte-for-byte what src/index.cpp:209-215 + the sort would hold (up to note N2 ties).
 #include <algorithm>
@@ -427,11 +431,6 @@ __global__ void apply_perm_kernel(const u32* __restrict__ perm2, const u64* __re
     key2[j] = ks[q];
     pay2[j] = v;
     chunk_vals[widx[j]] = v;
-}
-
-template <typename P>
-__global__ void copy_kernel(const P* __restrict__ src, P* __restrict__ dst, u64 m) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // ---- host driver ------------------------------------------------------------------------------------------------

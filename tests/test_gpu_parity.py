@@ -395,3 +395,32 @@ def test_fuzz_small_corpora():
         for d, sp in zip(docs, ix.spans(kws, docs)):
             assert np.array_equal(sp, oracle.port.spans(kws, text[off[d]:off[d + 1]].tobytes())), (case, d)
         ix.close()
+
+
+def test_reference_size_limit_errors():
+    """The two limits string_index::build enforces (src/index.cpp:195-200), with the reference's exact messages.
+    They only depend on the document-boundary array, so crafted boundaries reach them without a huge corpus."""
+    import torch
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    text = torch.zeros(1024, dtype=torch.uint8, device=dev)
+    # bits1 + bits2 > 64: three documents, one of them 2^62 bytes "long"
+    doc_off = torch.tensor([0, 1 << 62, (1 << 62) + 1, (1 << 62) + 2], dtype=torch.int64, device=dev)
+    ids = torch.arange(3, dtype=torch.int64, device=dev)
+    ix = cdb.StringIndex(device=0)
+    with pytest.raises(RuntimeError, match="^The amount of data exceeds the maximum range that CoffeeDB can handle$"):
+        ix.build_device(text.data_ptr(), doc_off.data_ptr(), ids.data_ptr(), 3, stream)
+    ix.close()
+    # the same check in the oracle's restatement of the width rule
+    rc, b1, b2, _w = oracle.port.widths(doc_off.cpu().numpy())
+    assert rc == 1 and b1 + b2 > 64
+    # bits1 > 32: 2^32 (empty) documents
+    if torch.cuda.mem_get_info()[0] > 60 * (1 << 30):
+        nd = 1 << 32
+        doc_off = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
+        ix = cdb.StringIndex(device=0)
+        with pytest.raises(RuntimeError, match="^The number of objects exceeds the maximum range that CoffeeDB can handle$"):
+            ix.build_device(text.data_ptr(), doc_off.data_ptr(), ids.data_ptr(), nd, stream)
+        ix.close()
+        del doc_off
+        torch.cuda.empty_cache()
