@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, co
                                                      const i64* __restrict__ pat_off, i64 npat,
                                                      i64* __restrict__ left_out, i64* __restrict__ right_out,
                                                      int* __restrict__ err, u32* __restrict__ large_list,
-                                                     unsigned long long* __restrict__ counters) {
+                                                     unsigned long long* __restrict__ counters, u64* __restrict__ wocc) {
     __shared__ u16 s_tab[256];
     s_tab[threadIdx.x] = tab.sym[threadIdx.x];
     __syncthreads();
@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, co
         large_list[atomicAdd(counters + 0, 1ull)] = (u32)q;
         occ = 0;
     }
+    if (q < npat) wocc[q] = (u64)occ;  // occurrences the warp path will read for this pattern (0: large path or no hit)
     unsigned long long s = (unsigned long long)occ, mx = s;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -271,9 +272,6 @@ void build_prefix_table(Index& ix, cudaStream_t st) {
 }
 
 // ---- K5-K7 gather (phase A) + translate (phase B) ---------------------------------------------------------------
-constexpr u64 GS_LOCAL = 1ull << 62;
-constexpr u64 GS_INCL = 2ull << 62;
-constexpr u64 GS_MASK = (1ull << 62) - 1;
 constexpr int kMaxRanges = 64;   // doc-range partitions of ids[] used by translate_kernel (each <= ~32 MB of ids)
 
 // Bitonic sorting network over 32*R keys held in registers, R per lane, in the all-ascending "flip + disperse"
@@ -456,112 +454,67 @@ constexpr size_t warp_smem_bytes() {
     return ((size_t)32 * MAXR + 32) * 4 + ((size_t)32 * MAXR + 64) * 4;
 }
 
-// Phase A.  One CTA = one tile of kTileWarps consecutive patterns, one warp each.  Per pattern: read the SA interval,
-// reduce to doc indices, sort, run-length encode; the tile's row count enters a decoupled look-back over per-tile
-// status words (exact CSR row offsets in the same pass); the row leaves as compact (count << 32 | doc) words plus
-// the row's split points at the doc-range boundaries (seg) that phase B iterates over.  dlarge[q] holds the
-// (already known) row count of the patterns that took the large path; their rows are written by large_emit_kernel.
-//   seg layout: [tile][r = 0..nranges][kTileWarps] u16, seg(q, r) = number of row entries with doc < (r << rshift)
+// Phase A.  One warp per pattern, no communication between warps: read the SA interval, reduce to doc indices, sort,
+// run-length encode.  The compact row (count << 32 | doc) goes to cpairs at alloc_off[q] — the exclusive scan of the
+// warp-path occurrence counts, known right after the search, an upper bound of the row lengths — and the exact row
+// length to rowlen[q]; a scan of rowlen gives the CSR offsets afterwards (no look-back chain, no CTA barrier: with one
+// the kernel spent 27 % of its warp time waiting).  seg holds the row's split points at the doc-range boundaries for
+// phase B.  Patterns on the large path report the row length computed there (dlarge) and write nothing else.
+//   seg layout: [q / 8][r = 0..nranges][q % 8] u16, seg(q, r) = number of row entries with doc < (r << rshift)
 // MAXR = 32: intervals up to kWarpCap, 3 CTAs per SM.  MAXR = 4: batches whose longest warp-path interval is <= 128
 // occurrences (short rows: sharded corpora, long keywords) — the same code with the long sorting networks compiled
-// out, a third of the registers and a tenth of the shared memory, so twice as many CTAs per SM hide the per-tile
-// latency (ticket, look-back) that dominates there.
+// out, half the registers and a tenth of the shared memory, so twice as many warps per SM hide the latency.
 template <typename SAT, int MAXR>
 __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
-                                                                     const i64* __restrict__ left,
-                                                                     const i64* __restrict__ right, i64 npat,
-                                                                     const u64* __restrict__ dlarge, u64* status,
-                                                                     u32* ticket, u64* __restrict__ row_off,
-                                                                     u64* __restrict__ cpairs, u16* __restrict__ seg,
-                                                                     int nranges, int rshift) {
+                                                                                    const i64* __restrict__ left,
+                                                                                    const i64* __restrict__ right, i64 npat,
+                                                                                    const u64* __restrict__ dlarge,
+                                                                                    const u64* __restrict__ alloc_off,
+                                                                                    u64* __restrict__ rowlen,
+                                                                                    u64* __restrict__ cpairs,
+                                                                                    u16* __restrict__ seg, int nranges,
+                                                                                    int rshift) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ u64 s_d[kTileWarps];
-    __shared__ u64 s_prefix;
-    __shared__ u32 s_tile;
-    __shared__ u16 s_seg[(kMaxRanges + 1) * kTileWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const i64 tile = s_tile;
-    const i64 q = tile * kTileWarps + warp;
+    const i64 q = (i64)blockIdx.x * kTileWarps + warp;
+    if (q >= npat) return;
     u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<MAXR>());
     u32* s_pos = s_doc + 32 * MAXR + 32;
-    int occ = 0, nheads = 0;
+    int nheads = 0;
     u64 d = 0;
-    if (q < npat) {
-        const i64 l = left[q];
-        const i64 occ64 = right[q] - l;
-        if (occ64 > kWarpCap) {
-            d = dlarge[q];
-        } else if (occ64 > 0) {
-            occ = (int)occ64;
-            if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
-            else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
-            d = (u64)nheads;
-        }
+    const i64 l = left[q];
+    const i64 occ64 = right[q] - l;
+    if (occ64 > kWarpCap) {
+        d = dlarge[q];
+    } else if (occ64 > 0) {
+        const int occ = (int)occ64;
+        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane);
+        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane);
+        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
+        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+        d = (u64)nheads;
     }
+    if (lane == 0) rowlen[q] = d;
     // split points of the row at the doc-range boundaries (nheads == 0 for empty / large-path rows -> all zero)
-    for (int r = lane; r <= nranges; r += 32) {
-        const u64 bound = (u64)r << rshift;
-        int lo = 0, hi = nheads;  // first j with doc_j >= bound
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((u64)s_doc[pad_idx(mid)] < bound)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        s_seg[r * kTileWarps + warp] = (u16)lo;
-    }
-    if (lane == 0) s_d[warp] = d;
-    __syncthreads();
-    {   // the tile's seg block leaves as one contiguous run
-        const int nseg = (nranges + 1) * kTileWarps;
-        u16* g = seg + (size_t)tile * nseg;
-        for (int i = threadIdx.x; i < nseg; i += kTileWarps * 32) g[i] = s_seg[i];
-    }
-    // tile aggregate -> decoupled look-back (warp 0, 32 predecessor tiles per round)
-    if (warp == 0) {
-        u64 agg = 0;
-#pragma unroll
-        for (int w = 0; w < kTileWarps; ++w) agg += s_d[w];
-        if (lane == 0) st_relaxed_u64(status + tile, (tile == 0 ? GS_INCL : GS_LOCAL) | agg);
-        u64 excl = 0;
-        if (tile > 0) {
-            i64 t = tile - 1;
-            for (;;) {
-                const i64 idx = t - lane;
-                u64 v;
-                for (;;) {
-                    v = idx >= 0 ? ld_relaxed_u64(status + idx) : GS_INCL;
-                    if (__all_sync(0xffffffffu, (v >> 62) != 0)) break;
-                }
-                const u32 incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-                u64 part = lane <= first ? (v & GS_MASK) : 0;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                excl += part;
-                if (incl_mask) break;
-                t -= 32;
+    {
+        u16* g = seg + (size_t)(q / kTileWarps) * (nranges + 1) * kTileWarps + (q % kTileWarps);
+        for (int r = lane; r <= nranges; r += 32) {
+            const u64 bound = (u64)r << rshift;
+            int lo = 0, hi = nheads;  // first j with doc_j >= bound
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((u64)s_doc[pad_idx(mid)] < bound)
+                    lo = mid + 1;
+                else
+                    hi = mid;
             }
-            if (lane == 0) st_relaxed_u64(status + tile, GS_INCL | (excl + agg));
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            if ((tile + 1) * kTileWarps >= npat) row_off[npat] = excl + agg;
+            g[r * kTileWarps] = (u16)lo;
         }
     }
-    __syncthreads();
-    if (q >= npat) return;
-    u64 row = s_prefix;
-    for (int w = 0; w < warp; ++w) row += s_d[w];
-    if (lane == 0) row_off[q] = row;
     // compact row: (count << 32 | doc), coalesced 8-byte stores
+    const u64 row = alloc_off[q];
     for (int r = lane; r < nheads; r += 32)
         st_stream_u64(cpairs + row + r,
                       ((u64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]) << 32) | (u64)s_doc[pad_idx(r)]);
@@ -579,9 +532,9 @@ constexpr int kTrWarps = 8;
 // kTrU x 32 consecutive entries of the item, starting at flat index i0.  FULL: all of them exist.
 template <bool FULL>
 __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs, const u64* __restrict__ ids,
-                                                 i64* __restrict__ pairs, const u32* s_excl, const u64* s_adj, u32 i0,
-                                                 u32 tot, int lane, u64 pol_keep, u64 pol_stream) {
-    u64 p[kTrU], cp[kTrU];
+                                                 i64* __restrict__ pairs, const u32* s_excl, const u64* s_in,
+                                                 const u64* s_out, u32 i0, u32 tot, int lane, u64 pol_keep, u64 pol_stream) {
+    u64 p[kTrU], cp[kTrU];  // p: where the (id, count) pair goes
 #pragma unroll
     for (int u = 0; u < kTrU; ++u) {
         const u32 idx = i0 + u * 32 + lane;
@@ -590,8 +543,8 @@ __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs,
 #pragma unroll
             for (int st = 16; st; st >>= 1)
                 if (s_excl[j + st] <= idx) j += st;
-            p[u] = s_adj[j] + idx;
-            cp[u] = ld_hint_u64(cpairs + p[u], pol_stream);
+            p[u] = s_out[j] + idx;
+            cp[u] = ld_hint_u64(cpairs + (s_in[j] + idx), pol_stream);
         }
     }
     // ptxas otherwise sinks every load next to its use and runs the kTrU chains one after another (one request in
@@ -615,12 +568,14 @@ __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs,
 }
 
 __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __restrict__ cpairs,
+                                                                  const u64* __restrict__ alloc_off,
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
                                                                   const i64* __restrict__ ids, i64* __restrict__ pairs,
                                                                   i64 npat, int nranges, unsigned long long* ticket) {
     __shared__ u32 s_excl[kTrWarps][32];
-    __shared__ u64 s_adj[kTrWarps][32];
+    __shared__ u64 s_in[kTrWarps][32];   // compact rows sit at alloc_off (upper-bound offsets) ...
+    __shared__ u64 s_out[kTrWarps][32];  // ... the result rows at row_off (exact CSR offsets)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 ntile = (npat + 31) >> 5;
     const i64 nitems = ntile * nranges;
@@ -638,12 +593,15 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         const int r = (int)(item / ntile);
         const i64 q = (item - (i64)r * ntile) * 32 + lane;
         u32 len = 0;
-        u64 base = 0;
+        u64 base_in = 0, base_out = 0;
         if (q < npat) {
             const u16* sg = seg + ((size_t)(q / kTileWarps) * (nranges + 1) + r) * kTileWarps + (q % kTileWarps);
             const u32 s = sg[0], e = sg[kTileWarps];
             len = e - s;
-            if (len) base = row_off[q] + s;
+            if (len) {
+                base_in = alloc_off[q] + s;
+                base_out = row_off[q] + s;
+            }
         }
         u32 incl = len;
 #pragma unroll
@@ -655,13 +613,15 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         if (tot == 0) continue;
         __syncwarp();
         s_excl[warp][lane] = incl - len;
-        s_adj[warp][lane] = base - (incl - len);
+        s_in[warp][lane] = base_in - (incl - len);
+        s_out[warp][lane] = base_out - (incl - len);
         __syncwarp();
         const u64* idp = reinterpret_cast<const u64*>(ids);
         u32 i0 = 0;
         for (; i0 + 32 * kTrU <= tot; i0 += 32 * kTrU)
-            translate_rounds<true>(cpairs, idp, pairs, s_excl[warp], s_adj[warp], i0, tot, lane, pol_keep, pol_stream);
-        if (i0 < tot) translate_rounds<false>(cpairs, idp, pairs, s_excl[warp], s_adj[warp], i0, tot, lane, pol_keep, pol_stream);
+            translate_rounds<true>(cpairs, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
+        if (i0 < tot)
+            translate_rounds<false>(cpairs, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
     }
 }
 
@@ -745,6 +705,16 @@ static void ids_ranges(i64 nd, int* nranges, int* rshift) {
     *nranges = (int)ceil_div(nd > 0 ? nd : 1, (i64)1 << sh);
 }
 
+// a[0..n) -> its exclusive scan, a[n] = total.  Small batches (a query() per request) take one single-block launch.
+static void scan_in_place(u64* a, u64 n, cudaStream_t st) {
+    if (n <= 16384) {
+        prim::scan_blocksums_kernel<<<1, 1024, 0, st>>>(a, n);
+        CDB_LAUNCH_CHECK();
+    } else {
+        prim::exclusive_scan<u64>(a, a, n, st);
+    }
+}
+
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
@@ -754,18 +724,20 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(6, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] gather ticket, [4] translate ticket, [5] longest warp-path interval
+    DevBuf<unsigned long long> counters(6, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] unused, [4] translate ticket, [5] longest warp-path interval
     DevBuf<u32> large_list(npat, st);
-    DevBuf<u64> status(ntiles, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
-    CDB_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), st));
     cudaEvent_t* ev = thread_ctx(ix.device).ev;  // 7 of the thread's cached timing events
     CDB_CUDA(cudaEventRecord(ev[0], st));
     SearchCtx c = make_ctx(ix);
+    DevBuf<u64> alloc_off(npat + 1, st);
     int* err = reinterpret_cast<int*>(counters.p + 2);
     search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, ix.symtab, d_pat, d_pat_off, npat, left.p, right.p, err,
-                                                                      large_list.p, counters.p);
+                                                                      large_list.p, counters.p, alloc_off.p);
     CDB_LAUNCH_CHECK();
+    // where every pattern's compact row goes: exclusive scan (in place) of the warp-path occurrence counts, which are
+    // upper bounds of the row lengths
+    scan_in_place(alloc_off.p, (u64)npat, st);
     CDB_CUDA(cudaEventRecord(ev[1], st));
     unsigned long long hc[6];
     CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -848,19 +820,21 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u64> cpairs((size_t)cap_pairs, st);
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
+    // row_off first receives the exact row lengths, then becomes their exclusive scan = the CSR offsets
     if (hc[5] <= 128) {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<4>();
         gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
-                                                                              status.p, reinterpret_cast<u32*>(counters.p + 3),
-                                                                              row_off.p, cpairs.p, seg.p, nranges, rshift);
+                                                                              alloc_off.p, row_off.p, cpairs.p, seg.p, nranges,
+                                                                              rshift);
     } else {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
         CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
-                                                                               status.p, reinterpret_cast<u32*>(counters.p + 3),
-                                                                               row_off.p, cpairs.p, seg.p, nranges, rshift);
+                                                                               alloc_off.p, row_off.p, cpairs.p, seg.p, nranges,
+                                                                               rshift);
     }
     CDB_LAUNCH_CHECK();
+    scan_in_place(row_off.p, (u64)npat, st);
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     {
@@ -872,7 +846,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         }
         const i64 nitems = ceil_div(npat, 32) * nranges;
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
-        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, alloc_off.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
                                                          counters.p + 4);
         CDB_LAUNCH_CHECK();
     }
@@ -1091,7 +1065,7 @@ static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nk
     if (!use_scan) {
         SearchCtx c = make_ctx(ix);
         search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, ix.symtab, d_kw.p, d_koff.p, nkw, left.p, right.p,
-                                                                          reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr);
+                                                                          reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr, nullptr);
         CDB_LAUNCH_CHECK();
         ooff.alloc((size_t)nkw + 1, st);
         span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
