@@ -292,12 +292,13 @@ def test_concurrent_queries_and_rebuild():
 
 
 def test_config5_flavour_utf8_long_documents():
-    """BASELINE configs[4] flavour at test scale: valid UTF-8, ragged documents up to ~70 KB among 40 000 short ones
-    (bits1 + bits2 = 33 -> 64-bit suffix-array elements), bytes on both sides of 0x80 with n >> 4096 -> several
-    signed-radix levels of the note-N1 layout.  Bit-exact suffix array and (id, count) rows against the oracle."""
+    """BASELINE configs[4] flavour at test scale (10.7 MB): valid UTF-8, ragged documents up to ~70 KB among 300 000
+    short ones (bits1 + bits2 = 36 -> 64-bit suffix-array elements), bytes on both sides of 0x80 with n >> 4096 ->
+    several signed-radix levels of the note-N1 layout (chuck_size = n/256 = 41 621).  Bit-exact suffix array and
+    (id, count) rows against the oracle."""
     rng = np.random.default_rng(5)
-    lens = rng.integers(0, 40, size=40000)
-    lens[rng.integers(0, 40000, size=30)] = rng.integers(20000, 50000, size=30)
+    lens = rng.integers(0, 40, size=300000)
+    lens[rng.integers(0, 300000, size=40)] = rng.integers(20000, 50000, size=40)
     text, off, ids = corpora.utf8_fast(lens, seed=78)
     ix = build(text, off, ids)
     sa, b1, w = oracle.port.build_sa(text, off)
