@@ -397,10 +397,10 @@ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 // Loads SA[l, l+occ) (coalesced, all R loads of a lane in flight at once), reduces to doc indices, sorts them in
 // registers and run-length encodes them straight from the registers: the distinct docs go to s_doc[0 .. nheads) in
 // ascending order, the rank of each run's first element to s_pos (s_pos[nheads] = occ), both indexed through
-// pad_idx.  Returns nheads.
+// pad_idx.  Returns nheads; all_distinct tells that every run has length 1 (s_pos is then not written).
 template <typename SAT, int R>
 __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32* s_doc, u32* s_pos,
-                                             int lane) {
+                                             int lane, bool& all_distinct) {
     SAT v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -432,6 +432,16 @@ __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, 
         if (lane >= o) incl += t;
     }
     const int nheads = __shfl_sync(0xffffffffu, incl, 31);
+    all_distinct = nheads == occ;
+    if (all_distinct) {
+        // the common case (no document hit twice): the compact list is the sorted list itself, every count is 1 —
+        // R stores at fixed offsets (rank lane*R + r sits at pad_idx = lane*R + r + (lane*R >> 5)), no s_pos
+        u32* dst = s_doc + lane * R + ((lane * R) >> 5);
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[r] = x[r];
+        __syncwarp();
+        return nheads;
+    }
     // compact list index j lives at pad_idx(j): when there are no repeats lane l writes j = l*R + r, and without the
     // padding all lanes of one store would hit the same bank
     int o = incl - nh;
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
     u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<MAXR>());
     u32* s_pos = s_doc + 32 * MAXR + 32;
     int nheads = 0;
+    bool all_distinct = false;
     u64 d = 0;
     const i64 l = left[q];
     const i64 occ64 = right[q] - l;
@@ -488,12 +499,12 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
         d = dlarge[q];
     } else if (occ64 > 0) {
         const int occ = (int)occ64;
-        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane);
-        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane);
-        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane);
-        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
-        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
-        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane);
+        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
         d = (u64)nheads;
     }
     if (lane == 0) rowlen[q] = d;
@@ -515,9 +526,13 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
     }
     // compact row: (count << 32 | doc), coalesced 8-byte stores
     const u64 row = alloc_off[q];
-    for (int r = lane; r < nheads; r += 32)
-        st_stream_u64(cpairs + row + r,
-                      ((u64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]) << 32) | (u64)s_doc[pad_idx(r)]);
+    if (all_distinct) {
+        for (int r = lane; r < nheads; r += 32) st_stream_u64(cpairs + row + r, (1ull << 32) | (u64)s_doc[pad_idx(r)]);
+    } else {
+        for (int r = lane; r < nheads; r += 32)
+            st_stream_u64(cpairs + row + r,
+                          ((u64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]) << 32) | (u64)s_doc[pad_idx(r)]);
+    }
 }
 
 // Phase B.  pairs[i] = (ids[doc_i], count_i) for every compact entry i.  ids[] (8 bytes per document, 800 MB at the
