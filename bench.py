@@ -334,7 +334,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
-    phase = {k: 0.0 for k in ("search_ms", "count_ms", "large_ms", "scan_ms", "emit_ms", "total_ms")}
+    phase = {k: 0.0 for k in ("search_ms", "gather_ms", "large_ms", "tail_ms", "translate_ms", "total_ms")}
     barrier()
     if rank == 0:
         sampler.start()
@@ -408,8 +408,8 @@ def run_ours(args):
     # are this design's own overhead and are NOT counted as algorithmic bytes.
     kernels = {
         "search_kernel": (phase["search_ms"], alg["search"] * npat),
-        "gather_kernel": (phase["count_ms"], width * occ_pp * npat),
-        "translate_kernel": (phase["emit_ms"], 24.0 * d_pp * npat),
+        "gather_kernel": (phase["gather_ms"], width * occ_pp * npat),
+        "translate_kernel": (phase["translate_ms"], 24.0 * d_pp * npat),
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]

@@ -116,7 +116,7 @@ def last_locate_stats() -> dict:
     ms = (C.c_double * 6)()
     cn = (C.c_int64 * 4)()
     lib().cdb_last_locate_stats(ms, cn)
-    return {"search_ms": ms[0], "count_ms": ms[1], "large_ms": ms[2], "scan_ms": ms[3], "emit_ms": ms[4],
+    return {"search_ms": ms[0], "gather_ms": ms[1], "large_ms": ms[2], "tail_ms": ms[3], "translate_ms": ms[4],
             "total_ms": ms[5], "npat": cn[0], "pairs": cn[1], "occurrences": cn[2], "nlarge": cn[3]}
 
 

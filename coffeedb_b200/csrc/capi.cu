@@ -150,8 +150,8 @@ uint64_t cdb_launch_count(void) { return g_launches.load(); }
 void cdb_last_locate_stats(double* ms6, int64_t* counts4) {
     const LocateStats& s = g_locate_stats;
     if (ms6) {
-        ms6[0] = s.search_ms; ms6[1] = s.count_ms; ms6[2] = s.large_ms;
-        ms6[3] = s.scan_ms; ms6[4] = s.emit_ms; ms6[5] = s.total_ms;
+        ms6[0] = s.search_ms; ms6[1] = s.gather_ms; ms6[2] = s.large_ms;
+        ms6[3] = s.tail_ms; ms6[4] = s.translate_ms; ms6[5] = s.total_ms;
     }
     if (counts4) {
         counts4[0] = s.npat; counts4[1] = s.total_pairs; counts4[2] = s.total_occ; counts4[3] = s.nlarge;

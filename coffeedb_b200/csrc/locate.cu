@@ -881,9 +881,9 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         LocateStats& ls = g_locate_stats;
         cudaEventElapsedTime(&ls.search_ms, ev[0], ev[1]);
         cudaEventElapsedTime(&ls.large_ms, ev[2], ev[3]);
-        cudaEventElapsedTime(&ls.count_ms, ev[3], ev[4]);  // gather_kernel (phase A)
-        cudaEventElapsedTime(&ls.emit_ms, ev[4], ev[5]);   // translate_kernel (phase B)
-        cudaEventElapsedTime(&ls.scan_ms, ev[5], ev[6]);   // large-path emit + final read-back
+        cudaEventElapsedTime(&ls.gather_ms, ev[3], ev[4]);  // gather_kernel (phase A)
+        cudaEventElapsedTime(&ls.translate_ms, ev[4], ev[5]);   // translate_kernel (phase B)
+        cudaEventElapsedTime(&ls.tail_ms, ev[5], ev[6]);   // large-path emit + final read-back
         cudaEventElapsedTime(&ls.total_ms, ev[0], ev[6]);
         ls.npat = npat;
         ls.total_pairs = (long long)total_pairs;

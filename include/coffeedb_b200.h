@@ -146,7 +146,8 @@ int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t
  * and number of key-range chunks. */
 cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks);
 /* Phase timing of the calling thread's last locate (milliseconds, CUDA events on the launching stream):
- * ms6 = {search, count, large-interval path, offset scan, emit, total}; counts4 = {npat, pairs, occurrences,
+ * ms6 = {search (incl. the occurrence scan), gather (phase A, incl. the row-length scan), large-interval path,
+ * tail (large-path emit + total read-back), translate (phase B), total}; counts4 = {npat, pairs, occurrences,
  * patterns that took the large-interval path}. */
 void cdb_last_locate_stats(double* ms6, int64_t* counts4);
 /* Number of CUDA kernels this library has launched in this process. */
