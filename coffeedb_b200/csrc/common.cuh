@@ -187,6 +187,14 @@ __device__ __forceinline__ u64 ld_hint_u64(const u64* p, u64 policy) {
 __device__ __forceinline__ void st_hint_v2(i64* p, longlong2 v, u64 policy) {
     asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
 }
+__device__ __forceinline__ u32 ld_hint_u32(const u32* p, u64 policy) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(u32* p, u32 v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // streaming 8-byte store (written once, read by a later kernel)
 __device__ __forceinline__ void st_stream_u64(u64* p, u64 v) {
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

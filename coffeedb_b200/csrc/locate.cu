@@ -9,15 +9,16 @@
 //                          compared as big-endian integers (== unsigned memcmp).
 //   K5-K7 gather_kernel    phase A, one launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
 //                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, bitonic
-//                          sorting network in registers, run-length encoding, then the tile's row count enters a
-//                          decoupled look-back over per-tile status words, which yields the exact CSR row offset
-//                          without a second pass; rows leave as compact (count << 32 | doc) words.
+//                          sorting network in registers, run-length encoding.  Warps never wait for each other: the
+//                          compact row (u32 docs, + u16 counts when a document is hit more than once) goes to the scan
+//                          of the occurrence counts (an upper bound), the exact CSR offsets come from a scan of the
+//                          row lengths afterwards.
 //         translate_kernel phase B: pairs = (ids[doc], count), ordered by doc range so that the slice of ids[] in use
 //                          stays in L2 (a fused gather spent 99 GB of DRAM reads on 25.8 GB of algorithmic bytes).
 //   K5-K7 large path       patterns with longer intervals are expanded into (entry << 32 | doc) keys, sorted by
 //                          the device radix sort (the same engine as the build) and run-length encoded, in
-//                          sub-batches of bounded size; their row counts are known before gather_kernel runs and
-//                          take part in its look-back.
+//                          sub-batches of bounded size; their row lengths are known before gather_kernel runs and
+//                          enter the same scan, the rows themselves are emitted straight into the CSR result.
 //   K8  span_* kernels     highlight spans from suffix-array positions or from a direct scan of the requested
 //                          documents.
 // All integer work; bounded by HBM traffic and, in gather_kernel, by the ALU pipe (64*S + w*occ + 24*d
@@ -465,7 +466,8 @@ constexpr size_t warp_smem_bytes() {
 }
 
 // Phase A.  One warp per pattern, no communication between warps: read the SA interval, reduce to doc indices, sort,
-// run-length encode.  The compact row (count << 32 | doc) goes to cpairs at alloc_off[q] — the exclusive scan of the
+// run-length encode.  The compact row (u32 docs in cdocs; u16 counts in ccnt only when some document is hit more than
+// once, flagged in bit 15 of the row's seg entries) goes to alloc_off[q] — the exclusive scan of the
 // warp-path occurrence counts, known right after the search, an upper bound of the row lengths — and the exact row
 // length to rowlen[q]; a scan of rowlen gives the CSR offsets afterwards (no look-back chain, no CTA barrier: with one
 // the kernel spent 27 % of its warp time waiting).  seg holds the row's split points at the doc-range boundaries for
@@ -481,7 +483,8 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
                                                                                     const u64* __restrict__ dlarge,
                                                                                     const u64* __restrict__ alloc_off,
                                                                                     u64* __restrict__ rowlen,
-                                                                                    u64* __restrict__ cpairs,
+                                                                                    u32* __restrict__ cdocs,
+                                                                                    u16* __restrict__ ccnt,
                                                                                     u16* __restrict__ seg, int nranges,
                                                                                     int rshift) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -521,18 +524,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
                 else
                     hi = mid;
             }
-            g[r * kTileWarps] = (u16)lo;
+            g[r * kTileWarps] = (u16)(lo | ((nheads && !all_distinct) ? 0x8000 : 0));
         }
     }
-    // compact row: (count << 32 | doc), coalesced 8-byte stores
+    // compact row: coalesced 4-byte doc stores (+ 2-byte counts for the rare rows with repeats)
     const u64 row = alloc_off[q];
-    if (all_distinct) {
-        for (int r = lane; r < nheads; r += 32) st_stream_u64(cpairs + row + r, (1ull << 32) | (u64)s_doc[pad_idx(r)]);
-    } else {
-        for (int r = lane; r < nheads; r += 32)
-            st_stream_u64(cpairs + row + r,
-                          ((u64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]) << 32) | (u64)s_doc[pad_idx(r)]);
-    }
+    for (int r = lane; r < nheads; r += 32) st_stream_u32(cdocs + row + r, s_doc[pad_idx(r)]);
+    if (!all_distinct)
+        for (int r = lane; r < nheads; r += 32) ccnt[row + r] = (u16)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]);
 }
 
 // Phase B.  pairs[i] = (ids[doc_i], count_i) for every compact entry i.  ids[] (8 bytes per document, 800 MB at the
@@ -546,10 +545,13 @@ constexpr int kTrWarps = 8;
 
 // kTrU x 32 consecutive entries of the item, starting at flat index i0.  FULL: all of them exist.
 template <bool FULL>
-__device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs, const u64* __restrict__ ids,
+__device__ __forceinline__ void translate_rounds(const u32* __restrict__ cdocs, const u16* __restrict__ ccnt,
+                                                 const u64* __restrict__ ids,
                                                  i64* __restrict__ pairs, const u32* s_excl, const u64* s_in,
                                                  const u64* s_out, u32 i0, u32 tot, int lane, u64 pol_keep, u64 pol_stream) {
-    u64 p[kTrU], cp[kTrU];  // p: where the (id, count) pair goes
+    u64 p[kTrU];   // where the (id, count) pair goes
+    u32 doc[kTrU];
+    u32 cnt[kTrU];
 #pragma unroll
     for (int u = 0; u < kTrU; ++u) {
         const u32 idx = i0 + u * 32 + lane;
@@ -559,7 +561,10 @@ __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs,
             for (int st = 16; st; st >>= 1)
                 if (s_excl[j + st] <= idx) j += st;
             p[u] = s_out[j] + idx;
-            cp[u] = ld_hint_u64(cpairs + (s_in[j] + idx), pol_stream);
+            const u64 in = s_in[j];  // bit 63: the row has repeated documents, its counts are in ccnt
+            const u64 src = (in & ~(1ull << 63)) + idx;
+            doc[u] = ld_hint_u32(cdocs + src, pol_stream);
+            cnt[u] = (in >> 63) ? (u32)__ldg(ccnt + src) : 1u;
         }
     }
     // ptxas otherwise sinks every load next to its use and runs the kTrU chains one after another (one request in
@@ -570,8 +575,8 @@ __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs,
     for (int u = 0; u < kTrU; ++u) {
         const u32 idx = i0 + u * 32 + lane;
         if (FULL || idx < tot) {
-            v[u].x = (i64)ld_hint_u64(ids + (u32)cp[u], pol_keep);
-            v[u].y = (i64)(cp[u] >> 32);
+            v[u].x = (i64)ld_hint_u64(ids + doc[u], pol_keep);
+            v[u].y = (i64)cnt[u];
         }
     }
     __syncwarp();
@@ -582,7 +587,8 @@ __device__ __forceinline__ void translate_rounds(const u64* __restrict__ cpairs,
     }
 }
 
-__global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __restrict__ cpairs,
+__global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u32* __restrict__ cdocs,
+                                                                  const u16* __restrict__ ccnt,
                                                                   const u64* __restrict__ alloc_off,
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
@@ -611,10 +617,10 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         u64 base_in = 0, base_out = 0;
         if (q < npat) {
             const u16* sg = seg + ((size_t)(q / kTileWarps) * (nranges + 1) + r) * kTileWarps + (q % kTileWarps);
-            const u32 s = sg[0], e = sg[kTileWarps];
+            const u32 s = sg[0] & 0x7fffu, e = sg[kTileWarps] & 0x7fffu;
             len = e - s;
             if (len) {
-                base_in = alloc_off[q] + s;
+                base_in = (alloc_off[q] + s) | ((u64)(sg[0] >> 15) << 63);
                 base_out = row_off[q] + s;
             }
         }
@@ -628,15 +634,15 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u64* __r
         if (tot == 0) continue;
         __syncwarp();
         s_excl[warp][lane] = incl - len;
-        s_in[warp][lane] = base_in - (incl - len);
+        s_in[warp][lane] = base_in - (incl - len);  // the flag in bit 63 survives: offsets stay far below 2^63
         s_out[warp][lane] = base_out - (incl - len);
         __syncwarp();
         const u64* idp = reinterpret_cast<const u64*>(ids);
         u32 i0 = 0;
         for (; i0 + 32 * kTrU <= tot; i0 += 32 * kTrU)
-            translate_rounds<true>(cpairs, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
+            translate_rounds<true>(cdocs, ccnt, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
         if (i0 < tot)
-            translate_rounds<false>(cpairs, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
+            translate_rounds<false>(cdocs, ccnt, idp, pairs, s_excl[warp], s_in[warp], s_out[warp], i0, tot, lane, pol_keep, pol_stream);
     }
 }
 
@@ -832,20 +838,21 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         nranges = 1;
         rshift = 40;
     }
-    DevBuf<u64> cpairs((size_t)cap_pairs, st);
+    DevBuf<u32> cdocs((size_t)cap_pairs, st);
+    DevBuf<u16> ccnt((size_t)cap_pairs, st);  // only touched for rows with repeated documents
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
     // row_off first receives the exact row lengths, then becomes their exclusive scan = the CSR offsets
     if (hc[5] <= 128) {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<4>();
         gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
-                                                                              alloc_off.p, row_off.p, cpairs.p, seg.p, nranges,
+                                                                              alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
                                                                               rshift);
     } else {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
         CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
-                                                                               alloc_off.p, row_off.p, cpairs.p, seg.p, nranges,
+                                                                               alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
                                                                                rshift);
     }
     CDB_LAUNCH_CHECK();
@@ -861,7 +868,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         }
         const i64 nitems = ceil_div(npat, 32) * nranges;
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
-        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cpairs.p, alloc_off.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cdocs.p, ccnt.p, alloc_off.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
                                                          counters.p + 4);
         CDB_LAUNCH_CHECK();
     }
