@@ -395,13 +395,105 @@ __device__ __forceinline__ void warp_bitonic_regs(u32 (&x)[R], int lane, u32* tb
 
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 
+// Distribution sort for intervals whose documents are spread over the corpus (the usual case: a pattern's hits fall
+// into unrelated documents).  N = 32*R buckets by doc * N / nd (monotone in doc, so bucket order is doc order):
+// count with shared-memory atomics, scan, scatter; the array is then sorted up to the order inside each bucket, and
+// because neighbouring buckets are already in order, `largest bucket size` phases of an odd-even transposition over the
+// whole array (unconditional compare-exchanges of neighbours, in registers) finish it.  About 650 warp instructions
+// for 1024 keys whose largest bucket holds 6, against about 2 400 for the sorting network.  Returns false — with x[]
+// untouched — when some bucket holds more than kBucketMax keys (clustered or repeated documents): the caller then
+// runs the sorting network.  In: x[r] = key of element r*32 + lane (0xffffffff beyond occ).  Out: blocked layout,
+// lane holds ranks lane*R .. lane*R + R-1, like warp_bitonic_regs.
+//   s_out: 33*R words (pad_idx layout), s_cnt: 33*R words.  bucket_mul = floor(2^32 * 1024 / nd), saturated.
+constexpr u32 kBucketMax = 24;
+
+template <int R>
+__device__ __forceinline__ bool warp_bucket_sort(u32 (&x)[R], int occ, u32 bucket_mul, u32* s_out, u32* s_cnt, int lane) {
+    constexpr int N = 32 * R;
+    constexpr int SH = R == 32 ? 0 : R == 16 ? 1 : R == 8 ? 2 : R == 4 ? 3 : R == 2 ? 4 : 5;  // 1024 / N
+    static_assert(R >= 2 && R <= 32, "bucket sort: 2 <= R <= 32");
+    auto bucket = [&](u32 doc) { return pad_idx((int)min(__umulhi(doc, bucket_mul) >> SH, (u32)(N - 1))); };
+#pragma unroll
+    for (int t = 0; t < R + 1; ++t)
+        if (t * 32 + lane < 33 * R) s_cnt[t * 32 + lane] = 0;  // counter of bucket b lives at pad_idx(b) < 33*R
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (r * 32 + lane < occ) atomicAdd(&s_cnt[bucket(x[r])], 1u);
+    __syncwarp();
+    // exclusive scan of the counters; lane owns buckets lane*R .. lane*R + R-1 (conflict-free through the padding)
+    u32* mine = s_cnt + lane * R + ((lane * R) >> 5);
+    u32 sum = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const u32 c = mine[j];
+        sum += c;
+        mx = max(mx, c);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (mx > kBucketMax) return false;
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    u32 run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const u32 c = mine[j];
+        mine[j] = run;
+        run += c;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r * 32 + lane < occ) {
+            const u32 p = atomicAdd(&s_cnt[bucket(x[r])], 1u);
+            s_out[pad_idx((int)p)] = x[r];
+        }
+    }
+    __syncwarp();
+    {
+        const u32* src = s_out + lane * R + ((lane * R) >> 5);
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = lane * R + r < occ ? src[r] : 0xffffffffu;
+    }
+    __syncwarp();  // s_out is the caller's s_doc: all reads done before it is written again
+    if (mx >= 2) {
+        for (u32 ph = 0; ph < mx; ph += 2) {
+            // even phase: pairs (2i, 2i+1), all inside a lane (R is even)
+#pragma unroll
+            for (int r = 0; r + 1 < R; r += 2) {
+                const u32 a = x[r], b = x[r + 1];
+                x[r] = min(a, b);
+                x[r + 1] = max(a, b);
+            }
+            // odd phase: pairs (2i+1, 2i+2); the last key of a lane pairs with the first key of the next lane
+#pragma unroll
+            for (int r = 1; r + 1 < R; r += 2) {
+                const u32 a = x[r], b = x[r + 1];
+                x[r] = min(a, b);
+                x[r + 1] = max(a, b);
+            }
+            const u32 up = __shfl_down_sync(0xffffffffu, x[0], 1);
+            const u32 dn = __shfl_up_sync(0xffffffffu, x[R - 1], 1);
+            const u32 last = lane < 31 ? min(x[R - 1], up) : x[R - 1];
+            const u32 first = lane > 0 ? max(x[0], dn) : x[0];
+            x[R - 1] = last;
+            x[0] = first;
+        }
+    }
+    return true;
+}
+
 // Loads SA[l, l+occ) (coalesced, all R loads of a lane in flight at once), reduces to doc indices, sorts them in
 // registers and run-length encodes them straight from the registers: the distinct docs go to s_doc[0 .. nheads) in
 // ascending order, the rank of each run's first element to s_pos (s_pos[nheads] = occ), both indexed through
 // pad_idx.  Returns nheads; all_distinct tells that every run has length 1 (s_pos is then not written).
 template <typename SAT, int R>
-__device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32* s_doc, u32* s_pos,
-                                             int lane, bool& all_distinct) {
+__device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32 bucket_mul,
+                                             u32* s_doc, u32* s_pos, int lane, bool& all_distinct) {
     SAT v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -414,7 +506,12 @@ __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, 
         const int i = r * 32 + lane;
         x[r] = i < occ ? (u32)((u64)v[r] & mask) : 0xffffffffu;  // doc index <= 2^32-2 (bits1 <= 32)
     }
-    warp_bitonic_regs<R>(x, lane, s_doc);  // s_doc doubles as the transpose buffer (33*R words) before it is filled
+    // s_doc / s_pos double as the sorts' scratch (33*R words each) before they are filled
+    bool sorted = false;
+    if constexpr (R >= 8) {
+        if (bucket_mul) sorted = warp_bucket_sort<R>(x, occ, bucket_mul, s_doc, s_pos, lane);
+    }
+    if (!sorted) warp_bitonic_regs<R>(x, lane, s_doc);
     // lane holds ranks lane*R .. lane*R + R-1; a rank is a run head when its doc differs from the previous rank's
     const u32 prev_last = __shfl_up_sync(0xffffffffu, x[R - 1], 1);
     u32 hm = 0;
@@ -478,6 +575,7 @@ constexpr size_t warp_smem_bytes() {
 // out, half the registers and a tenth of the shared memory, so twice as many warps per SM hide the latency.
 template <typename SAT, int MAXR>
 __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
+                                                                                    u32 bucket_mul,
                                                                                     const i64* __restrict__ left,
                                                                                     const i64* __restrict__ right, i64 npat,
                                                                                     const u64* __restrict__ dlarge,
@@ -502,12 +600,12 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_ker
         d = dlarge[q];
     } else if (occ64 > 0) {
         const int occ = (int)occ64;
-        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
-        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
-        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, s_doc, s_pos, lane, all_distinct);
+        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
         d = (u64)nheads;
     }
     if (lane == 0) rowlen[q] = d;
@@ -842,16 +940,21 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u16> ccnt((size_t)cap_pairs, st);  // only touched for rows with repeated documents
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
+    // distribution-sort scale: bucket = doc * 1024 / nd (0 switches the sorting network on for every interval)
+    const char* env_buckets = getenv("CDB_GATHER_BUCKETS");
+    const bool use_buckets = !env_buckets || atoi(env_buckets) != 0;
+    const u32 bucket_mul =
+        use_buckets && ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
     // row_off first receives the exact row lengths, then becomes their exclusive scan = the CSR offsets
     if (hc[5] <= 128) {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<4>();
-        gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
+        gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p,
                                                                               alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
                                                                               rshift);
     } else {
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
         CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, left.p, right.p, npat, dlarge.p,
+        gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p,
                                                                                alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
                                                                                rshift);
     }

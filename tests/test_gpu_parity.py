@@ -182,6 +182,43 @@ def test_translate_many_doc_ranges(monkeypatch):
     ix.close()
 
 
+@pytest.mark.parametrize("buckets", ["1", "0"])
+def test_gather_distribution_sort_and_fallback(buckets, monkeypatch):
+    """gather_kernel sorts the documents of an interval with a distribution sort when they are spread over the corpus
+    and with the sorting network when they cluster (or with CDB_GATHER_BUCKETS=0); both must give the reference's rows.
+    Corpus A: 200 000 short documents, 6- and 7-byte patterns with ~730 / ~170 hits in unrelated documents (a few
+    documents twice).  Corpus B: every hit falls into the first 300 of 100 300 documents, most of them repeatedly."""
+    monkeypatch.setenv("CDB_GATHER_BUCKETS", buckets)
+    text, off, ids = corpora.uniform(200000, 20, seed=61, lo=ord("a"), hi=ord("d"))
+    ix = build(text, off, ids)
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    p6, o6 = corpora.uniform_patterns(150, 6, seed=62, lo=ord("a"), hi=ord("d"))
+    p7, o7 = corpora.uniform_patterns(150, 7, seed=63, lo=ord("a"), hi=ord("d"))
+    pats = [bytes(p6[o6[i]:o6[i + 1]]) for i in range(150)] + [bytes(p7[o7[i]:o7[i + 1]]) for i in range(150)]
+    pats += [b"abcd", b"dddddddd", b"zz"]  # large path / few hits / none, mixed into the batch
+    row_off, pairs = ix.locate_batch(pats)
+    lens = np.diff(row_off)
+    assert lens[:150].min() > 512 and lens[150:300].min() > 128  # the R = 32 and R = 8 code paths
+    for q, kw in enumerate(pats):
+        assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+    ix.close()
+
+    rng = np.random.default_rng(64)
+    head = rng.integers(ord("a"), ord("d") + 1, size=300 * 2000, dtype=np.uint8)
+    tail = rng.integers(ord("x"), ord("z") + 1, size=100000 * 8, dtype=np.uint8)
+    text = np.concatenate([head, tail])
+    off = np.concatenate([np.arange(300, dtype=np.int64) * 2000, 600000 + np.arange(100001, dtype=np.int64) * 8])
+    ids = np.arange(100300, dtype=np.int64)[::-1].copy() + 7
+    ix = build(text, off, ids)
+    sa, b1, _w = oracle.port.build_sa(text, off)
+    p5, o5 = corpora.uniform_patterns(200, 5, seed=65, lo=ord("a"), hi=ord("d"))
+    pats = [bytes(p5[o5[i]:o5[i + 1]]) for i in range(200)] + [b"xyz", b"xyzxyz", b"ab"]
+    row_off, pairs = ix.locate_batch(pats)
+    for q, kw in enumerate(pats):
+        assert np.array_equal(pairs[row_off[q]:row_off[q + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+    ix.close()
+
+
 def test_n1_layout_against_live_oracle():
     """Note N1 at a size with several radix levels above chuck_size: the suffix array must equal the oracle's
     signed-radix / unsigned-leaf layout and every query must return the reference's (sometimes non-brute-force)
