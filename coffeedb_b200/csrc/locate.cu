@@ -404,7 +404,7 @@ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 // untouched — when some bucket holds more than kBucketMax keys (clustered or repeated documents): the caller then
 // runs the sorting network.  In: x[r] = key of element r*32 + lane (0xffffffff beyond occ).  Out: blocked layout,
 // lane holds ranks lane*R .. lane*R + R-1, like warp_bitonic_regs.
-//   s_out: 33*R words (pad_idx layout), s_cnt: 33*R words.  bucket_mul = floor(2^32 * 1024 / nd), saturated.
+//   s_out: 33*R words (pad_idx layout), s_cnt: 33*R words, 16-byte aligned.  bucket_mul = floor(2^32 * 1024 / nd), saturated.
 constexpr u32 kBucketMax = 24;
 
 template <int R>
@@ -413,9 +413,10 @@ __device__ __forceinline__ bool warp_bucket_sort(u32 (&x)[R], int occ, u32 bucke
     constexpr int SH = R == 32 ? 0 : R == 16 ? 1 : R == 8 ? 2 : R == 4 ? 3 : R == 2 ? 4 : 5;  // 1024 / N
     static_assert(R >= 2 && R <= 32, "bucket sort: 2 <= R <= 32");
     auto bucket = [&](u32 doc) { return pad_idx((int)min(__umulhi(doc, bucket_mul) >> SH, (u32)(N - 1))); };
+    // counter of bucket b lives at pad_idx(b) < 33*R
 #pragma unroll
-    for (int t = 0; t < R + 1; ++t)
-        if (t * 32 + lane < 33 * R) s_cnt[t * 32 + lane] = 0;  // counter of bucket b lives at pad_idx(b) < 33*R
+    for (int t = 0; t < (33 * R / 4 + 31) / 32; ++t)
+        if (t * 32 + lane < 33 * R / 4) reinterpret_cast<uint4*>(s_cnt)[t * 32 + lane] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r)
