@@ -27,7 +27,7 @@ EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
     "cdb_build", "cdb_build_device", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
-    "cdb_splice", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count",
+    "cdb_splice", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats",
 ]
 
 CDB_OK = 0
@@ -91,6 +91,8 @@ def lib():
         L.cdb_sa_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.cdb_locate_batch.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Result)]
         L.cdb_result_free.argtypes = [C.POINTER(Result)]
+        L.cdb_query.argtypes = [vp, vp, C.c_int64, C.POINTER(Result)]
+        L.cdb_query_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cdb_result_free.restype = None
         L.cdb_locate_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp, C.POINTER(DeviceResult)]
         L.cdb_device_result_free.argtypes = [C.POINTER(DeviceResult)]
@@ -169,9 +171,26 @@ class StringIndex:
         _check(self._L.cdb_build(self._h))
 
     def query(self, keyword: bytes) -> list[tuple[int, int]]:
-        """string_index::query (src/index.cpp:237-326): [(id, count)] in ascending doc index."""
-        row_off, pairs = self.locate_batch([keyword])
-        return [(int(a), int(b)) for a, b in pairs]
+        """string_index::query (src/index.cpp:237-326): [(id, count)] in ascending doc index.  One keyword through
+        cdb_query: calls from concurrent threads (ctypes drops the GIL) share device batches."""
+        return [(int(a), int(b)) for a, b in self.query_array(keyword)]
+
+    def query_array(self, keyword: bytes) -> np.ndarray:
+        """query() as an int64 [d, 2] array."""
+        kw = bytes(keyword)
+        res = Result()
+        _check(self._L.cdb_query(self._h, kw, len(kw), C.byref(res)))
+        try:
+            tp = res.total_pairs
+            return np.ctypeslib.as_array(res.pairs, shape=(tp, 2)).copy() if tp else np.zeros((0, 2), np.int64)
+        finally:
+            self._L.cdb_result_free(C.byref(res))
+
+    def query_stats(self) -> dict:
+        """Coalescing counters of query(): keywords submitted, device batches issued, largest batch."""
+        q, b, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._L.cdb_query_stats(self._h, C.byref(q), C.byref(b), C.byref(m)))
+        return {"queries": q.value, "batches": b.value, "largest": m.value}
 
     # -- batched / device forms ------------------------------------------------------------------------
     def locate_batch(self, patterns, pat_off=None):

@@ -1,12 +1,15 @@
 // C ABI (include/coffeedb_b200.h) over the device index.  Every entry point converts C++ exceptions into a
 // status code + thread-local message; the three conditions the reference throws on carry the reference's
 // exact text (src/index.cpp:196,199,240).
+#include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <new>
 
+#include "../host/micro_batcher.hpp"
 #include "index.cuh"
 #include "locate.cuh"
 
@@ -72,7 +75,49 @@ struct HostResultOwner {
     size_t row_cap;
     void* pairs;
     size_t pairs_cap;
+    // cdb_query: the result is a view of one row of a shared batch result (kept alive by `shared`)
+    void* shared = nullptr;  // std::shared_ptr<QueryBatchResult>*
+    int64_t view_off[2] = {0, 0};
 };
+
+// One coalesced device batch of cdb_query callers: a host cdb_result, released when its last row view goes.
+struct QueryBatchResult {
+    cdb_result r{};
+    const int64_t* row_off = nullptr;
+    const int64_t* pairs = nullptr;
+    ~QueryBatchResult() { cdb_result_free(&r); }
+};
+struct QueryBackend {
+    const cdb_index* h;
+    std::shared_ptr<QueryBatchResult> operator()(const std::string& bytes, const std::vector<int64_t>& off) const {
+        auto res = std::make_shared<QueryBatchResult>();
+        const cdb_status s = cdb_locate_batch(h, bytes.data(), off.data(), (int64_t)off.size() - 1, &res->r);
+        if (s != CDB_OK) throw Error(s, cdb_last_error());  // rethrown in every member of the batch
+        res->row_off = res->r.row_off;
+        res->pairs = res->r.pairs;
+        return res;
+    }
+};
+using QueryBatcher = coffeedb_b200::micro_batcher<QueryBackend, QueryBatchResult>;
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    return std::max(lo, std::min(hi, atoi(e)));
+}
+
+static QueryBatcher& query_batcher(const Index* ix) {
+    std::lock_guard<std::mutex> lk(ix->batcher_mu);
+    if (!ix->batcher) {
+        // CDB_QUERY_MAX_BATCH keywords per device batch, CDB_QUERY_IN_FLIGHT batches on the device at a time (the
+        // second one overlaps its kernels with the first one's read-back), CDB_QUERY_LINGER_US extra wait of a
+        // batch leader for company (0: an idle device serves a lone caller at once)
+        ix->batcher = std::make_shared<QueryBatcher>(
+            QueryBackend{reinterpret_cast<const cdb_index*>(ix)}, (size_t)env_int("CDB_QUERY_MAX_BATCH", 1 << 16, 1, 1 << 24),
+            env_int("CDB_QUERY_IN_FLIGHT", 2, 1, 64), std::chrono::microseconds(env_int("CDB_QUERY_LINGER_US", 0, 0, 1000000)));
+    }
+    return *static_cast<QueryBatcher*>(ix->batcher.get());
+}
 
 struct DeviceSetter {
     int prev = -1;
@@ -443,10 +488,50 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
 void cdb_result_free(cdb_result* r) {
     if (!r || !r->_owner) return;
     HostResultOwner* own = static_cast<HostResultOwner*>(r->_owner);
+    if (own->shared) delete static_cast<std::shared_ptr<QueryBatchResult>*>(own->shared);
     if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
     if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
     delete own;
     std::memset(r, 0, sizeof(*r));
+}
+
+cdb_status cdb_query(const cdb_index* h, const void* keyword, int64_t len, cdb_result* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || len < 0 || (len > 0 && !keyword)) throw Error(CDB_ERR_ARG, "cdb_query: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    if (len == 0) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");  // src/index.cpp:239-241
+    QueryBatcher::row_view v = query_batcher(ix).query(std::string_view(static_cast<const char*>(keyword), (size_t)len));
+    HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
+    own->shared = new std::shared_ptr<QueryBatchResult>(std::move(v.owner));
+    own->view_off[1] = v.count;
+    int64_t occ = 0;
+    for (int64_t i = 0; i < v.count; ++i) occ += v.pairs[2 * i + 1];
+    out->npat = 1;
+    out->total_pairs = v.count;
+    out->total_occurrences = occ;
+    out->row_off = own->view_off;
+    out->pairs = v.pairs;
+    out->_owner = own;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_query_stats(const cdb_index* h, uint64_t* queries, uint64_t* batches, uint64_t* largest) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix) throw Error(CDB_ERR_ARG, "cdb_query_stats: bad argument");
+    coffeedb_b200::micro_batcher_stats st;
+    {
+        std::lock_guard<std::mutex> lk(ix->batcher_mu);
+        if (ix->batcher) st = static_cast<QueryBatcher*>(ix->batcher.get())->statistics();
+    }
+    if (queries) *queries = st.queries;
+    if (batches) *batches = st.batches;
+    if (largest) *largest = st.largest;
+    return CDB_OK;
+    CDB_CATCH
 }
 
 cdb_status cdb_locate_spans(const cdb_index* h, const void* kw, const int64_t* kw_off, int64_t nkw, const int64_t* docs,

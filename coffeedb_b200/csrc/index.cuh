@@ -6,6 +6,7 @@
 //   sa       u32|u64 [n]     packed suffix array, element = (offset_in_doc << bits1) | doc_index — the
 //                            reference's own element format (src/index.cpp:209-215), so export is a memcpy
 #pragma once
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -53,6 +54,9 @@ struct Index {
     // build statistics
     double build_ms = 0, sort_ms = 0;
     i64 rounds = 0, chunks = 0;
+    // cdb_query's coalescing queue (capi.cu), created on first use
+    mutable std::mutex batcher_mu;
+    mutable std::shared_ptr<void> batcher;
 
     ~Index();
     void free_device();

@@ -67,10 +67,12 @@ public:
 
     void build() override { check(cdb_build(h_)); }
 
+    // One keyword, as the server calls it (src/database.cpp:387-393).  Concurrent calls on the same index — the
+    // reference runs query() from up to max(8, hw-1) httplib threads — are coalesced into one device batch by
+    // cdb_query (micro_batcher.hpp); a lone call is served at once.
     result_type query(const std::string& keyword) const override {
-        const int64_t off[2] = {0, (int64_t)keyword.size()};
         cdb_result r{};
-        check(cdb_locate_batch(h_, keyword.data(), off, 1, &r));
+        check(cdb_query(h_, keyword.data(), (int64_t)keyword.size(), &r));
         result_type out = row(r, 0);
         cdb_result_free(&r);
         return out;

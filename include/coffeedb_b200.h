@@ -125,6 +125,17 @@ cdb_status cdb_sa_device_ptr(const cdb_index* idx, const void** d_sa);
  * lock, database.cpp:387-393). */
 cdb_status cdb_locate_batch(const cdb_index* idx, const void* pat, const int64_t* pat_off, int64_t npat, cdb_result* out);
 void cdb_result_free(cdb_result* r);
+/* string_index::query(keyword) for ONE keyword, the call the reference's server makes (src/database.cpp:387-393, once
+ * per keyword of a request — src/interface.cpp:79-86 — from up to max(8, hw-1) worker threads at a time).  Concurrent
+ * callers on the same index are coalesced into one device batch ("group commit", SURVEY.md §8f-2,
+ * coffeedb_b200/host/micro_batcher.hpp): whoever arrives while a batch is on the device joins the next one; a lone
+ * caller on an idle device is served at once.  `out` is a one-row result (npat = 1) that views the caller's row of
+ * the shared batch result; release it with cdb_result_free.  An empty keyword fails this caller only
+ * (CDB_ERR_EMPTY_KEYWORD); a device failure fails every member of the affected batch.
+ * Environment: CDB_QUERY_MAX_BATCH (65536), CDB_QUERY_IN_FLIGHT (2), CDB_QUERY_LINGER_US (0). */
+cdb_status cdb_query(const cdb_index* idx, const void* keyword, int64_t len, cdb_result* out);
+/* Counters of cdb_query on this index: keywords submitted, device batches issued, keywords in the largest batch. */
+cdb_status cdb_query_stats(const cdb_index* idx, uint64_t* queries, uint64_t* batches, uint64_t* largest);
 /* Same with patterns and results resident in device memory; work is enqueued on `stream` and the call
  * returns after the stream has drained (result sizes are data dependent). */
 cdb_status cdb_locate_batch_device(const cdb_index* idx, const void* d_pat, const int64_t* d_pat_off, int64_t npat,

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <atomic>
 #include <random>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -92,13 +94,34 @@ int main(int argc, char** argv) {
             kws.push_back(kw);
         }
         auto rows = static_cast<const sindex*>(p.get())->query_batch(kws);
+        std::vector<result_t> wants(kws.size());
         for (size_t t = 0; t < kws.size(); ++t) {
-            result_t want;
+            result_t& want = wants[t];
             for (size_t i = 0; i < docs.size(); ++i)
                 if (int64_t c = brute(docs[i], kws[t])) want.emplace_back(1000 + (int64_t)i * 3, c);
             REQUIRE(p->query(kws[t]) == want);
             REQUIRE(rows[t] == want);
         }
+        // the server's calling pattern: a pool of worker threads, one keyword per call (httplib.h:97-101); concurrent
+        // calls share device batches (cdb_query) and every caller still gets exactly its own row
+        std::atomic<int> bad{0};
+        std::vector<std::thread> workers;
+        for (int w = 0; w < 8; ++w)
+            workers.emplace_back([&, w] {
+                for (int rep = 0; rep < 4; ++rep)
+                    for (size_t t = 0; t < kws.size(); ++t) {
+                        const size_t k = (t + (size_t)w * 7) % kws.size();
+                        if (p->query(kws[k]) != wants[k]) ++bad;
+                    }
+            });
+        for (auto& w : workers) w.join();
+        REQUIRE(bad == 0);
+        uint64_t nq = 0, nb = 0, largest = 0;
+        REQUIRE(cdb_query_stats(static_cast<const sindex*>(p.get())->handle(), &nq, &nb, &largest) == CDB_OK);
+        REQUIRE(nq == kws.size() + 8 * 4 * kws.size());
+        REQUIRE(nb >= 1 && nb <= nq && largest >= 1 && largest <= 8);
+        std::printf("coalesced queries: %llu in %llu batches (largest %llu)\n", (unsigned long long)nq,
+                    (unsigned long long)nb, (unsigned long long)largest);
     }
     {  // $correlation composition (src/interface.cpp:79-146): OR of three keywords of one key, AND with a second key
         namespace cor = coffeedb_b200::correlation;

@@ -219,6 +219,45 @@ def test_gather_distribution_sort_and_fallback(buckets, monkeypatch):
     ix.close()
 
 
+def test_query_coalesces_concurrent_callers():
+    """cdb_query (what string_index::query maps to): one keyword per call, as the reference's server issues it from
+    its worker pool (src/database.cpp:387-393); concurrent callers share device batches and each one gets exactly the
+    row locate_batch gives for its keyword.  An empty keyword fails its own caller only, with the reference's text."""
+    import threading
+
+    text, off, ids = corpora.uniform(3000, 120, seed=71, lo=ord("a"), hi=ord("f"))
+    ix = build(text, off, ids)
+    pat, poff = corpora.uniform_patterns(240, 3, seed=72, lo=ord("a"), hi=ord("f"))
+    pats = [bytes(pat[poff[i]:poff[i + 1]]) for i in range(240)] + [b"zz", b"a"]  # no hit / large-interval path
+    row_off, pairs = ix.locate_batch(pats)
+    want = [pairs[row_off[q]:row_off[q + 1]] for q in range(len(pats))]
+    assert np.array_equal(ix.query_array(pats[0]), want[0])  # a lone caller
+    bad, errs = [], []
+
+    def worker(w):
+        try:
+            for rep in range(3):
+                for q in range(w, len(pats), 4):
+                    if not np.array_equal(ix.query_array(pats[q]), want[q]):
+                        bad.append((w, q))
+                if w == 2:
+                    with pytest.raises(RuntimeError, match="Empty keywords are not allowed"):
+                        ix.query(b"")
+        except Exception as e:  # noqa: BLE001 - reported below
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(16)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs and not bad, (errs[:3], bad[:5])
+    st = ix.query_stats()
+    assert st["queries"] == 1 + 3 * sum(len(range(w, len(pats), 4)) for w in range(16))
+    assert 1 <= st["batches"] <= st["queries"] and 1 <= st["largest"] <= 16
+    ix.close()
+
+
 def test_n1_layout_against_live_oracle():
     """Note N1 at a size with several radix levels above chuck_size: the suffix array must equal the oracle's
     signed-radix / unsigned-leaf layout and every query must return the reference's (sometimes non-brute-force)

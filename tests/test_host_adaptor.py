@@ -19,7 +19,7 @@ def compile_adaptor(name, extra=()):
     cdb.lib()  # fails loudly when the library has not been built
     exe = os.path.join(OUT, name)
     libdir = os.path.dirname(cdb.LIB_PATH)
-    cmd = ["g++", "-std=c++20", "-O1", "-w", *extra, SRC, "-o", exe, f"-L{libdir}", "-lcoffeedb_b200",
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-pthread", *extra, SRC, "-o", exe, f"-L{libdir}", "-lcoffeedb_b200",
            f"-Wl,-rpath,{libdir}"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return exe
@@ -45,3 +45,16 @@ def test_adaptor_on_device():
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "adaptor gpu ok" in r.stdout
+
+
+def test_micro_batcher_host_logic():
+    """coffeedb_b200/host/micro_batcher.hpp (the coalescing queue behind cdb_query / string_index::query) with a
+    host-only stand-in backend: own rows, batches form, batch-size / in-flight limits, linger, error delivery."""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "test_batcher")
+    src = os.path.join(ROOT, "tests", "host", "test_batcher.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-pthread", src, "-o", exe], check=True,
+                   capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "micro_batcher ok" in r.stdout
