@@ -441,6 +441,45 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
         if (pat_off[q + 1] <= pat_off[q]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
     cudaStream_t st = thread_ctx(ix->device).stream;
     HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
+    // small batches (experimental, CDB_SMALL_BATCH): one upload, two launches, one synchronisation; rows arrive in the
+    // thread's mapped pinned buffer and are copied into the caller's result
+    if (const int small = small_batch_limit(); small > 0 && npat > 0 && npat <= small) {
+        try {
+            SmallResult sr;
+            if (locate_small(*ix, (const u8*)pat, pat_off, npat, st, &sr)) {
+                i64 total_pairs = 0;
+                for (i64 q = 0; q < npat; ++q) total_pairs += (i64)sr.rowlen[q];
+                own->row_off = g_pinned.get((size_t)(npat + 1) * 8, &own->row_cap);
+                own->pairs = g_pinned.get((size_t)(total_pairs ? total_pairs : 1) * 16, &own->pairs_cap);
+                i64* ro = (i64*)own->row_off;
+                i64* pr = (i64*)own->pairs;
+                ro[0] = 0;
+                u64 base = 0;  // rows sit at the scan of the occurrence counts
+                for (i64 q = 0; q < npat; ++q) {
+                    std::memcpy(pr + 2 * ro[q], sr.pairs + 2 * base, (size_t)sr.rowlen[q] * 16);
+                    ro[q + 1] = ro[q] + (i64)sr.rowlen[q];
+                    base += sr.rowocc[q];
+                }
+                g_locate_stats = LocateStats{};
+                g_locate_stats.npat = npat;
+                g_locate_stats.total_pairs = total_pairs;
+                g_locate_stats.total_occ = sr.total_occ;
+                out->npat = npat;
+                out->total_pairs = total_pairs;
+                out->total_occurrences = sr.total_occ;
+                out->row_off = ro;
+                out->pairs = pr;
+                out->_owner = own;
+                return CDB_OK;
+            }
+        } catch (...) {
+            cudaStreamSynchronize(st);
+            if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+            if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+            delete own;
+            throw;
+        }
+    }
     cdb_device_result dr;
     std::memset(&dr, 0, sizeof(dr));
     try {

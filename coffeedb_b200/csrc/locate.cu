@@ -24,6 +24,8 @@
 // All integer work; bounded by HBM traffic and, in gather_kernel, by the ALU pipe (64*S + w*occ + 24*d
 // algorithmic bytes per pattern).
 #include <algorithm>
+#include <cstring>
+#include <map>
 #include <cstdlib>
 #include <vector>
 
@@ -1273,6 +1275,144 @@ void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, con
         spans.insert(spans.end(), uspans.begin() + 2 * a, uspans.begin() + 2 * b);
         span_off[t + 1] = (i64)spans.size() / 2;
     }
+}
+
+// ---- small batches (EXPERIMENTAL, off by default: CDB_SMALL_BATCH = largest batch that takes this path) ----------
+// One keyword through the general path costs ~130 us of launches, synchronisations and stream-ordered allocations
+// (a dozen kernels, three cudaStreamSynchronize, four copies), whatever the work.  A batch of up to kSmallMaxPat keywords
+// takes ONE upload, TWO launches and ONE synchronisation instead: the packed request (zeroed counters + offsets +
+// keyword bytes) goes up in a single copy, search_kernel finds the intervals, and small_gather_kernel does the rest per
+// warp — sort, run-length, ids[] lookup (random reads do not matter at this size) — writing (id, count) pairs straight
+// into mapped pinned memory of the calling thread at the scan of the occurrence counts, which every warp computes for
+// itself.  Batches with a long interval (> kWarpCap) or more than kSmallCapPairs occurrences report that in the header
+// and the caller falls back to the general path.  All buffers are cached per host thread and device.
+constexpr int kSmallMaxPat = 256;
+constexpr u64 kSmallCapPairs = 1u << 16;  // 1 MB of pairs
+constexpr size_t kSmallPatBytes = 16384;
+constexpr size_t kSmallHdrWords = 4;      // out: [0] long intervals [1] occurrences [2] empty-keyword flag [3] unused
+
+template <typename SAT>
+__global__ void __launch_bounds__(kTileWarps * 32) small_gather_kernel(const SAT* __restrict__ sa, u64 mask, u32 bucket_mul,
+                                                                         const i64* __restrict__ left,
+                                                                         const i64* __restrict__ right, int npat,
+                                                                         const u64* __restrict__ wocc,
+                                                                         const unsigned long long* __restrict__ counters,
+                                                                         const i64* __restrict__ ids, u64* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kTileWarps + warp;
+    u64* rowlen = out + kSmallHdrWords;          // exact row length of every pattern
+    u64* rowocc = rowlen + kSmallMaxPat;         // its occurrence count (rows sit at the scan of these)
+    longlong2* pairs = reinterpret_cast<longlong2*>(rowocc + kSmallMaxPat);
+    const u64 nlarge = counters[0], total = counters[1], err = counters[2] & 0xffffffffull;
+    if (q == 0 && lane == 0) {
+        out[0] = nlarge;
+        out[1] = total;
+        out[2] = err;
+    }
+    if (q >= npat || nlarge != 0 || err != 0 || total > kSmallCapPairs) return;  // the host falls back (or throws)
+    u64 base = 0;
+    for (int i = lane; i < q; i += 32) base += wocc[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<32>());
+    u32* s_pos = s_doc + 32 * 32 + 32;
+    const i64 l = left[q];
+    const int occ = (int)(right[q] - l);  // <= kWarpCap: no long interval in this batch
+    int nheads = 0;
+    bool all_distinct = false;
+    if (occ > 0) {
+        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 256) nheads = load_sort_rle<SAT, 8>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else if (occ <= 512) nheads = load_sort_rle<SAT, 16>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        else nheads = load_sort_rle<SAT, 32>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+    }
+    if (lane == 0) {
+        rowlen[q] = (u64)nheads;
+        rowocc[q] = (u64)occ;
+    }
+    for (int r = lane; r < nheads; r += 32) {
+        const u32 doc = s_doc[pad_idx(r)];
+        const i64 cnt = all_distinct ? 1 : (i64)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]);
+        pairs[base + r] = make_longlong2(__ldg(ids + doc), cnt);
+    }
+}
+
+struct SmallCtx {
+    u8* h_in = nullptr;   // pinned staging of the packed request
+    u8* d_in = nullptr;   // [counters: 8 words, zero][pat_off: npat + 1][keyword bytes]
+    u8* d_tmp = nullptr;  // left, right, wocc, large_list
+    u64* h_out = nullptr; // mapped pinned: header, rowlen, rowocc, pairs
+    u64* d_out = nullptr;
+};
+static constexpr size_t kSmallInBytes = 64 + 8 * (kSmallMaxPat + 1) + kSmallPatBytes;
+static constexpr size_t kSmallOutBytes = (kSmallHdrWords + 2 * kSmallMaxPat) * 8 + kSmallCapPairs * 16;
+
+static SmallCtx& small_ctx(int device) {
+    static thread_local std::map<int, SmallCtx> ctxs;  // lives as long as the thread (like its stream)
+    SmallCtx& c = ctxs[device];
+    if (!c.h_in) {
+        CDB_CUDA(cudaHostAlloc((void**)&c.h_in, kSmallInBytes, cudaHostAllocDefault));
+        CDB_CUDA(cudaMalloc((void**)&c.d_in, kSmallInBytes));
+        CDB_CUDA(cudaMalloc((void**)&c.d_tmp, (size_t)kSmallMaxPat * 32 + 64));
+        CDB_CUDA(cudaHostAlloc((void**)&c.h_out, kSmallOutBytes, cudaHostAllocMapped));
+        CDB_CUDA(cudaHostGetDevicePointer((void**)&c.d_out, c.h_out, 0));
+    }
+    return c;
+}
+
+template <typename SAT>
+static bool locate_small_typed(const Index& ix, const u8* pat, const i64* pat_off, int npat, cudaStream_t st, SmallResult* res) {
+    SmallCtx& sc = small_ctx(ix.device);
+    const i64 p0 = pat_off[0], pbytes = pat_off[npat] - p0;
+    std::memset(sc.h_in, 0, 64);
+    i64* h_off = reinterpret_cast<i64*>(sc.h_in + 64);
+    for (int q = 0; q <= npat; ++q) h_off[q] = pat_off[q] - p0;
+    u8* h_bytes = sc.h_in + 64 + 8 * (size_t)(npat + 1);
+    std::memcpy(h_bytes, pat + p0, (size_t)pbytes);
+    const size_t in_bytes = 64 + 8 * (size_t)(npat + 1) + (size_t)pbytes;
+    CDB_CUDA(cudaMemcpyAsync(sc.d_in, sc.h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(sc.d_in);
+    const i64* d_off = reinterpret_cast<const i64*>(sc.d_in + 64);
+    const u8* d_pat = sc.d_in + 64 + 8 * (size_t)(npat + 1);
+    i64* left = reinterpret_cast<i64*>(sc.d_tmp);
+    i64* right = left + kSmallMaxPat;
+    u64* wocc = reinterpret_cast<u64*>(right + kSmallMaxPat);
+    u32* large_list = reinterpret_cast<u32*>(wocc + kSmallMaxPat);
+    SearchCtx c = make_ctx(ix);
+    search_kernel<SAT><<<1, 256, 0, st>>>(c, ix.symtab, d_pat, d_off, (i64)npat, left, right, reinterpret_cast<int*>(counters + 2),
+                                         large_list, counters, wocc);
+    CDB_LAUNCH_CHECK();
+    const u32 bucket_mul = ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
+    const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
+    CDB_CUDA(cudaFuncSetAttribute(small_gather_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    small_gather_kernel<SAT><<<(unsigned)ceil_div((i64)npat, kTileWarps), kTileWarps * 32, smem, st>>>(
+        reinterpret_cast<const SAT*>(ix.d_sa), ix.mask, bucket_mul, left, right, npat, wocc, counters, ix.d_ids, sc.d_out);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaStreamSynchronize(st));
+    const u64* h = sc.h_out;
+    if (h[2]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
+    if (h[0] != 0 || h[1] > kSmallCapPairs) return false;  // long interval or too many occurrences: general path
+    res->total_occ = (i64)h[1];
+    res->rowlen = h + kSmallHdrWords;
+    res->rowocc = res->rowlen + kSmallMaxPat;
+    res->pairs = reinterpret_cast<const i64*>(res->rowocc + kSmallMaxPat);
+    return true;
+}
+
+int small_batch_limit() {
+    const char* e = getenv("CDB_SMALL_BATCH");  // read per call: the tests switch it
+    if (!e) return 0;                           // off until the path has been verified on a GPU
+    const int v = atoi(e);
+    return v < 0 ? 0 : (v > kSmallMaxPat ? kSmallMaxPat : v);
+}
+
+bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, cudaStream_t st, SmallResult* res) {
+    if (npat <= 0 || npat > kSmallMaxPat || pat_off[npat] - pat_off[0] > (i64)kSmallPatBytes) return false;
+    return ix.width == 4 ? locate_small_typed<u32>(ix, pat, pat_off, (int)npat, st, res)
+                         : locate_small_typed<u64>(ix, pat, pat_off, (int)npat, st, res);
 }
 
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,

@@ -5,6 +5,17 @@ namespace cdb {
 // Batched locate with patterns and results in device memory (see locate.cu).
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
                    cdb_device_result* out);
+// Small-batch fast path (locate.cu, experimental): one upload, two launches, one synchronisation.  On success the
+// rows are in mapped pinned memory of the calling thread — valid until its next call: row q has rowlen[q] pairs at
+// pairs + 2 * (rowocc[0] + ... + rowocc[q-1]).  Returns false when the batch has to take the general path.
+struct SmallResult {
+    i64 total_occ = 0;
+    const u64* rowlen = nullptr;
+    const u64* rowocc = nullptr;
+    const i64* pairs = nullptr;
+};
+int small_batch_limit();  // CDB_SMALL_BATCH (0 = path disabled)
+bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, cudaStream_t st, SmallResult* res);
 // Highlight spans (see spans.cu).
 void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const i64* docs, i64 ndocs,
                   cudaStream_t st, std::vector<i64>& span_off, std::vector<i64>& spans);

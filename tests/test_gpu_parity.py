@@ -2,6 +2,7 @@
 (coffeedb_b200 is a ctypes binding); expected values are the golden vectors generated from the compiled
 reference, the live oracle, and size-independent properties at larger sizes."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -255,6 +256,37 @@ def test_query_coalesces_concurrent_callers():
     st = ix.query_stats()
     assert st["queries"] == 1 + 3 * sum(len(range(w, len(pats), 4)) for w in range(16))
     assert 1 <= st["batches"] <= st["queries"] and 1 <= st["largest"] <= 16
+    ix.close()
+
+
+@pytest.mark.skipif(os.environ.get("CDB_TEST_EXPERIMENTAL") != "1",
+                    reason="small-batch path has not been run on a GPU yet: opt in with CDB_TEST_EXPERIMENTAL=1")
+def test_small_batch_path_matches_general_path(monkeypatch):
+    """CDB_SMALL_BATCH: batches of up to 256 keywords take one upload, two launches and one synchronisation; the
+    result must equal the general path's, and batches the path cannot take (a long interval, too many occurrences)
+    must fall back silently."""
+    text, off, ids = corpora.uniform(20000, 60, seed=81, lo=ord("a"), hi=ord("e"))
+    ix = build(text, off, ids)
+    pat, poff = corpora.sampled_patterns(text, off, 400, 5, 9, seed=82)  # <= ~370 occurrences each
+    pats = [bytes(pat[poff[i]:poff[i + 1]]) for i in range(400)]
+    p5, o5 = corpora.uniform_patterns(250, 5, seed=83, lo=ord("a"), hi=ord("e"))
+    many = [bytes(p5[o5[i]:o5[i + 1]]) for i in range(250)]  # 250 x ~370 occurrences: over the 65 536-pair capacity
+    batches = [pats[:1], pats[1:8], pats[8:72], pats[72:328], [b"zzzz"], [b"zz", pats[0], b"q"],
+               pats[:5] + [b"a"],  # b"a": ~240 000 occurrences, the long-interval path -> fallback
+               many]
+    want = [ix.locate_batch(b) for b in batches]
+    monkeypatch.setenv("CDB_SMALL_BATCH", "256")
+    for b, (wro, wpairs) in zip(batches, want):
+        ro, pairs = ix.locate_batch(b)
+        assert np.array_equal(ro, wro) and np.array_equal(pairs, wpairs), b[:3]
+    took_small = []
+    for b in batches:
+        ix.locate_batch(b)
+        took_small.append(cdb.last_locate_stats()["total_ms"] == 0.0)
+    assert took_small[:6] == [True] * 6 and took_small[6:] == [False, False]
+    with pytest.raises(RuntimeError, match="Empty keywords are not allowed"):
+        ix.locate_batch([b"ab", b""])
+    assert np.array_equal(ix.query_array(pats[3]), want[1][1][want[1][0][2]:want[1][0][3]])  # cdb_query on top of it
     ix.close()
 
 
