@@ -6,8 +6,8 @@ so when rank g indexes the documents ``[g*nd/W, (g+1)*nd/W)`` the full row of a 
 shard rows in rank order — per-document counts never need summing.  What the ranks exchange per batch is small:
 
 * the packed pattern batch, broadcast from the rank that received the request,
-* per-pattern (row length, occurrences) of every shard, one ``all_gather`` -> global CSR offsets by a scan in rank
-  order, and the occurrence totals the reference's ``count`` needs as column sums,
+* per-pattern (row length, occurrences) of every shard (4-byte integers when every shard has < 2^31 suffixes), one
+  ``all_gather`` -> global CSR offsets by a scan in rank order, and the occurrence totals the reference's ``count`` needs as column sums,
 * optionally the rows themselves, gathered to one rank (``gather_rows``), for callers that need the flat answer.
 
 Plumbing is ``torch.distributed`` (NCCL over NVLink on GPUs; the CPU tests run the same code over gloo with a fake
@@ -84,6 +84,7 @@ class ShardedStringIndex:
         self.nd_local = 0
         self.nd_global = None
         self.doc_base = None
+        self.narrow = False
 
     # -- corpus --------------------------------------------------------------------------------------------------
     def add_many(self, ids, text, doc_off):
@@ -102,15 +103,20 @@ class ShardedStringIndex:
         self._exchange_sizes()
 
     def _exchange_sizes(self):
-        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        mine = torch.tensor([self.nd_local], dtype=torch.int64, device=self.device)
+        info = getattr(self.local, "info", None)
+        n_local = int(info()["n"]) if info is not None else 1 << 62  # suffixes of this shard (unknown: assume large)
+        sizes = torch.zeros(2 * self.world, dtype=torch.int64, device=self.device)
+        mine = torch.tensor([self.nd_local, n_local], dtype=torch.int64, device=self.device)
         if self.world > 1:
             dist.all_gather_into_tensor(sizes, mine, group=self.group)
         else:
             sizes.copy_(mine)
-        sizes = sizes.cpu()
-        self.nd_global = int(sizes.sum())
-        self.doc_base = int(sizes[: self.rank].sum())
+        sizes = sizes.cpu().view(self.world, 2)
+        self.nd_global = int(sizes[:, 0].sum())
+        self.doc_base = int(sizes[: self.rank, 0].sum())
+        # per-pattern row lengths and occurrence counts of a shard are bounded by its suffix count: when every shard
+        # has fewer than 2^31 suffixes the per-batch exchange carries 4-byte instead of 8-byte integers
+        self.narrow = bool(int(sizes[:, 1].max()) < (1 << 31))
 
     # -- query ---------------------------------------------------------------------------------------------------
     def broadcast_patterns(self, patterns=None, pat_off=None, src: int = 0):
@@ -133,8 +139,18 @@ class ShardedStringIndex:
             d_off.copy_(torch.from_numpy(pat_off))
         if self.world > 1:
             dist.broadcast(d_pat, src, group=self.group)
-            dist.broadcast(d_off, src, group=self.group)
+            self._broadcast_offsets(d_off, d_pat.numel(), src)
         return d_pat, d_off
+
+    def _broadcast_offsets(self, d_off, nbytes: int, src: int):
+        """Pattern offsets travel as 4-byte integers whenever the packed batch is shorter than 2 GB."""
+        if nbytes >= (1 << 31):
+            dist.broadcast(d_off, src, group=self.group)
+            return
+        off32 = d_off.to(torch.int32) if self.rank == src else torch.empty(d_off.numel(), dtype=torch.int32, device=self.device)
+        dist.broadcast(off32, src, group=self.group)
+        if self.rank != src:
+            d_off.copy_(off32)
 
     def locate_local(self, d_pat, d_off):
         """This shard's rows for the batch -> (row_off, pairs[total,2], occ[npat], keep)."""
@@ -166,7 +182,7 @@ class ShardedStringIndex:
             d_pat, d_off = device_patterns
             if self.world > 1:
                 dist.broadcast(d_pat, src, group=self.group)
-                dist.broadcast(d_off, src, group=self.group)
+                self._broadcast_offsets(d_off, d_pat.numel(), src)
         else:
             d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
         npat = d_off.numel() - 1
@@ -175,12 +191,13 @@ class ShardedStringIndex:
         if self.world > 1:
             # ONE collective per batch: every shard's (row lengths, occurrences) per pattern.  The occurrence totals the
             # reference's `count` needs are the column sums, so no separate all_reduce.
-            mine = torch.stack([rows, occ]).reshape(-1)                       # [2 * npat]
-            allst = torch.empty(self.world * 2 * npat, dtype=torch.int64, device=self.device)
+            xdt = torch.int32 if self.narrow else torch.int64
+            mine = torch.stack([rows, occ]).reshape(-1).to(xdt)               # [2 * npat]
+            allst = torch.empty(self.world * 2 * npat, dtype=xdt, device=self.device)
             dist.all_gather_into_tensor(allst, mine, group=self.group)
             allst = allst.view(self.world, 2, npat)
-            shard_rows = allst[:, 0, :]
-            occ = allst[:, 1, :].sum(dim=0)
+            shard_rows = allst[:, 0, :].to(torch.int64)
+            occ = allst[:, 1, :].sum(dim=0, dtype=torch.int64)
         else:
             shard_rows = rows.view(1, npat)
         return ShardedResult(row_off, pairs, shard_rows, occ, self.rank, keep)

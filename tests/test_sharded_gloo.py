@@ -43,8 +43,18 @@ class OracleShard:
         row_off[1:] = np.cumsum([len(r) for r in rows])
         return row_off, (np.concatenate(rows) if rows and row_off[-1] else np.zeros((0, 2), np.int64))
 
+    def info(self):
+        return {"n": int(len(self.text))}
+
     def close(self):
         pass
+
+
+class OracleShardWide(OracleShard):
+    """Reports a suffix count beyond 2^31, which keeps the per-batch exchange on 8-byte integers."""
+
+    def info(self):
+        return {"n": 1 << 33}
 
 
 def _free_port():
@@ -55,7 +65,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, wide=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,10 +75,11 @@ def _worker(rank, world, port, q):
         text, off, ids = corpora.ragged(901, 50, seed=5, alphabet=b"abc")
         nd = len(ids)
         lo, hi = shard_range(nd, rank, world)
-        ix = ShardedStringIndex(device=torch.device("cpu"), index_factory=OracleShard)
+        ix = ShardedStringIndex(device=torch.device("cpu"), index_factory=OracleShardWide if wide else OracleShard)
         ix.add_many(ids[lo:hi], text, off[lo:hi + 1])
         ix.build()
         assert ix.nd_global == nd and ix.doc_base == lo
+        assert ix.narrow == (not wide)  # 4-byte exchange whenever every shard has < 2^31 suffixes
         spat, soff = corpora.sampled_patterns(text, off, 60, 1, 6, seed=6)
         pats = [bytes(spat[soff[i]:soff[i + 1]]) for i in range(60)] + [b"zz", b"a"]
         # only the source rank knows the request
@@ -99,12 +110,12 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_index_over_gloo(world):
+@pytest.mark.parametrize("world,wide", [(2, False), (3, False), (2, True)])
+def test_sharded_index_over_gloo(world, wide):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, wide)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=300) for _ in range(world)]
