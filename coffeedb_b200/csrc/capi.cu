@@ -106,6 +106,16 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     return std::max(lo, std::min(hi, atoi(e)));
 }
 
+// CDB_L2_PERSIST_MB (experiment switch, default: leave the device limit alone): size of the persisting-L2 carve-out,
+// which is what translate_kernel's evict_last hint on ids[] can draw on.  Device-wide; applied after a build.
+static void apply_l2_persist_limit() {
+    const char* e = getenv("CDB_L2_PERSIST_MB");
+    if (!e) return;
+    const long mb = atol(e);
+    if (mb < 0) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20) != cudaSuccess) cudaGetLastError();
+}
+
 static QueryBatcher& query_batcher(const Index* ix) {
     std::lock_guard<std::mutex> lk(ix->batcher_mu);
     if (!ix->batcher) {
@@ -298,6 +308,7 @@ cdb_status cdb_build(cdb_index* h) {
         ix->d_ids = (const i64*)ix->own_ids;
         ix->nd = nd;
         build_index(*ix, st);
+        apply_l2_persist_limit();
     } catch (...) {
         cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
@@ -330,6 +341,7 @@ cdb_status cdb_build_device(cdb_index* h, const void* d_text, const int64_t* d_d
     ix->nd = nd;
     try {
         build_index(*ix, (cudaStream_t)stream);
+        apply_l2_persist_limit();
     } catch (...) {
         cudaStreamSynchronize((cudaStream_t)stream);
         ix->free_device();
