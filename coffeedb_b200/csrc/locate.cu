@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "index.cuh"
@@ -577,7 +578,7 @@ constexpr size_t warp_smem_bytes() {
 // occurrences (short rows: sharded corpora, long keywords) — the same code with the long sorting networks compiled
 // out, half the registers and a tenth of the shared memory, so twice as many warps per SM hide the latency.
 template <typename SAT, int MAXR>
-__global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
+__global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5 : MAXR == 16 ? 4 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
                                                                                     u32 bucket_mul,
                                                                                     const i64* __restrict__ left,
                                                                                     const i64* __restrict__ right, i64 npat,
@@ -949,18 +950,28 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     const u32 bucket_mul =
         use_buckets && ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
     // row_off first receives the exact row lengths, then becomes their exclusive scan = the CSR offsets
-    if (hc[5] <= 128) {
-        const size_t smem = (size_t)kTileWarps * warp_smem_bytes<4>();
-        gather_kernel<SAT, 4><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p,
-                                                                              alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
-                                                                              rshift);
-    } else {
-        const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
-        CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gather_kernel<SAT, 32><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p,
-                                                                               alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges,
-                                                                               rshift);
-    }
+    // kernel variant by the batch's longest warp-path interval: shorter sorting arrays need fewer registers and less
+    // shared memory, so more warps per SM hide the latency.  The 256- and 512-key variants (shards of a split corpus)
+    // are EXPERIMENTAL — not yet run on a GPU — and only chosen with CDB_GATHER_VARIANTS=1.
+    const char* env_var = getenv("CDB_GATHER_VARIANTS");
+    const bool mid_variants = env_var && atoi(env_var) != 0;
+    auto launch_gather = [&](auto maxr_tag) {
+        constexpr int MAXR = decltype(maxr_tag)::value;
+        const size_t smem = (size_t)kTileWarps * warp_smem_bytes<MAXR>();
+        if (smem > 48 * 1024)
+            CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gather_kernel<SAT, MAXR><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat,
+                                                                                 dlarge.p, alloc_off.p, row_off.p, cdocs.p, ccnt.p,
+                                                                                 seg.p, nranges, rshift);
+    };
+    if (hc[5] <= 128)
+        launch_gather(std::integral_constant<int, 4>{});
+    else if (mid_variants && hc[5] <= 256)
+        launch_gather(std::integral_constant<int, 8>{});
+    else if (mid_variants && hc[5] <= 512)
+        launch_gather(std::integral_constant<int, 16>{});
+    else
+        launch_gather(std::integral_constant<int, 32>{});
     CDB_LAUNCH_CHECK();
     scan_in_place(row_off.p, (u64)npat, st);
     CDB_CUDA(cudaEventRecord(ev[4], st));

@@ -290,6 +290,35 @@ def test_small_batch_path_matches_general_path(monkeypatch):
     ix.close()
 
 
+@pytest.mark.skipif(os.environ.get("CDB_TEST_EXPERIMENTAL") != "1",
+                    reason="256-/512-key gather variants have not been run on a GPU yet: opt in with CDB_TEST_EXPERIMENTAL=1")
+def test_gather_mid_size_variants(monkeypatch):
+    """CDB_GATHER_VARIANTS=1: batches whose longest interval is <= 256 / <= 512 occurrences run gather_kernel compiled
+    for 8 / 16 keys per lane (more warps per SM); rows must not change."""
+    text, off, ids = corpora.uniform(200000, 20, seed=91, lo=ord("a"), hi=ord("d"))
+    ix = build(text, off, ids)
+    for m in (7, 6):  # ~130-210 occurrences (the 256-key variant) and ~650-810 (the full-size kernel)
+        p, o = corpora.uniform_patterns(200, m, seed=92 + m, lo=ord("a"), hi=ord("d"))
+        pats = [bytes(p[o[i]:o[i + 1]]) for i in range(200)]
+        want = ix.locate_batch(pats)
+        monkeypatch.setenv("CDB_GATHER_VARIANTS", "1")
+        got = ix.locate_batch(pats)
+        monkeypatch.delenv("CDB_GATHER_VARIANTS")
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), m
+    # 512-key variant: half of the 6-byte patterns' documents (a corpus of 100 000 documents)
+    text, off, ids = corpora.uniform(100000, 20, seed=95, lo=ord("a"), hi=ord("d"))
+    ix2 = build(text, off, ids)
+    p, o = corpora.uniform_patterns(200, 6, seed=96, lo=ord("a"), hi=ord("d"))
+    pats = [bytes(p[o[i]:o[i + 1]]) for i in range(200)]
+    want = ix2.locate_batch(pats)
+    assert 256 < np.diff(want[0]).max() <= 512
+    monkeypatch.setenv("CDB_GATHER_VARIANTS", "1")
+    got = ix2.locate_batch(pats)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    ix.close()
+    ix2.close()
+
+
 def test_n1_layout_against_live_oracle():
     """Note N1 at a size with several radix levels above chuck_size: the suffix array must equal the oracle's
     signed-radix / unsigned-leaf layout and every query must return the reference's (sometimes non-brute-force)
