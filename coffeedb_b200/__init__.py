@@ -27,7 +27,7 @@ EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
     "cdb_build", "cdb_build_device", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
-    "cdb_splice", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats",
+    "cdb_splice", "cdb_verify_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
 ]
 
 CDB_OK = 0
@@ -102,10 +102,12 @@ def lib():
         L.cdb_spans_free.restype = None
         L.cdb_splice.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
         L.cdb_splice.restype = C.c_int64
+        L.cdb_verify_sa.argtypes = [vp, i64p]
         L.cdb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p]
         L.cdb_last_locate_stats.argtypes = [C.POINTER(C.c_double), i64p]
         L.cdb_last_locate_stats.restype = None
         L.cdb_launch_count.restype = C.c_uint64
+        L.cdb_trim.restype = None
         _lib = L
     return _lib
 
@@ -249,6 +251,16 @@ class StringIndex:
         t, s, r, c = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
         _check(self._L.cdb_build_stats(self._h, C.byref(t), C.byref(s), C.byref(r), C.byref(c)))
         return {"total_ms": t.value, "sort_ms": s.value, "rounds": r.value, "chunks": c.value}
+
+    def verify_sa(self) -> dict:
+        """Independent device-side check of the suffix array (adjacent-pair order under the reference's comparator,
+        src/index.cpp:92-93 / note N1; permutation; ties).  `ok` is True iff nothing is out of place."""
+        out = (C.c_int64 * 8)()
+        _check(self._L.cdb_verify_sa(self._h, out))
+        keys = ["inversions", "invalid", "duplicates", "ties", "ties_unordered", "signed_queue", "unchecked", "signed_rule_pairs"]
+        d = {k: int(out[i]) for i, k in enumerate(keys)}
+        d["ok"] = not (d["inversions"] or d["invalid"] or d["duplicates"] or d["ties_unordered"] or d["unchecked"])
+        return d
 
     def export_sa(self) -> np.ndarray:
         """The packed suffix array widened to uint64 (element = (offset << bits) | doc, src/index.cpp:209-215)."""

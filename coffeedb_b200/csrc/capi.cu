@@ -8,10 +8,12 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../host/micro_batcher.hpp"
 #include "index.cuh"
 #include "locate.cuh"
+#include "verify.cuh"
 
 namespace cdb {
 
@@ -46,6 +48,7 @@ public:
             if (it != free_.end() && it->first <= bytes * 2 + (1 << 20)) {
                 void* p = it->second;
                 *cap_out = it->first;
+                held_ -= it->first;
                 free_.erase(it);
                 return p;
             }
@@ -56,17 +59,45 @@ public:
         *cap_out = cap;
         return p;
     }
+    // Keeps at most kMaxBytes / kMaxEntries of idle buffers (CDB_PINNED_POOL_MB overrides the byte cap): beyond that the
+    // largest idle buffers go back to the driver, so a server with varying batch sizes does not pile up page-locked memory.
     void put(void* p, size_t cap) {
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            free_.emplace(cap, p);
+            held_ += cap;
+            while (!free_.empty() && (held_ > max_bytes() || free_.size() > kMaxEntries)) {
+                auto it = std::prev(free_.end());
+                held_ -= it->first;
+                drop.push_back(it->second);
+                free_.erase(it);
+            }
+        }
+        for (void* q : drop) cudaFreeHost(q);
+    }
+    void trim() {
         std::lock_guard<std::mutex> g(mu_);
-        free_.emplace(cap, p);
+        for (auto& kv : free_) cudaFreeHost(kv.second);
+        free_.clear();
+        held_ = 0;
     }
     ~PinnedPool() {
         for (auto& kv : free_) cudaFreeHost(kv.second);
     }
 
 private:
+    static constexpr size_t kMaxEntries = 64;
+    static size_t max_bytes() {
+        static const size_t v = [] {
+            const char* e = getenv("CDB_PINNED_POOL_MB");
+            return e ? (size_t)atoll(e) << 20 : (size_t)32 << 30;  // the 10 GB configuration's result is 12.9 GB
+        }();
+        return v;
+    }
     std::mutex mu_;
     std::multimap<size_t, void*> free_;
+    size_t held_ = 0;
 };
 static PinnedPool g_pinned;
 
@@ -104,16 +135,6 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     const char* e = getenv(name);
     if (!e) return dflt;
     return std::max(lo, std::min(hi, atoi(e)));
-}
-
-// CDB_L2_PERSIST_MB (experiment switch, default: leave the device limit alone): size of the persisting-L2 carve-out,
-// which is what translate_kernel's evict_last hint on ids[] can draw on.  Device-wide; applied after a build.
-static void apply_l2_persist_limit() {
-    const char* e = getenv("CDB_L2_PERSIST_MB");
-    if (!e) return;
-    const long mb = atol(e);
-    if (mb < 0) return;
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20) != cudaSuccess) cudaGetLastError();
 }
 
 static QueryBatcher& query_batcher(const Index* ix) {
@@ -202,6 +223,8 @@ const char* cdb_version(void) { return "coffeedb_b200 0.1 (sm_100a)"; }
 
 uint64_t cdb_launch_count(void) { return g_launches.load(); }
 
+void cdb_trim(void) { g_pinned.trim(); }
+
 void cdb_last_locate_stats(double* ms6, int64_t* counts4) {
     const LocateStats& s = g_locate_stats;
     if (ms6) {
@@ -268,14 +291,24 @@ cdb_status cdb_add_many(cdb_index* h, const int64_t* ids, const void* text, cons
     if (!ix || nd < 0 || (nd > 0 && (!ids || !doc_off))) throw Error(CDB_ERR_ARG, "cdb_add_many: bad argument");
     if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
     if (nd == 0) return CDB_OK;
-    const u8* p = static_cast<const u8*>(text);
-    const i64 base = (i64)ix->h_text.size() - doc_off[0];
-    ix->h_text.insert(ix->h_text.end(), p + doc_off[0], p + doc_off[nd]);
-    ix->h_ids.insert(ix->h_ids.end(), ids, ids + nd);
-    ix->h_off.reserve(ix->h_off.size() + nd);
-    for (i64 d = 1; d <= nd; ++d) {
+    // validate everything before the staging vectors are touched: a rejected call leaves the index unchanged
+    if (doc_off[0] < 0) throw Error(CDB_ERR_ARG, "cdb_add_many: doc_off[0] must be >= 0");
+    for (i64 d = 1; d <= nd; ++d)
         if (doc_off[d] < doc_off[d - 1]) throw Error(CDB_ERR_ARG, "cdb_add_many: doc_off must be non-decreasing");
-        ix->h_off.push_back(base + doc_off[d]);
+    if (doc_off[nd] > doc_off[0] && !text) throw Error(CDB_ERR_ARG, "cdb_add_many: text is NULL");
+    const u8* p = static_cast<const u8*>(text);
+    const size_t text0 = ix->h_text.size(), ids0 = ix->h_ids.size(), off0 = ix->h_off.size();
+    try {
+        const i64 base = (i64)text0 - doc_off[0];
+        if (doc_off[nd] > doc_off[0]) ix->h_text.insert(ix->h_text.end(), p + doc_off[0], p + doc_off[nd]);
+        ix->h_ids.insert(ix->h_ids.end(), ids, ids + nd);
+        ix->h_off.reserve(off0 + (size_t)nd);
+        for (i64 d = 1; d <= nd; ++d) ix->h_off.push_back(base + doc_off[d]);
+    } catch (...) {  // out of host memory half way: roll back
+        ix->h_text.resize(text0);
+        ix->h_ids.resize(ids0);
+        ix->h_off.resize(off0);
+        throw;
     }
     return CDB_OK;
     CDB_CATCH
@@ -308,7 +341,6 @@ cdb_status cdb_build(cdb_index* h) {
         ix->d_ids = (const i64*)ix->own_ids;
         ix->nd = nd;
         build_index(*ix, st);
-        apply_l2_persist_limit();
     } catch (...) {
         cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
@@ -341,7 +373,6 @@ cdb_status cdb_build_device(cdb_index* h, const void* d_text, const int64_t* d_d
     ix->nd = nd;
     try {
         build_index(*ix, (cudaStream_t)stream);
-        apply_l2_persist_limit();
     } catch (...) {
         cudaStreamSynchronize((cudaStream_t)stream);
         ix->free_device();
@@ -393,6 +424,17 @@ cdb_status cdb_sa_device_ptr(const cdb_index* h, const void** d_sa) {
     const Index* ix = reinterpret_cast<const Index*>(h);
     if (!ix || !ix->built || !d_sa) throw Error(CDB_ERR_STATE, "index has not been built");
     *d_sa = ix->d_sa;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_verify_sa(const cdb_index* h, int64_t* out8) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out8) throw Error(CDB_ERR_ARG, "cdb_verify_sa: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    DeviceSetter ds(ix->device);
+    verify_index(*ix, thread_ctx(ix->device).stream, out8);
     return CDB_OK;
     CDB_CATCH
 }
@@ -453,7 +495,7 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
         if (pat_off[q + 1] <= pat_off[q]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
     cudaStream_t st = thread_ctx(ix->device).stream;
     HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
-    // small batches (experimental, CDB_SMALL_BATCH): one upload, two launches, one synchronisation; rows arrive in the
+    // small batches (CDB_SMALL_BATCH, default 256 keywords): one upload, two launches, one synchronisation; rows arrive in the
     // thread's mapped pinned buffer and are copied into the caller's result
     if (const int small = small_batch_limit(); small > 0 && npat > 0 && npat <= small) {
         try {

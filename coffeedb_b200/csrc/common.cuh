@@ -18,7 +18,20 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (grid-size heuristics of the build kernels)
+
+// SM count of the current device (persistent grids are sized from it)
+inline int num_sms() {
+    static thread_local int cached_dev = -1, cached = kNumSMs;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
 
 struct Error : std::runtime_error {
     cdb_status code;

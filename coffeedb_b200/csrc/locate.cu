@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -817,6 +818,22 @@ static int bits_for_u64(u64 v) {
     return b;
 }
 
+// resident CTAs per SM of a kernel (its persistent grids are exactly one wave), cached per kernel and device
+static int resident_ctas(const void* kernel, int threads) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    CDB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({kernel, dev});
+    if (it != cache.end()) return it->second;
+    int v = 0;
+    CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, 0));
+    v = v > 0 ? v : 1;
+    cache[{kernel, dev}] = v;
+    return v;
+}
+
 // Doc-range partition of ids[] for translate_kernel: ranges of 2^rshift documents (default 2^22 = 32 MB of ids,
 // CDB_RANGE_BITS overrides), at most kMaxRanges of them.
 static void ids_ranges(i64 nd, int* nranges, int* rshift) {
@@ -951,10 +968,10 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         use_buckets && ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
     // row_off first receives the exact row lengths, then becomes their exclusive scan = the CSR offsets
     // kernel variant by the batch's longest warp-path interval: shorter sorting arrays need fewer registers and less
-    // shared memory, so more warps per SM hide the latency.  The 256- and 512-key variants (shards of a split corpus)
-    // are EXPERIMENTAL — not yet run on a GPU — and only chosen with CDB_GATHER_VARIANTS=1.
+    // shared memory, so more warps per SM hide the latency.  The 256- and 512-key variants serve the shards of a split
+    // corpus (CDB_GATHER_VARIANTS=0 leaves only the 128- and 1024-key kernels).
     const char* env_var = getenv("CDB_GATHER_VARIANTS");
-    const bool mid_variants = env_var && atoi(env_var) != 0;
+    const bool mid_variants = !env_var || atoi(env_var) != 0;
     auto launch_gather = [&](auto maxr_tag) {
         constexpr int MAXR = decltype(maxr_tag)::value;
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<MAXR>();
@@ -977,14 +994,9 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     {
-        static int per_sm = 0;  // resident translate CTAs per SM: its grid is exactly one wave
-        if (!per_sm) {
-            int v = 0;
-            CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, translate_kernel, kTrWarps * 32, 0));
-            per_sm = v > 0 ? v : 1;
-        }
         const i64 nitems = ceil_div(npat, 32) * nranges;
-        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)kNumSMs * per_sm);
+        const int per_sm = resident_ctas((const void*)translate_kernel, kTrWarps * 32);
+        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)num_sms() * per_sm);
         translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cdocs.p, ccnt.p, alloc_off.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
                                                          counters.p + 4);
         CDB_LAUNCH_CHECK();
@@ -1288,7 +1300,7 @@ void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, con
     }
 }
 
-// ---- small batches (EXPERIMENTAL, off by default: CDB_SMALL_BATCH = largest batch that takes this path) ----------
+// ---- small batches (CDB_SMALL_BATCH = largest batch that takes this path, default 256; 0 = general path only) ------
 // One keyword through the general path costs ~130 us of launches, synchronisations and stream-ordered allocations
 // (a dozen kernels, three cudaStreamSynchronize, four copies), whatever the work.  A batch of up to kSmallMaxPat keywords
 // takes ONE upload, TWO launches and ONE synchronisation instead: the packed request (zeroed counters + offsets +
@@ -1414,8 +1426,8 @@ static bool locate_small_typed(const Index& ix, const u8* pat, const i64* pat_of
 }
 
 int small_batch_limit() {
-    const char* e = getenv("CDB_SMALL_BATCH");  // read per call: the tests switch it
-    if (!e) return 0;                           // off until the path has been verified on a GPU
+    const char* e = getenv("CDB_SMALL_BATCH");  // read per call: the tests switch it (0 = general path only)
+    if (!e) return kSmallMaxPat;
     const int v = atoi(e);
     return v < 0 ? 0 : (v > kSmallMaxPat ? kSmallMaxPat : v);
 }

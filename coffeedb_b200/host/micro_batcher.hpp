@@ -73,9 +73,12 @@ public:
         leave_guard leave{this, &lk};
         if (!open_) open_ = std::make_shared<batch>();
         std::shared_ptr<batch> b = open_;
-        const size_t mine = b->n++;
+        // strong guarantee: the keyword's bytes and offset go in first (either may throw bad_alloc, and a slot without
+        // an offset would shift every later member's row); the slot is counted last
+        b->off.reserve(b->off.size() + 1);
         b->bytes.append(keyword.data(), keyword.size());
-        b->off.push_back((int64_t)b->bytes.size());
+        b->off.push_back((int64_t)b->bytes.size());  // cannot throw: reserved above
+        const size_t mine = b->n++;
         ++stats_.queries;
         if (b->n >= max_batch_) {
             open_.reset();  // full: later arrivals start the next batch
@@ -83,7 +86,11 @@ public:
         }
         if (mine == 0) {
             slot_cv_.wait(lk, [&] { return in_flight_ < max_in_flight_; });
-            if (linger_.count() > 0 && b->n < max_batch_) b->cv.wait_for(lk, linger_, [&] { return b->n >= max_batch_; });
+            if (linger_.count() > 0 && b->n < max_batch_) {
+                b->cv.wait_for(lk, linger_, [&] { return b->n >= max_batch_; });
+                // the lock was dropped while lingering: another leader may have taken the slot
+                slot_cv_.wait(lk, [&] { return in_flight_ < max_in_flight_; });
+            }
             if (open_ == b) open_.reset();  // close: nobody joins from here on
             ++in_flight_;
             ++stats_.batches;

@@ -81,6 +81,8 @@ class ShardedStringIndex:
         self.device = device
         make = index_factory or (lambda: StringIndex(device=device.index if device.type == "cuda" else -1))
         self.local = make()
+        # collectives and p2p calls take GLOBAL ranks; `src` / `dst` arguments of this class are ranks inside `group`
+        self._global = (lambda r: dist.get_global_rank(group, r)) if (dist.is_initialized() and group is not None) else (lambda r: r)
         self.nd_local = 0
         self.nd_global = None
         self.doc_base = None
@@ -130,7 +132,7 @@ class ShardedStringIndex:
                 pat, pat_off = np.ascontiguousarray(patterns, np.uint8), np.ascontiguousarray(pat_off, np.int64)
             hdr[0], hdr[1] = len(pat), len(pat_off) - 1
         if self.world > 1:
-            dist.broadcast(hdr, src, group=self.group)
+            dist.broadcast(hdr, self._global(src), group=self.group)
         nbytes, npat = int(hdr[0]), int(hdr[1])
         d_pat = torch.zeros(nbytes + 8, dtype=torch.uint8, device=self.device)
         d_off = torch.zeros(npat + 1, dtype=torch.int64, device=self.device)
@@ -138,17 +140,17 @@ class ShardedStringIndex:
             d_pat[:nbytes].copy_(torch.from_numpy(pat))
             d_off.copy_(torch.from_numpy(pat_off))
         if self.world > 1:
-            dist.broadcast(d_pat, src, group=self.group)
+            dist.broadcast(d_pat, self._global(src), group=self.group)
             self._broadcast_offsets(d_off, d_pat.numel(), src)
         return d_pat, d_off
 
     def _broadcast_offsets(self, d_off, nbytes: int, src: int):
         """Pattern offsets travel as 4-byte integers whenever the packed batch is shorter than 2 GB."""
         if nbytes >= (1 << 31):
-            dist.broadcast(d_off, src, group=self.group)
+            dist.broadcast(d_off, self._global(src), group=self.group)
             return
         off32 = d_off.to(torch.int32) if self.rank == src else torch.empty(d_off.numel(), dtype=torch.int32, device=self.device)
-        dist.broadcast(off32, src, group=self.group)
+        dist.broadcast(off32, self._global(src), group=self.group)
         if self.rank != src:
             d_off.copy_(off32)
 
@@ -181,7 +183,7 @@ class ShardedStringIndex:
         if device_patterns is not None:
             d_pat, d_off = device_patterns
             if self.world > 1:
-                dist.broadcast(d_pat, src, group=self.group)
+                dist.broadcast(d_pat, self._global(src), group=self.group)
                 self._broadcast_offsets(d_off, d_pat.numel(), src)
         else:
             d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
@@ -215,7 +217,7 @@ class ShardedStringIndex:
                 else:
                     buf = torch.empty((totals[r], 2), dtype=torch.int64, device=self.device)
                     if totals[r]:
-                        dist.recv(buf, src=r, group=self.group)
+                        dist.recv(buf, src=self._global(r), group=self.group)
                     parts.append(buf)
             out = torch.empty((int(res.global_row_off[-1]), 2), dtype=torch.int64, device=self.device)
             # destination of entry j of shard r's row q: global_row_off[q] + sum_{r' < r} rows[r'][q] + j
@@ -231,7 +233,7 @@ class ShardedStringIndex:
                 base += rows
             return res.global_row_off, out
         if totals[self.rank]:
-            dist.send(res.pairs.contiguous(), dst=dst, group=self.group)
+            dist.send(res.pairs.contiguous(), dst=self._global(dst), group=self.group)
         return None
 
     def close(self):

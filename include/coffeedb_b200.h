@@ -103,7 +103,12 @@ cdb_status cdb_add_many(cdb_index* idx, const int64_t* ids, const void* text, co
  * array on the device.  Element = (offset_in_doc << bits) | doc_index, 4 bytes wide iff bits1+bits2 <= 32. */
 cdb_status cdb_build(cdb_index* idx);
 /* Same, from a corpus already resident in device memory (text[n], doc_off[nd+1], ids[nd] are BORROWED and
- * must outlive the index).  `stream` is a cudaStream_t (NULL = default stream). */
+ * must outlive the index).  `stream` is a cudaStream_t (NULL = default stream).
+ * Contract of the borrowed buffers: doc_off[0] == 0 and doc_off is non-decreasing; d_text is 16-byte aligned and has at
+ * least 64 READABLE bytes after its last document, i.e. the allocation is >= doc_off[nd] + 64 bytes (their content
+ * does not matter): the kernels fetch text in aligned 8- and 16-byte windows, and a window that starts inside the
+ * last document may reach past its end.  cdb_build pads its own copy; a caller of this entry point must allocate
+ * the padding itself. */
 cdb_status cdb_build_device(cdb_index* idx, const void* d_text, const int64_t* d_doc_off, const int64_t* d_ids,
                             int64_t nd, void* stream);
 
@@ -118,6 +123,15 @@ cdb_status cdb_prefix_directory(const cdb_index* idx, int32_t* symbols, int32_t*
 cdb_status cdb_export_sa(const cdb_index* idx, void* buf, int64_t buf_bytes);
 /* Device pointer of the packed suffix array (borrowed). */
 cdb_status cdb_sa_device_ptr(const cdb_index* idx, const void** d_sa);
+
+/* Independent device-side check of the built suffix array (test / bench instrumentation; shares no code with the build).
+ * Every adjacent pair is compared with the reference's comparator (std::string_view <, src/index.cpp:92-93; in the
+ * note-N1 layout the signed rule of src/index.h:66-73 for groups larger than chuck_size, src/index.cpp:97-125), and the
+ * array is checked to be a permutation of all (doc, offset) pairs.
+ * out8 = {inversions, invalid elements, duplicate positions, ties (adjacent byte-identical suffixes), ties not in
+ * ascending packed order, pairs queued for the signed-rule check, queued pairs left unchecked, pairs checked under the
+ * signed rule}.  A correct array has out8[0] = out8[1] = out8[2] = out8[4] = out8[6] = 0. */
+cdb_status cdb_verify_sa(const cdb_index* idx, int64_t* out8);
 
 /* Batched string_index::query(keyword) (src/index.cpp:237-326): pattern q = pat[pat_off[q], pat_off[q+1]).
  * An empty pattern fails the whole batch with CDB_ERR_EMPTY_KEYWORD.  Re-entrant: may be called concurrently
@@ -163,6 +177,9 @@ cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_
 void cdb_last_locate_stats(double* ms6, int64_t* counts4);
 /* Number of CUDA kernels this library has launched in this process. */
 uint64_t cdb_launch_count(void);
+/* Returns the idle pinned host buffers the library keeps for result re-use to the driver (the pool is also capped:
+ * CDB_PINNED_POOL_MB, default 32 GB, at most 64 buffers). */
+void cdb_trim(void);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,14 @@ def test_suffix_array_is_a_permutation(big):
     assert int(s2) % (1 << 64) == want2 % (1 << 64) or int(s2) == ((want2 + (1 << 63)) % (1 << 64)) - (1 << 63)
 
 
+def test_suffix_array_order_verified_on_device(big):
+    """n adjacent-pair compares with the comparator of src/index.cpp:92-93 + the permutation bit map, on the device,
+    independent of the build and of the oracle: 0 inversions, 0 invalid, 0 duplicates."""
+    ix, _text, _ids = big
+    v = ix.verify_sa()
+    assert v["ok"] and v["inversions"] == 0 and v["invalid"] == 0 and v["duplicates"] == 0, v
+
+
 def test_rows_equal_brute_force_scan(big):
     ix, text, ids = big
     pat, poff = corpora.uniform_patterns(24, 5, seed=5)

@@ -42,8 +42,10 @@ def test_suffix_array_matches_reference(name, golden):
     ix.close()
 
 
+@pytest.mark.parametrize("small", ["0", "256"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_locate_matches_reference(name, golden):
+def test_locate_matches_reference(name, small, golden, monkeypatch):
+    monkeypatch.setenv("CDB_SMALL_BATCH", small)  # the general path and the small-batch path
     text, off, ids, pats = cases.CASES[name]()
     ix = build(text, off, ids)
     row_off, pairs = ix.locate_batch(golden[f"{name}/pat"], golden[f"{name}/pat_off"])
@@ -118,6 +120,7 @@ def test_chunked_build_equals_single_chunk():
 def test_large_interval_path(limit, monkeypatch):
     """Intervals longer than the warp path's capacity go through the device radix sort, in sub-batches of bounded
     size (CDB_LARGE_LIMIT occurrences; "1" = one pattern per sub-batch)."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")  # these batches are small: keep them on the general path
     if limit:
         monkeypatch.setenv("CDB_LARGE_LIMIT", limit)
     text, off, ids = corpora.uniform(20000, 50, seed=43, lo=ord("a"), hi=ord("c"))
@@ -167,6 +170,7 @@ def test_highlight_spans_match_reference(golden):
 def test_translate_many_doc_ranges(monkeypatch):
     """translate_kernel walks ids[] by doc range (32 MB slices at production sizes); CDB_RANGE_BITS shrinks the
     ranges so that a small corpus exercises the multi-range path, including rows that miss most ranges."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")  # these batches are small: keep them on the general path
     text, off, ids = corpora.uniform(20000, 60, seed=51, lo=ord("a"), hi=ord("e"))
     ix = build(text, off, ids)
     sa, b1, _w = oracle.port.build_sa(text, off)
@@ -189,6 +193,7 @@ def test_gather_distribution_sort_and_fallback(buckets, monkeypatch):
     and with the sorting network when they cluster (or with CDB_GATHER_BUCKETS=0); both must give the reference's rows.
     Corpus A: 200 000 short documents, 6- and 7-byte patterns with ~730 / ~170 hits in unrelated documents (a few
     documents twice).  Corpus B: every hit falls into the first 300 of 100 300 documents, most of them repeatedly."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")  # these batches are small: keep them on the general path
     monkeypatch.setenv("CDB_GATHER_BUCKETS", buckets)
     text, off, ids = corpora.uniform(200000, 20, seed=61, lo=ord("a"), hi=ord("d"))
     ix = build(text, off, ids)
@@ -259,10 +264,8 @@ def test_query_coalesces_concurrent_callers():
     ix.close()
 
 
-@pytest.mark.skipif(os.environ.get("CDB_TEST_EXPERIMENTAL") != "1",
-                    reason="small-batch path has not been run on a GPU yet: opt in with CDB_TEST_EXPERIMENTAL=1")
 def test_small_batch_path_matches_general_path(monkeypatch):
-    """CDB_SMALL_BATCH: batches of up to 256 keywords take one upload, two launches and one synchronisation; the
+    """CDB_SMALL_BATCH (default 256; 0 = off): batches of up to 256 keywords take one upload, two launches and one synchronisation; the
     result must equal the general path's, and batches the path cannot take (a long interval, too many occurrences)
     must fall back silently."""
     text, off, ids = corpora.uniform(20000, 60, seed=81, lo=ord("a"), hi=ord("e"))
@@ -274,8 +277,10 @@ def test_small_batch_path_matches_general_path(monkeypatch):
     batches = [pats[:1], pats[1:8], pats[8:72], pats[72:328], [b"zzzz"], [b"zz", pats[0], b"q"],
                pats[:5] + [b"a"],  # b"a": ~240 000 occurrences, the long-interval path -> fallback
                many]
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")
     want = [ix.locate_batch(b) for b in batches]
-    monkeypatch.setenv("CDB_SMALL_BATCH", "256")
+    assert cdb.last_locate_stats()["total_ms"] > 0.0  # the general path ran
+    monkeypatch.delenv("CDB_SMALL_BATCH")  # default: on
     for b, (wro, wpairs) in zip(batches, want):
         ro, pairs = ix.locate_batch(b)
         assert np.array_equal(ro, wro) and np.array_equal(pairs, wpairs), b[:3]
@@ -290,29 +295,29 @@ def test_small_batch_path_matches_general_path(monkeypatch):
     ix.close()
 
 
-@pytest.mark.skipif(os.environ.get("CDB_TEST_EXPERIMENTAL") != "1",
-                    reason="256-/512-key gather variants have not been run on a GPU yet: opt in with CDB_TEST_EXPERIMENTAL=1")
 def test_gather_mid_size_variants(monkeypatch):
-    """CDB_GATHER_VARIANTS=1: batches whose longest interval is <= 256 / <= 512 occurrences run gather_kernel compiled
+    """CDB_GATHER_VARIANTS (default 1; 0 = only the 128- and 1024-key kernels): batches whose longest interval is <= 256 / <= 512 occurrences run gather_kernel compiled
     for 8 / 16 keys per lane (more warps per SM); rows must not change."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")  # these batches are small: keep them on the general path
     text, off, ids = corpora.uniform(200000, 20, seed=91, lo=ord("a"), hi=ord("d"))
     ix = build(text, off, ids)
     for m in (7, 6):  # ~130-210 occurrences (the 256-key variant) and ~650-810 (the full-size kernel)
         p, o = corpora.uniform_patterns(200, m, seed=92 + m, lo=ord("a"), hi=ord("d"))
         pats = [bytes(p[o[i]:o[i + 1]]) for i in range(200)]
+        monkeypatch.setenv("CDB_GATHER_VARIANTS", "0")
         want = ix.locate_batch(pats)
-        monkeypatch.setenv("CDB_GATHER_VARIANTS", "1")
-        got = ix.locate_batch(pats)
         monkeypatch.delenv("CDB_GATHER_VARIANTS")
+        got = ix.locate_batch(pats)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), m
     # 512-key variant: half of the 6-byte patterns' documents (a corpus of 100 000 documents)
     text, off, ids = corpora.uniform(100000, 20, seed=95, lo=ord("a"), hi=ord("d"))
     ix2 = build(text, off, ids)
     p, o = corpora.uniform_patterns(200, 6, seed=96, lo=ord("a"), hi=ord("d"))
     pats = [bytes(p[o[i]:o[i + 1]]) for i in range(200)]
+    monkeypatch.setenv("CDB_GATHER_VARIANTS", "0")
     want = ix2.locate_batch(pats)
     assert 256 < np.diff(want[0]).max() <= 512
-    monkeypatch.setenv("CDB_GATHER_VARIANTS", "1")
+    monkeypatch.delenv("CDB_GATHER_VARIANTS")
     got = ix2.locate_batch(pats)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     ix.close()
@@ -348,6 +353,7 @@ def test_n1_layout_against_live_oracle():
 
 def test_prefix_directory_on_and_off(monkeypatch):
     """Same answers with the prefix directory disabled (reference recurrences) and at several directory depths."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")  # these batches are small: keep them on the general path
     text, off, ids = corpora.ragged(4000, 80, seed=71, alphabet=b"abcdefg")
     sa, b1, _w = oracle.port.build_sa(text, off)
     spat, soff = corpora.sampled_patterns(text, off, 200, 1, 14, seed=72)
@@ -562,3 +568,68 @@ def test_reference_size_limit_errors():
         ix.close()
         del doc_off
         torch.cuda.empty_cache()
+
+
+# ---- cdb_verify_sa: the independent device-side order / permutation check ------------------------------------------
+class _DevView:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_verifier_accepts_every_golden_case(name, golden):
+    """The verifier (adjacent pairs under the reference's comparator, signed rule in the note-N1 layout; permutation)
+    accepts the arrays that are bit-identical to the compiled reference's, and counts exactly the ties the canonical
+    array holds (adjacent elements with byte-identical suffixes)."""
+    text, off, ids, _ = cases.CASES[name]()
+    ix = build(text, off, ids)
+    v = ix.verify_sa()
+    assert v["ok"], v
+    sa = ix.export_sa()
+    inf = ix.info()
+    docs = (sa & np.uint64(inf["mask"])).astype(np.int64)
+    offs = (sa >> np.uint64(inf["bits"])).astype(np.int64)
+    t = text.tobytes()
+    suf = [t[off[d] + o: off[d + 1]] for d, o in zip(docs.tolist(), offs.tolist())] if inf["n"] <= 200_000 else None
+    if suf is not None:
+        assert v["ties"] == sum(1 for a, b in zip(suf, suf[1:]) if a == b)
+    if name.startswith("n1"):
+        assert v["signed_rule_pairs"] > 0  # the signed rule really decided pairs in the note-N1 cases
+    ix.close()
+
+
+def test_verifier_detects_corruption():
+    import torch
+    text, off, ids = corpora.uniform(300, 200, seed=77)
+    ix = build(text, off, ids)
+    inf = ix.info()
+    assert ix.verify_sa()["ok"]
+    sa = torch.as_tensor(_DevView(ix.sa_device_ptr(), inf["n"], "<i4" if inf["width"] == 4 else "<i8"), device="cuda:0")
+    a, b = int(sa[1000]), int(sa[40000])
+    sa[1000], sa[40000] = b, a          # two elements swapped: still a permutation, no longer sorted
+    torch.cuda.synchronize()
+    v = ix.verify_sa()
+    assert not v["ok"] and v["inversions"] >= 2 and v["duplicates"] == 0 and v["invalid"] == 0
+    sa[1000], sa[40000] = a, a          # one element twice: a duplicate position (and one missing)
+    torch.cuda.synchronize()
+    v = ix.verify_sa()
+    assert not v["ok"] and v["duplicates"] == 1
+    sa[40000] = b
+    sa[5] = (199 + 50) << inf["bits"]   # offset beyond the end of document 0
+    torch.cuda.synchronize()
+    v = ix.verify_sa()
+    assert not v["ok"] and v["invalid"] == 1
+    ix.close()
+
+
+def test_verifier_rejects_plain_order_where_reference_is_signed():
+    """On a mixed-byte corpus the plainly sorted array (compat_signed = 0) is NOT the reference's layout: a verifier
+    applying the reference's rules must flag it, and accept it when told the index is in plain order."""
+    text, off, ids, _ = cases.CASES["n1_mixed"]()
+    plain = build(text, off, ids, compat_signed=False)
+    assert plain.verify_sa()["ok"]      # checked under its own (unsigned) rule
+    ref = build(text, off, ids)
+    assert ref.verify_sa()["ok"] and ref.verify_sa()["signed_rule_pairs"] > 0
+    assert not np.array_equal(plain.export_sa(), ref.export_sa())
+    plain.close()
+    ref.close()

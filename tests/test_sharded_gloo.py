@@ -110,6 +110,55 @@ def _worker(rank, world, port, q, wide=False):
         dist.destroy_process_group()
 
 
+def _subgroup_worker(rank, world, port, q):
+    """Shards on a SUBSET of the ranks (global ranks 1 and 2 of 3): group-local ranks differ from global ranks, which the
+    collectives and the send/recv of gather_rows must translate."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from coffeedb_b200.sharded import ShardedStringIndex, shard_range
+        grp = dist.new_group([1, 2])
+        if rank in (1, 2):
+            text, off, ids = corpora.ragged(400, 40, seed=15, alphabet=b"ab")
+            g_rank, g_world = dist.get_rank(grp), 2
+            lo, hi = shard_range(len(ids), g_rank, g_world)
+            ix = ShardedStringIndex(group=grp, device=torch.device("cpu"), index_factory=OracleShard)
+            assert ix.rank == g_rank and ix.world == 2
+            ix.add_many(ids[lo:hi], text, off[lo:hi + 1])
+            ix.build()
+            pats = [b"ab", b"ba", b"aab", b"bbbb", b"zz"]
+            res = ix.locate_batch(pats if g_rank == 1 else None, src=1)  # group rank 1 = global rank 2 holds the request
+            flat = ix.gather_rows(res, dst=1)
+            if g_rank == 1:
+                sa, b1, _w = oracle.port.build_sa(text, off)
+                gro, gp = flat
+                for qi, kw in enumerate(pats):
+                    assert np.array_equal(gp.numpy()[gro[qi]:gro[qi + 1]], oracle.port.query(text, off, ids, sa, b1, kw)), kw
+            else:
+                assert flat is None
+        q.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_index_on_a_subgroup():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(3)]
+    for p in procs:
+        p.join(60)
+    assert all(msg == "ok" for _r, msg in out), out
+
+
 @pytest.mark.parametrize("world,wide", [(2, False), (3, False), (2, True)])
 def test_sharded_index_over_gloo(world, wide):
     ctx = mp.get_context("spawn")
