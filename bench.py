@@ -162,6 +162,152 @@ def pick_workload(name, world):
     return "cfg3"
 
 
+
+def brute_rows(text, ids, L, snd, kws):
+    """Independent check, written in torch: (id, count) rows of every keyword in ascending doc index of THIS shard, from
+    a plain scan of its text (no suffix array, no library code)."""
+    import torch
+    n = snd * L
+    rows = []
+    for kw in kws:
+        m = len(kw)
+        hit = text[: n - m + 1] == kw[0]
+        for j in range(1, m):
+            hit &= text[j: n - m + 1 + j] == kw[j]
+        pos = torch.nonzero(hit).flatten()
+        del hit
+        pos = pos[(pos % L) <= L - m]  # an occurrence never crosses a document end
+        docs, counts = torch.unique(pos // L, return_counts=True)
+        rows.append(torch.stack([ids[docs], counts], dim=1).cpu().numpy())
+    return rows
+
+
+def sharded_row_parity(sh, text, ids, w, snd, pat, poff, rank, world, nsample=48):
+    """Row-level parity of the sharded path (N > 1), inside the bench run: a sample of the batch's keywords is located
+    collectively, the flat answer is assembled on rank 0 (gather_rows: shard rows concatenated in rank order) and
+    compared with the concatenation of every shard's brute-force rows."""
+    import torch.distributed as dist
+    step = max(1, w["npat"] // nsample)
+    kws = [bytes(pat[poff[q]:poff[q + 1]]) for q in range(0, w["npat"], step)][:nsample]
+    res = sh.locate_batch(kws if rank == 0 else None, src=0)
+    flat = sh.gather_rows(res, dst=0)
+    mine = brute_rows(text, ids, w["doclen"], snd, kws)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    if rank != 0:
+        return None
+    gro, gp = flat
+    gro, gp = gro.cpu().numpy(), gp.cpu().numpy()
+    bad = 0
+    for q in range(len(kws)):
+        want = np.concatenate([gathered[r][q] for r in range(world)]) if world else np.zeros((0, 2), np.int64)
+        bad += not np.array_equal(gp[gro[q]:gro[q + 1]], want)
+    return {"status": "ok" if bad == 0 else f"MISMATCH in {bad} rows", "patterns": len(kws), "pairs": int(gro[-1]),
+            "how": "gather_rows on rank 0 vs per-shard brute-force scans (torch) concatenated in rank order"}
+
+
+def secondary_workloads(sh, ix, text, snd, w, dev, hbm_peak):
+    """Extra, driver-visible numbers beside the headline (N = 1): W8s on the same index — 8-byte keywords sampled from
+    the corpus, longer than the prefix directory, so the search refines by binary search — and the cfg2
+    workload (1 GB corpus, 10^5 keywords) on its own index."""
+    import torch
+    import coffeedb_b200 as cdb
+    out = {}
+
+    def timed(sh_, d_pat, d_poff, npat, steps=3):
+        for _ in range(2):
+            sh_.locate_batch(device_patterns=(d_pat, d_poff), src=0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ph = {k: 0.0 for k in ("search_ms", "gather_ms", "translate_ms", "total_ms")}
+        e0.record()
+        for _ in range(steps):
+            res = sh_.locate_batch(device_patterns=(d_pat, d_poff), src=0)
+            st = cdb.last_locate_stats()
+            for k in ph:
+                ph[k] += st[k] / steps
+            pairs, occ = int(res.pairs.shape[0]), int(st["occurrences"])
+            del res
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"queries_per_sec": npat / (ms / 1e3), "ms_per_step": ms, "phases_ms": ph, "pairs_per_step": pairs,
+                "occurrences_per_step": occ}
+
+    # W8s
+    npat, L = w["npat"], w["doclen"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    docs_s = torch.randint(0, snd, (npat,), device=dev, generator=g)
+    offs_s = torch.randint(0, L - 8 + 1, (npat,), device=dev, generator=g)
+    idx = (docs_s * L + offs_s).unsqueeze(1) + torch.arange(8, device=dev).unsqueeze(0)
+    d_pat = torch.zeros(npat * 8 + 8, dtype=torch.uint8, device=dev)
+    d_pat[: npat * 8] = text[idx.reshape(-1)]
+    d_poff = torch.arange(npat + 1, dtype=torch.int64, device=dev) * 8
+    del idx, docs_s, offs_s
+    r = timed(sh, d_pat, d_poff, npat)
+    inf = ix.info()
+    S = 2 * int(np.ceil(np.log2(max(inf["n"], 2))))
+    r["algorithmic_bytes_per_step"] = (64.0 * S) * npat + inf["width"] * r["occurrences_per_step"] + 24.0 * r["pairs_per_step"]
+    r["frac_of_hbm_peak"] = r["algorithmic_bytes_per_step"] / (r["phases_ms"]["total_ms"] / 1e3) / 1e9 / hbm_peak
+    r["what"] = "10^6 eight-byte keywords sampled from the corpus (every one hits), same index; 64*S + w*occ + 24*d bytes"
+    out["w8s"] = r
+    del d_pat, d_poff
+    # cfg2
+    try:
+        from coffeedb_b200.sharded import ShardedStringIndex
+        w2 = dict(WORKLOADS["cfg2"])
+        t2, o2, i2, snd2 = make_shard(w2, 0, 1, dev)
+        sh2 = ShardedStringIndex(device=dev)
+        sh2.build_device(t2.data_ptr(), o2.data_ptr(), i2.data_ptr(), snd2, torch.cuda.current_stream().cuda_stream, keep=(t2, o2, i2))
+        b2 = sh2.local.build_stats()
+        p2, po2 = make_patterns(w2)
+        dp = torch.zeros(len(p2) + 8, dtype=torch.uint8, device=dev)
+        dp[: len(p2)] = torch.from_numpy(p2).to(dev)
+        dpo = torch.from_numpy(po2).to(dev)
+        r2 = timed(sh2, dp, dpo, w2["npat"], steps=5)
+        r2["build_ms"] = b2["total_ms"]
+        r2["build_corpus_GB_per_s"] = w2["nd"] * w2["doclen"] / 1e9 / (b2["total_ms"] / 1e3)
+        r2["what"] = "BASELINE configs[1]: 10^7 docs x 100 B, 10^5 five-byte keywords per step"
+        out["cfg2"] = r2
+        sh2.close()
+        del t2, o2, i2, dp, dpo
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 - secondary numbers must not take the bench line down
+        out["cfg2"] = {"error": repr(e)[:200]}
+    # cfg5 shape on one GPU: 1 GiB of valid UTF-8 in documents of up to 64 KB — 64-bit elements, the note-N1 layout, no
+    # prefix directory: the search runs the reference's own recurrences (src/index.cpp:262-287), one thread per keyword
+    try:
+        from coffeedb_b200.sharded import ShardedStringIndex
+        from tests import corpora
+        t5, o5, i5, nd5, n5 = corpora.utf8_corpus_on_device(1 << 30, seed=55, device_index=dev.index or 0)
+        sh5 = ShardedStringIndex(device=dev)
+        sh5.build_device(t5.data_ptr(), o5.data_ptr(), i5.data_ptr(), nd5, torch.cuda.current_stream().cuda_stream, keep=(t5, o5, i5))
+        b5 = sh5.local.build_stats()
+        v5 = sh5.local.verify_sa()
+        np5 = 100_000
+        g = torch.Generator(device=dev)
+        g.manual_seed(77)
+        starts = torch.randint(0, n5 - 8, (np5,), device=dev, generator=g)
+        dp = torch.zeros(np5 * 8 + 8, dtype=torch.uint8, device=dev)
+        dp[: np5 * 8] = t5[(starts.unsqueeze(1) + torch.arange(8, device=dev).unsqueeze(0)).reshape(-1)]
+        dpo = torch.arange(np5 + 1, dtype=torch.int64, device=dev) * 8
+        r5 = timed(sh5, dp, dpo, np5, steps=5)
+        inf5 = sh5.local.info()
+        r5.update({"build_ms": b5["total_ms"], "build_corpus_GB_per_s": n5 / 1e9 / (b5["total_ms"] / 1e3), "rounds": b5["rounds"],
+                   "docs": nd5, "corpus_bytes": n5, "sa_width": inf5["width"], "verified": bool(v5["ok"]),
+                   "signed_rule_pairs": v5["signed_rule_pairs"], "prefix_directory_symbols": sh5.local.prefix_directory()["symbols"],
+                   "what": "BASELINE configs[4] shape on one GPU (1 GiB): UTF-8 documents of up to 64 KB, note-N1 layout; "
+                           "10^5 eight-byte keywords sampled from the corpus (they may straddle documents: then no hit)"})
+        out["cfg5_shape"] = r5
+        sh5.close()
+        del t5, o5, i5, dp, dpo
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["cfg5_shape"] = {"error": repr(e)[:200]}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ reference
 def reference_index_from_gpu(w, verbose=False):
     """Full-size index for the reference's query(): corpus generated as in our arm, suffix array built on the GPU
@@ -227,10 +373,11 @@ def run_reference(args):
     else:
         ref, inf = reference_self_built(w)
         how = f"reference build()+query() on the first {inf['nd']} documents of {wname} (no GPU to build the full index)"
-    # bounded sample per step: ~3 s of host time
+    # every step runs the SAME batch as our arm's step (all npat keywords of the workload); on a slow host the step is
+    # capped at ~20 s of host time and says so
     probe = min(w["npat"], 20_000)
     s, _tp, _to = ref.query_batch_timed(pat[: poff[probe]], poff[: probe + 1], threads)
-    per_step = int(min(w["npat"], max(probe, 3.0 / max(s / probe, 1e-9))))
+    per_step = int(min(w["npat"], max(probe, 20.0 / max(s / probe, 1e-9))))
     times = []
     tp = to = 0
     for it in range(args.warmup + args.steps):
@@ -239,17 +386,32 @@ def run_reference(args):
             times.append(s)
     total = float(np.sum(times))
     val = per_step * len(times) / total
+    # the reference's OWN build, on a bounded prefix of the same corpus (the full 10^10-suffix build takes tens of
+    # minutes on host cores): string_index::build() (src/index.cpp:178-236), all host threads
+    rb = None
+    try:
+        r2, inf2 = reference_self_built(w, nd_cap=1_000_000)
+        rb = {"docs": inf2["nd"], "corpus_bytes": inf2["n"], "seconds": inf2["build_s"],
+              "corpus_GB_per_s": inf2["n"] / 1e9 / inf2["build_s"], "threads": threads,
+              "what": "string_index::build() of the unmodified reference on 10^6 documents of the workload's shape (100 MB)"}
+        r2.close()
+    except Exception as e:  # noqa: BLE001
+        rb = {"error": repr(e)[:200]}
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": wname, "docs": w["nd"], "doc_bytes": w["doclen"], "patterns_per_step": per_step,
-                   "pattern_bytes": w["m"], "n_suffixes": inf["n"]},
+        "config": {"workload": wname, "docs": w["nd"], "doc_bytes": w["doclen"], "corpus_bytes": w["nd"] * w["doclen"],
+                   "patterns_per_step": per_step, "pattern_bytes": w["m"], "n_suffixes_per_gpu": inf["n"],
+                   "sa_width": inf.get("width"),
+                   "l2": "host caches; inputs far larger than any cache",
+                   "parallelism": f"{threads} host threads pulling 64-keyword blocks (the reference's httplib pool pattern)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": f"{per_step} of {w['npat']} patterns per step; {how}",
                          "pairs_per_step": tp, "occurrences_per_step": to},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_build": rb,
     }
     print(json.dumps(out))
 
@@ -291,6 +453,11 @@ def run_ours(args):
     build_wall = time.perf_counter() - t0
     inf, bst = ix.info(), ix.build_stats()
     n_shard, width = inf["n"], inf["width"]
+    # independent device-side check of the built suffix array: every adjacent pair under the reference's comparator
+    # (src/index.cpp:92-93) + permutation bit map — not part of any timed region
+    t0 = time.perf_counter()
+    verify = ix.verify_sa() if args.verify else None
+    verify_s = time.perf_counter() - t0
     bst_warm = None
     if args.rebuild:  # second build of the same corpus: device memory already touched once, allocator warm
         sh.build_device(text.data_ptr(), doc_off.data_ptr(), ids.data_ptr(), snd, stream, keep=(text, doc_off, ids))
@@ -454,9 +621,26 @@ def run_ours(args):
         except Exception as e:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e!r}"}
 
-    build_ms = torch.tensor([bst["total_ms"], bst_warm["total_ms"] if bst_warm else 0.0], dtype=torch.float64, device=dev)
+    # ---- N > 1: row-level parity of the sharded answer, inside this run (the GPU test box has one GPU)
+    parity_sharded = None
+    if world > 1:
+        try:
+            parity_sharded = sharded_row_parity(sh, text, ids, w, snd, pat, poff, rank, world)
+        except Exception as e:  # noqa: BLE001
+            parity_sharded = {"status": f"failed: {e!r}"[:300]}
+    # ---- secondary workloads (N = 1, the 10 GB configuration): W8s and cfg2 as extra keys
+    extras = None
+    if world == 1 and args.extras and wname == "cfg3" and args.patterns == "w5":
+        try:
+            extras = secondary_workloads(sh, ix, text, snd, w, dev, hbm_peak)
+        except Exception as e:  # noqa: BLE001
+            extras = {"error": repr(e)[:300]}
+
+    build_ms = torch.tensor([bst["total_ms"], bst_warm["total_ms"] if bst_warm else 0.0,
+                             0.0 if (verify is None or verify["ok"]) else 1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(build_ms, op=dist.ReduceOp.MAX)  # every shard builds concurrently: the job takes the slowest
+    verified_all = float(build_ms[2].item()) == 0.0
     build_ms, rebuild_ms = float(build_ms[0].item()), float(build_ms[1].item())
     if rank == 0:
         out = {
@@ -481,9 +665,15 @@ def run_ours(args):
                       "sort_ms": bst["sort_ms"], "rounds": bst["rounds"], "chunks": bst["chunks"], "wall_s": build_wall,
                       "rebuild_ms": rebuild_ms if bst_warm else None,
                       "rebuild_corpus_GB_per_s": (w["nd"] * w["doclen"] / 1e9 / (rebuild_ms / 1e3)) if bst_warm else None,
+                      "verified": (bool(verified_all) if verify is not None else None),
+                      "verify": (dict(verify, seconds=verify_s, what="cdb_verify_sa on every shard: adjacent suffix pairs under "
+                                      "std::string_view < (src/index.cpp:92-93), permutation bit map; rank 0's counters shown")
+                                 if verify is not None else None),
                       "compulsory_bytes": n_shard * (1 + width),
                       "frac_of_hbm_peak": n_shard * (1 + width) / 1e9 / (bst["total_ms"] / 1e3) / hbm_peak},
             "pairs_per_step": global_pairs, "occurrences_per_step": global_occ,
+            "parity_sharded": parity_sharded,
+            "extras": extras,
         }
         print(json.dumps(out))
     ix.close()
@@ -566,6 +756,8 @@ def main():
                     help="w5 = uniform 5-byte keywords (the metric's workload); w8s = sampled 8-byte substrings")
     ap.add_argument("--no-rebuild", dest="rebuild", action="store_false",
                     help="skip the second (warm) build of the same corpus (build.rebuild_ms)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip cdb_verify_sa after the build")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary workloads (W8s, cfg2)")
     ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

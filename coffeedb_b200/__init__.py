@@ -26,8 +26,9 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
     "cdb_build", "cdb_build_device", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
-    "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_spans_free",
-    "cdb_splice", "cdb_verify_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
+    "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
+    "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
+    "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
 ]
 
 CDB_OK = 0
@@ -52,6 +53,11 @@ class DeviceResult(C.Structure):
 class Spans(C.Structure):
     _fields_ = [("ntext", C.c_int64), ("total_spans", C.c_int64), ("span_off", C.POINTER(C.c_int64)),
                 ("spans", C.POINTER(C.c_int64)), ("_owner", C.c_void_p)]
+
+
+class DeviceSpans(C.Structure):
+    _fields_ = [("ntext", C.c_int64), ("total_spans", C.c_int64), ("span_off", C.c_void_p), ("spans", C.c_void_p),
+                ("_owner", C.c_void_p)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -98,11 +104,17 @@ def lib():
         L.cdb_device_result_free.argtypes = [C.POINTER(DeviceResult)]
         L.cdb_device_result_free.restype = None
         L.cdb_locate_spans.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(Spans)]
+        L.cdb_locate_spans_batch.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.POINTER(Spans)]
+        L.cdb_locate_spans_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp,
+                                                    C.POINTER(DeviceSpans)]
+        L.cdb_device_spans_free.argtypes = [C.POINTER(DeviceSpans)]
+        L.cdb_device_spans_free.restype = None
         L.cdb_spans_free.argtypes = [C.POINTER(Spans)]
         L.cdb_spans_free.restype = None
         L.cdb_splice.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
         L.cdb_splice.restype = C.c_int64
         L.cdb_verify_sa.argtypes = [vp, i64p]
+        L.cdb_compare_sa.argtypes = [vp, vp, C.c_int64, i64p]
         L.cdb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p]
         L.cdb_last_locate_stats.argtypes = [C.POINTER(C.c_double), i64p]
         L.cdb_last_locate_stats.restype = None
@@ -262,6 +274,14 @@ class StringIndex:
         d["ok"] = not (d["inversions"] or d["invalid"] or d["duplicates"] or d["ties_unordered"] or d["unchecked"])
         return d
 
+    def compare_sa(self, other: np.ndarray) -> dict:
+        """Element-wise comparison with another packed suffix array of the same corpus (uint32/uint64 of the index's
+        width, host memory): identical elements, ties (different element, byte-identical suffix), real differences."""
+        other = np.ascontiguousarray(other)
+        out = (C.c_int64 * 3)()
+        _check(self._L.cdb_compare_sa(self._h, other.ctypes.data, other.nbytes, out))
+        return {"identical": int(out[0]), "ties": int(out[1]), "different": int(out[2])}
+
     def export_sa(self) -> np.ndarray:
         """The packed suffix array widened to uint64 (element = (offset << bits) | doc, src/index.cpp:209-215)."""
         inf = self.info()
@@ -289,6 +309,38 @@ class StringIndex:
         finally:
             self._L.cdb_spans_free(C.byref(sp))
         return [allsp[off[i]:off[i + 1]] for i in range(len(docs))]
+
+    def spans_batch(self, requests, texts) -> list[np.ndarray]:
+        """Batched highlight.  requests: list of keyword lists; texts: list of (request index, doc index).  -> one int64
+        [k, 2] array of merged inclusive [begin, end] spans per text (cdb_locate_spans_batch)."""
+        flat = [k for r in requests for k in r]
+        kw, kw_off = pack(flat)
+        rko = np.zeros(len(requests) + 1, np.int64)
+        if len(requests):
+            rko[1:] = np.cumsum([len(r) for r in requests])
+        treq = np.ascontiguousarray([t[0] for t in texts], np.int64)
+        tdoc = np.ascontiguousarray([t[1] for t in texts], np.int64)
+        sp = Spans()
+        _check(self._L.cdb_locate_spans_batch(self._h, kw.ctypes.data if len(kw) else None, kw_off.ctypes.data, len(flat),
+                                              rko.ctypes.data, len(requests), treq.ctypes.data if len(texts) else None,
+                                              tdoc.ctypes.data if len(texts) else None, len(texts), C.byref(sp)))
+        try:
+            off = np.ctypeslib.as_array(sp.span_off, shape=(len(texts) + 1,)).copy() if len(texts) else np.zeros(1, np.int64)
+            allsp = (np.ctypeslib.as_array(sp.spans, shape=(sp.total_spans, 2)).copy() if sp.total_spans
+                     else np.zeros((0, 2), np.int64))
+        finally:
+            self._L.cdb_spans_free(C.byref(sp))
+        return [allsp[off[i]:off[i + 1]] for i in range(len(texts))]
+
+    def spans_batch_device(self, d_kw, d_kw_off, nkw, d_req_kw_off, nreq, d_text_req, d_text_doc, ntext, stream=0) -> DeviceSpans:
+        """Device pointers in, device CSR out (caller frees with device_spans_free)."""
+        out = DeviceSpans()
+        _check(self._L.cdb_locate_spans_batch_device(self._h, d_kw, d_kw_off, nkw, d_req_kw_off, nreq, d_text_req, d_text_doc,
+                                                     ntext, stream, C.byref(out)))
+        return out
+
+    def device_spans_free(self, sp: DeviceSpans):
+        self._L.cdb_device_spans_free(C.byref(sp))
 
     def close(self):
         if self._h:

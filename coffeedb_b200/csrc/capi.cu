@@ -439,6 +439,19 @@ cdb_status cdb_verify_sa(const cdb_index* h, int64_t* out8) {
     CDB_CATCH
 }
 
+cdb_status cdb_compare_sa(const cdb_index* h, const void* other_sa, int64_t other_bytes, int64_t* out3) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out3) throw Error(CDB_ERR_ARG, "cdb_compare_sa: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    if (other_bytes != ix->n * ix->width || (other_bytes && !other_sa))
+        throw Error(CDB_ERR_ARG, "cdb_compare_sa: the other array must hold n elements of the index's width");
+    DeviceSetter ds(ix->device);
+    compare_index_sa(*ix, other_sa, thread_ctx(ix->device).stream, out3);
+    return CDB_OK;
+    CDB_CATCH
+}
+
 cdb_status cdb_build_stats(const cdb_index* h, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks) {
     CDB_TRY
     const Index* ix = reinterpret_cast<const Index*>(h);
@@ -627,36 +640,92 @@ cdb_status cdb_query_stats(const cdb_index* h, uint64_t* queries, uint64_t* batc
     CDB_CATCH
 }
 
-cdb_status cdb_locate_spans(const cdb_index* h, const void* kw, const int64_t* kw_off, int64_t nkw, const int64_t* docs,
-                            int64_t ndocs, cdb_spans* out) {
-    CDB_TRY
-    const Index* ix = reinterpret_cast<const Index*>(h);
-    if (!ix || !out || nkw < 0 || ndocs < 0) throw Error(CDB_ERR_ARG, "cdb_locate_spans: bad argument");
-    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+static cdb_status spans_host(const Index* ix, const void* kw, const int64_t* kw_off, int64_t nkw, const int64_t* req_kw_off,
+                             int64_t nreq, const int64_t* text_req, const int64_t* text_doc, int64_t ntext, cdb_spans* out) {
     std::memset(out, 0, sizeof(*out));
     DeviceSetter ds(ix->device);
-    cudaStream_t st;
-    CDB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = thread_ctx(ix->device).stream;
     std::vector<i64>* so = new std::vector<i64>();
     std::vector<i64>* sp = new std::vector<i64>();
     try {
-        locate_spans(*ix, (const u8*)kw, kw_off, nkw, docs, ndocs, st, *so, *sp);
+        locate_spans_batch(*ix, (const u8*)kw, kw_off, nkw, req_kw_off, nreq, text_req, text_doc, ntext, st, *so, *sp);
     } catch (...) {
         cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
         delete so;
         delete sp;
         throw;
     }
-    cudaStreamDestroy(st);
     auto* pair = new std::pair<std::vector<i64>*, std::vector<i64>*>(so, sp);
-    out->ntext = ndocs;
+    out->ntext = ntext;
     out->total_spans = (i64)sp->size() / 2;
     out->span_off = so->data();
     out->spans = sp->data();
     out->_owner = pair;
     return CDB_OK;
+}
+
+cdb_status cdb_locate_spans(const cdb_index* h, const void* kw, const int64_t* kw_off, int64_t nkw, const int64_t* docs,
+                            int64_t ndocs, cdb_spans* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || nkw < 0 || ndocs < 0 || (nkw > 0 && !kw_off) || (ndocs > 0 && !docs))
+        throw Error(CDB_ERR_ARG, "cdb_locate_spans: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    // one request that owns every keyword; every document is one of its texts
+    const int64_t req_kw_off[2] = {0, nkw};
+    std::vector<i64> text_req((size_t)ndocs, 0);
+    return spans_host(ix, kw, kw_off, nkw, req_kw_off, 1, text_req.data(), docs, ndocs, out);
     CDB_CATCH
+}
+
+cdb_status cdb_locate_spans_batch(const cdb_index* h, const void* kw, const int64_t* kw_off, int64_t nkw,
+                                  const int64_t* req_kw_off, int64_t nreq, const int64_t* text_req, const int64_t* text_doc,
+                                  int64_t ntext, cdb_spans* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || nkw < 0 || nreq < 0 || ntext < 0 || (nkw > 0 && !kw_off) || !req_kw_off ||
+        (ntext > 0 && (!text_req || !text_doc)))
+        throw Error(CDB_ERR_ARG, "cdb_locate_spans_batch: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    if (req_kw_off[0] != 0 || req_kw_off[nreq] != nkw) throw Error(CDB_ERR_ARG, "cdb_locate_spans_batch: req_kw_off must span [0, nkw]");
+    for (i64 r = 0; r < nreq; ++r)
+        if (req_kw_off[r + 1] < req_kw_off[r]) throw Error(CDB_ERR_ARG, "cdb_locate_spans_batch: req_kw_off must be non-decreasing");
+    for (i64 t = 0; t < ntext; ++t)
+        if (text_req[t] < 0 || text_req[t] >= nreq) throw Error(CDB_ERR_ARG, "cdb_locate_spans_batch: request index out of range");
+    return spans_host(ix, kw, kw_off, nkw, req_kw_off, nreq, text_req, text_doc, ntext, out);
+    CDB_CATCH
+}
+
+cdb_status cdb_locate_spans_batch_device(const cdb_index* h, const void* d_kw, const int64_t* d_kw_off, int64_t nkw,
+                                         const int64_t* d_req_kw_off, int64_t nreq, const int64_t* d_text_req,
+                                         const int64_t* d_text_doc, int64_t ntext, void* stream, cdb_device_spans* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || nkw < 0 || nreq < 0 || ntext < 0) throw Error(CDB_ERR_ARG, "cdb_locate_spans_batch_device: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf<u64> soff;
+    DevBuf<i64> sp;
+    i64 total = 0;
+    locate_spans_batch_device(*ix, (const u8*)d_kw, d_kw_off, nkw, d_req_kw_off, nreq, d_text_req, d_text_doc, ntext, st, soff, sp,
+                              &total);
+    out->ntext = ntext;
+    out->total_spans = total;
+    out->span_off = reinterpret_cast<int64_t*>(soff.detach());
+    out->spans = sp.detach();
+    out->_owner = (void*)st;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_device_spans_free(cdb_device_spans* s) {
+    if (!s) return;
+    cudaStream_t st = (cudaStream_t)s->_owner;
+    if (s->span_off) cudaFreeAsync(s->span_off, st);
+    if (s->spans) cudaFreeAsync(s->spans, st);
+    std::memset(s, 0, sizeof(*s));
 }
 
 void cdb_spans_free(cdb_spans* s) {

@@ -19,8 +19,7 @@
 //                          the device radix sort (the same engine as the build) and run-length encoded, in
 //                          sub-batches of bounded size; their row lengths are known before gather_kernel runs and
 //                          enter the same scan, the rows themselves are emitted straight into the CSR result.
-//   K8  span_* kernels     highlight spans from suffix-array positions or from a direct scan of the requested
-//                          documents.
+//   K8  highlight spans    live in spans.cu (batched over (request, document) texts).
 // All integer work; bounded by HBM traffic and, in gather_kernel, by the ALU pipe (64*S + w*occ + 24*d
 // algorithmic bytes per pattern).
 #include <algorithm>
@@ -1036,269 +1035,6 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     out->_owner = (void*)st;
 }
 
-
-// ---- K8 highlight spans ----------------------------------------------------------------------------------------
-// Replaces the occurrence enumeration of ac_automaton::render (src/database.cpp:58-77): every occurrence of every
-// keyword is an SA element inside that keyword's interval; the ones that fall in a requested document become
-// (doc, begin) -> end records, are sorted by the device radix sort and merged per document (overlapping
-// intervals merge, touching ones do not — database.cpp:66-76).
-__global__ void span_occ_kernel(const i64* __restrict__ left, const i64* __restrict__ right, u64 nkw, u64* __restrict__ occ) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nkw) occ[j] = (u64)(right[j] - left[j]);
-}
-
-template <typename SAT>
-__global__ void span_expand_kernel(const SAT* __restrict__ sa, u64 mask, int bits1, int bits2,
-                                   const i64* __restrict__ left, const u64* __restrict__ ooff, u64 nkw, u64 total,
-                                   const i64* __restrict__ kw_off, const i64* __restrict__ udocs, u64 nu,
-                                   u64* __restrict__ keys, u64* __restrict__ ends, unsigned long long* __restrict__ cursor) {
-    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
-        u64 lo = 0, hi = nkw - 1;
-        while (lo < hi) {
-            u64 mid = lo + (hi - lo + 1) / 2;
-            if (__ldg(ooff + mid) <= e)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        const u64 x = (u64)sa[(u64)left[lo] + (e - __ldg(ooff + lo))];
-        const i64 doc = (i64)(x & mask);
-        const u64 off = x >> bits1;
-        // membership in the sorted list of requested documents
-        u64 a = 0, b = nu;
-        while (a < b) {
-            u64 mid = (a + b) >> 1;
-            if (__ldg(udocs + mid) < doc)
-                a = mid + 1;
-            else
-                b = mid;
-        }
-        if (a < nu && __ldg(udocs + a) == doc) {
-            const u64 slot = atomicAdd(cursor, 1ull);
-            keys[slot] = (a << bits2) | off;
-            ends[slot] = off + (u64)(kw_off[lo + 1] - kw_off[lo]) - 1;
-        }
-    }
-}
-
-// Direct scan of the requested documents: one thread per (document, position) compares every keyword there.  Used
-// instead of the suffix-array enumeration (a) in the note-N1 layout, where the array is not sorted under the
-// comparator of the search and query() itself reproduces the reference's misses, while the reference's highlighter
-// scans the text and finds every occurrence (src/database.cpp:58-77), and (b) when the keywords occur far more often
-// in the whole corpus than the requested documents are long.
-__global__ void span_len_kernel(const i64* __restrict__ doc_off, const i64* __restrict__ udocs, u64 nu, u64* __restrict__ len) {
-    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < nu) len[u] = (u64)(doc_off[udocs[u] + 1] - doc_off[udocs[u]]);
-}
-
-template <bool WRITE>
-__global__ void span_scan_kernel(const u8* __restrict__ text, const i64* __restrict__ doc_off, const i64* __restrict__ udocs,
-                                 u64 nu, const u64* __restrict__ pos_off, u64 total_pos, const u8* __restrict__ kw,
-                                 const i64* __restrict__ kw_off, u64 nkw, int bits2, u64* __restrict__ keys,
-                                 u64* __restrict__ ends, unsigned long long* __restrict__ cursor) {
-    unsigned long long found = 0;
-    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total_pos; e += (u64)gridDim.x * blockDim.x) {
-        u64 lo = 0, hi = nu - 1;  // largest u with pos_off[u] <= e
-        while (lo < hi) {
-            const u64 mid = lo + (hi - lo + 1) / 2;
-            if (__ldg(pos_off + mid) <= e)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        const u64 p = e - __ldg(pos_off + lo);
-        const i64 doc = udocs[lo];
-        const i64 ds = doc_off[doc];
-        const u64 len = (u64)(doc_off[doc + 1] - ds);
-        for (u64 k = 0; k < nkw; ++k) {
-            const u64 m = (u64)(kw_off[k + 1] - kw_off[k]);
-            if (p + m > len) continue;
-            const u8* a = text + ds + p;
-            const u8* b = kw + kw_off[k];
-            u64 i = 0;
-            while (i < m && a[i] == b[i]) ++i;
-            if (i == m) {
-                if (WRITE) {
-                    const u64 slot = atomicAdd(cursor, 1ull);
-                    keys[slot] = (lo << bits2) | p;
-                    ends[slot] = p + m - 1;
-                } else {
-                    ++found;
-                }
-            }
-        }
-    }
-    if (!WRITE) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
-        if ((threadIdx.x & 31) == 0 && found) atomicAdd(cursor, found);
-    }
-}
-
-// one thread per requested document: merge its records (sorted by begin).  WRITE=false counts spans.
-template <bool WRITE>
-__global__ void span_merge_kernel(const u64* __restrict__ keys, const u64* __restrict__ ends, u64 nrec, int bits2, u64 nu,
-                                  u64* __restrict__ cnt, const u64* __restrict__ soff, i64* __restrict__ spans) {
-    const u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= nu) return;
-    const u64 klo = u << bits2;
-    u64 a = 0, b = nrec;
-    while (a < b) {
-        u64 mid = (a + b) >> 1;
-        if (keys[mid] < klo)
-            a = mid + 1;
-        else
-            b = mid;
-    }
-    const u64 offmask = bits2 >= 64 ? ~0ull : ((1ull << bits2) - 1);
-    u64 n = 0;
-    u64 out = WRITE ? soff[u] : 0;
-    bool open = false;
-    u64 cb = 0, ce = 0;
-    for (u64 r = a; r < nrec && (keys[r] >> bits2) == u; ++r) {
-        const u64 bg = keys[r] & offmask, en = ends[r];
-        if (open && bg <= ce) {
-            ce = en > ce ? en : ce;
-        } else {
-            if (open) {
-                if (WRITE) {
-                    spans[2 * out] = (i64)cb;
-                    spans[2 * out + 1] = (i64)ce;
-                    ++out;
-                }
-                ++n;
-            }
-            open = true;
-            cb = bg;
-            ce = en;
-        }
-    }
-    if (open) {
-        if (WRITE) {
-            spans[2 * out] = (i64)cb;
-            spans[2 * out + 1] = (i64)ce;
-        }
-        ++n;
-    }
-    if (!WRITE) cnt[u] = n;
-}
-
-template <typename SAT>
-static void spans_typed(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const std::vector<i64>& udocs,
-                        cudaStream_t st, std::vector<u64>& uoff, std::vector<i64>& uspans) {
-    const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
-    const u64 nu = udocs.size();
-    const i64 kbytes = kw_off[nkw] - kw_off[0];
-    DevBuf<u8> d_kw((size_t)kbytes + 8, st);
-    DevBuf<i64> d_koff((size_t)nkw + 1, st), d_udocs(nu, st);
-    std::vector<i64> rel((size_t)nkw + 1);
-    for (i64 k = 0; k <= nkw; ++k) rel[k] = kw_off[k] - kw_off[0];
-    CDB_CUDA(cudaMemcpyAsync(d_kw.p, kw + kw_off[0], (size_t)kbytes, cudaMemcpyHostToDevice, st));
-    CDB_CUDA(cudaMemcpyAsync(d_koff.p, rel.data(), (size_t)(nkw + 1) * 8, cudaMemcpyHostToDevice, st));
-    CDB_CUDA(cudaMemcpyAsync(d_udocs.p, udocs.data(), (size_t)nu * 8, cudaMemcpyHostToDevice, st));
-    DevBuf<i64> left(nkw, st), right(nkw, st);
-    DevBuf<unsigned long long> counters(2, st);
-    CDB_CUDA(cudaMemsetAsync(counters.p, 0, 16, st));
-    uoff.assign(nu + 1, 0);
-    uspans.clear();
-    // size of the direct scan: positions of the requested documents
-    DevBuf<u64> pos_off(nu + 1, st);
-    span_len_kernel<<<(unsigned)ceil_div((i64)nu, 256), 256, 0, st>>>(ix.d_off, d_udocs.p, nu, pos_off.p);
-    CDB_LAUNCH_CHECK();
-    prim::exclusive_scan<u64>(pos_off.p, pos_off.p, nu, st);
-    u64 total_pos = 0;
-    CDB_CUDA(cudaMemcpyAsync(&total_pos, pos_off.p + nu, 8, cudaMemcpyDeviceToHost, st));
-    const bool n1_layout = ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size;
-    const char* force = getenv("CDB_SPANS_SCAN");
-    bool use_scan = n1_layout || (force && atoi(force) == 1);
-    u64 total = 0;
-    DevBuf<u64> ooff;
-    if (!use_scan) {
-        SearchCtx c = make_ctx(ix);
-        search_kernel<SAT><<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(c, ix.symtab, d_kw.p, d_koff.p, nkw, left.p, right.p,
-                                                                          reinterpret_cast<int*>(counters.p + 1), nullptr, nullptr, nullptr);
-        CDB_LAUNCH_CHECK();
-        ooff.alloc((size_t)nkw + 1, st);
-        span_occ_kernel<<<(unsigned)ceil_div(nkw, 256), 256, 0, st>>>(left.p, right.p, (u64)nkw, ooff.p);
-        CDB_LAUNCH_CHECK();
-        prim::exclusive_scan<u64>(ooff.p, ooff.p, (u64)nkw, st);
-        CDB_CUDA(cudaMemcpyAsync(&total, ooff.p + nkw, 8, cudaMemcpyDeviceToHost, st));
-    }
-    CDB_CUDA(cudaStreamSynchronize(st));
-    // enumerating every occurrence in the corpus costs `total`; scanning the requested documents costs positions x keywords
-    if (!use_scan && !(force && atoi(force) == 0) && total > total_pos * (u64)nkw) use_scan = true;
-    DevBuf<u64> k0, k1, e0, e1;
-    unsigned long long nrec = 0;
-    if (use_scan) {
-        if (total_pos == 0) return;
-        const int grid = (int)std::min<i64>(ceil_div((i64)total_pos, 256), kNumSMs * 16);
-        span_scan_kernel<false><<<grid, 256, 0, st>>>(ix.d_text, ix.d_off, d_udocs.p, nu, pos_off.p, total_pos, d_kw.p, d_koff.p,
-                                                      (u64)nkw, ix.bits2, nullptr, nullptr, counters.p);
-        CDB_LAUNCH_CHECK();
-        CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
-        CDB_CUDA(cudaStreamSynchronize(st));
-        if (nrec == 0) return;
-        k0.alloc(nrec, st); k1.alloc(nrec, st); e0.alloc(nrec, st); e1.alloc(nrec, st);
-        CDB_CUDA(cudaMemsetAsync(counters.p, 0, 8, st));
-        span_scan_kernel<true><<<grid, 256, 0, st>>>(ix.d_text, ix.d_off, d_udocs.p, nu, pos_off.p, total_pos, d_kw.p, d_koff.p,
-                                                     (u64)nkw, ix.bits2, k0.p, e0.p, counters.p);
-        CDB_LAUNCH_CHECK();
-    } else {
-        if (total == 0) return;
-        k0.alloc(total, st); k1.alloc(total, st); e0.alloc(total, st); e1.alloc(total, st);
-        const int grid = (int)std::min<i64>(ceil_div((i64)total, 256), kNumSMs * 16);
-        span_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, ix.bits1, ix.bits2, left.p, ooff.p, (u64)nkw, total, d_koff.p,
-                                                       d_udocs.p, nu, k0.p, e0.p, counters.p);
-        CDB_LAUNCH_CHECK();
-        CDB_CUDA(cudaMemcpyAsync(&nrec, counters.p, 8, cudaMemcpyDeviceToHost, st));
-        CDB_CUDA(cudaStreamSynchronize(st));
-        if (nrec == 0) return;
-    }
-    int cb = rs::radix_sort_pairs<u64>(k0.p, k1.p, e0.p, e1.p, nrec, 0, ix.bits2 + bits_for_u64(nu - 1), st);
-    const u64* ks = cb ? k1.p : k0.p;
-    const u64* es = cb ? e1.p : e0.p;
-    DevBuf<u64> cnt(nu + 1, st);
-    span_merge_kernel<false><<<(unsigned)ceil_div((i64)nu, 128), 128, 0, st>>>(ks, es, nrec, ix.bits2, nu, cnt.p, nullptr, nullptr);
-    CDB_LAUNCH_CHECK();
-    prim::exclusive_scan<u64>(cnt.p, cnt.p, nu, st);
-    CDB_CUDA(cudaMemcpyAsync(uoff.data(), cnt.p, (nu + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CDB_CUDA(cudaStreamSynchronize(st));
-    const u64 ns = uoff[nu];
-    if (ns == 0) return;
-    DevBuf<i64> d_spans(ns * 2, st);
-    span_merge_kernel<true><<<(unsigned)ceil_div((i64)nu, 128), 128, 0, st>>>(ks, es, nrec, ix.bits2, nu, nullptr, cnt.p, d_spans.p);
-    CDB_LAUNCH_CHECK();
-    uspans.resize(ns * 2);
-    CDB_CUDA(cudaMemcpyAsync(uspans.data(), d_spans.p, ns * 16, cudaMemcpyDeviceToHost, st));
-    CDB_CUDA(cudaStreamSynchronize(st));
-}
-
-void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const i64* docs, i64 ndocs, cudaStream_t st,
-                  std::vector<i64>& span_off, std::vector<i64>& spans) {
-    span_off.assign((size_t)ndocs + 1, 0);
-    spans.clear();
-    for (i64 k = 0; k < nkw; ++k)
-        if (kw_off[k + 1] <= kw_off[k]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
-    for (i64 t = 0; t < ndocs; ++t)
-        if (docs[t] < 0 || docs[t] >= ix.nd) throw Error(CDB_ERR_ARG, "cdb_locate_spans: document index out of range");
-    if (nkw == 0 || ndocs == 0 || ix.n == 0) return;
-    std::vector<i64> udocs(docs, docs + ndocs);
-    std::sort(udocs.begin(), udocs.end());
-    udocs.erase(std::unique(udocs.begin(), udocs.end()), udocs.end());
-    std::vector<u64> uoff;
-    std::vector<i64> uspans;
-    if (ix.width == 4)
-        spans_typed<u32>(ix, kw, kw_off, nkw, udocs, st, uoff, uspans);
-    else
-        spans_typed<u64>(ix, kw, kw_off, nkw, udocs, st, uoff, uspans);
-    // back to the caller's document order (duplicates allowed)
-    for (i64 t = 0; t < ndocs; ++t) {
-        const size_t u = std::lower_bound(udocs.begin(), udocs.end(), docs[t]) - udocs.begin();
-        const u64 a = uoff[u], b = uoff[u + 1];
-        spans.insert(spans.end(), uspans.begin() + 2 * a, uspans.begin() + 2 * b);
-        span_off[t + 1] = (i64)spans.size() / 2;
-    }
-}
 
 // ---- small batches (CDB_SMALL_BATCH = largest batch that takes this path, default 256; 0 = general path only) ------
 // One keyword through the general path costs ~130 us of launches, synchronisations and stream-ordered allocations

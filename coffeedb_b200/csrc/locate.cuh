@@ -16,7 +16,12 @@ struct SmallResult {
 };
 int small_batch_limit();  // CDB_SMALL_BATCH (0 = path disabled)
 bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, cudaStream_t st, SmallResult* res);
-// Highlight spans (see spans.cu).
-void locate_spans(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const i64* docs, i64 ndocs,
-                  cudaStream_t st, std::vector<i64>& span_off, std::vector<i64>& spans);
+// Highlight spans (spans.cu): merged occurrence spans of each request's keywords inside each of its texts.
+// text t = document text_doc[t] highlighted for request text_req[t]; request r owns keywords [req_kw_off[r], req_kw_off[r+1]).
+void locate_spans_batch(const Index& ix, const u8* kw, const i64* kw_off, i64 nkw, const i64* req_kw_off, i64 nreq,
+                        const i64* text_req, const i64* text_doc, i64 ntext, cudaStream_t st, std::vector<i64>& span_off,
+                        std::vector<i64>& spans);
+void locate_spans_batch_device(const Index& ix, const u8* d_kw, const i64* d_kw_off, i64 nkw, const i64* d_req_kw_off, i64 nreq,
+                               const i64* d_text_req, const i64* d_text_doc, i64 ntext, cudaStream_t st, DevBuf<u64>& span_off,
+                               DevBuf<i64>& spans, i64* total_out);
 }  // namespace cdb

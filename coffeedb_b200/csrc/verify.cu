@@ -197,6 +197,65 @@ __global__ void __launch_bounds__(128) verify_signed_kernel(VerifyCtx c, i64 chu
     if (signed_rule) atomicAdd(cnt + 7, 1ull);
 }
 
+// Element-wise comparison with another packed suffix array of the same corpus (e.g. the compiled reference's): where
+// the elements differ the two suffixes must be byte-identical (a tie, note N2), anything else is a real difference.
+// counters: [0] identical elements [1] different elements, identical suffixes [2] different suffixes
+template <typename SAT>
+__global__ void __launch_bounds__(256) compare_sa_kernel(VerifyCtx c, const SAT* __restrict__ other, i64 base, i64 count,
+                                                         unsigned long long* __restrict__ cnt) {
+    const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    int kind = -1;
+    if (j < count) {
+        u64 pa;
+        const SufRef a = suffix_at<SAT>(c, base + j, &pa);
+        const u64 pb = (u64)other[j];
+        if (pa == pb) {
+            kind = 0;
+        } else {
+            VerifyCtx c2 = c;
+            c2.sa = other - base;  // suffix_at indexes with the global rank
+            u64 tmp;
+            const SufRef b = suffix_at<SAT>(c2, base + j, &tmp);
+            int ca, cb;
+            kind = 2;
+            if (a.len > 0 && b.len > 0) {
+                first_difference(c.text, a, b, &ca, &cb);
+                if (ca < 0 && cb < 0) kind = 1;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt + k, (unsigned long long)__popc(m));
+    }
+}
+
+void compare_index_sa(const Index& ix, const void* host_sa, cudaStream_t st, i64 out[3]) {
+    for (int k = 0; k < 3; ++k) out[k] = 0;
+    if (ix.n == 0) return;
+    VerifyCtx c{ix.d_sa, ix.n, ix.nd, ix.bits1, ix.mask, ix.d_off, ix.d_text};
+    DevBuf<unsigned long long> cnt(3, st);
+    CDB_CUDA(cudaMemsetAsync(cnt.p, 0, 24, st));
+    const i64 chunk = (i64)1 << 26;  // elements per upload
+    DevBuf<u8> buf((size_t)std::min<i64>(chunk, ix.n) * ix.width, st);
+    for (i64 base = 0; base < ix.n; base += chunk) {
+        const i64 count = std::min<i64>(chunk, ix.n - base);
+        CDB_CUDA(cudaMemcpyAsync(buf.p, (const u8*)host_sa + base * ix.width, (size_t)count * ix.width, cudaMemcpyHostToDevice, st));
+        const unsigned grid = (unsigned)ceil_div(count, 256);
+        if (ix.width == 4)
+            compare_sa_kernel<u32><<<grid, 256, 0, st>>>(c, reinterpret_cast<const u32*>(buf.p), base, count, cnt.p);
+        else
+            compare_sa_kernel<u64><<<grid, 256, 0, st>>>(c, reinterpret_cast<const u64*>(buf.p), base, count, cnt.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaStreamSynchronize(st));  // the staging buffer is re-used
+    }
+    unsigned long long h[3];
+    CDB_CUDA(cudaMemcpyAsync(h, cnt.p, 24, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) out[k] = (i64)h[k];
+}
+
 void verify_index(const Index& ix, cudaStream_t st, i64 out[8]) {
     for (int k = 0; k < 8; ++k) out[k] = 0;
     if (ix.n == 0) return;

@@ -84,6 +84,15 @@ typedef struct cdb_spans {
     void* _owner;
 } cdb_spans;
 
+/* Same, device memory (valid until cdb_device_spans_free). */
+typedef struct cdb_device_spans {
+    int64_t ntext;
+    int64_t total_spans;
+    int64_t* span_off; /* device [ntext+1] */
+    int64_t* spans;    /* device [2*total_spans] */
+    void* _owner;
+} cdb_device_spans;
+
 const char* cdb_last_error(void);
 const char* cdb_version(void);
 int cdb_device_count(void);
@@ -132,6 +141,11 @@ cdb_status cdb_sa_device_ptr(const cdb_index* idx, const void** d_sa);
  * ascending packed order, pairs queued for the signed-rule check, queued pairs left unchecked, pairs checked under the
  * signed rule}.  A correct array has out8[0] = out8[1] = out8[2] = out8[4] = out8[6] = 0. */
 cdb_status cdb_verify_sa(const cdb_index* idx, int64_t* out8);
+/* Element-wise comparison of the built array with another packed suffix array of the same corpus in host memory (n
+ * elements of the index's width — e.g. the array the compiled reference built): out3 = {identical elements, different
+ * elements whose two suffixes are byte-identical (SURVEY.md note N2 ties), elements naming different suffixes}.
+ * "Identical up to ties" is out3[2] == 0. */
+cdb_status cdb_compare_sa(const cdb_index* idx, const void* other_sa, int64_t other_bytes, int64_t* out3);
 
 /* Batched string_index::query(keyword) (src/index.cpp:237-326): pattern q = pat[pat_off[q], pat_off[q+1]).
  * An empty pattern fails the whole batch with CDB_ERR_EMPTY_KEYWORD.  Re-entrant: may be called concurrently
@@ -161,6 +175,20 @@ void cdb_device_result_free(cdb_device_result* r);
  * marker splicing (database.cpp:78-90) stays on the host (cdb_splice). */
 cdb_status cdb_locate_spans(const cdb_index* idx, const void* kw, const int64_t* kw_off, int64_t nkw,
                             const int64_t* docs, int64_t ndocs, cdb_spans* out);
+/* Batched highlight (src/database.cpp:139-165, 401-432: renderer / select() call render() once per selected object and
+ * constrained key).  nreq requests, request r owning the keywords [req_kw_off[r], req_kw_off[r+1]) of the keyword list
+ * (kw, kw_off[nkw+1]); ntext texts, text t = document text_doc[t] (doc index) highlighted with the keywords of request
+ * text_req[t].  One launch sequence and one synchronisation for the whole batch; spans of text t are
+ * spans[2*span_off[t] .. 2*span_off[t+1]).  A document may appear in any number of texts. */
+cdb_status cdb_locate_spans_batch(const cdb_index* idx, const void* kw, const int64_t* kw_off, int64_t nkw,
+                                  const int64_t* req_kw_off, int64_t nreq, const int64_t* text_req, const int64_t* text_doc,
+                                  int64_t ntext, cdb_spans* out);
+/* Same with every array resident in device memory (the keyword bytes readable 8 bytes past their end); work is
+ * enqueued on `stream` and the call returns after the stream has drained. */
+cdb_status cdb_locate_spans_batch_device(const cdb_index* idx, const void* d_kw, const int64_t* d_kw_off, int64_t nkw,
+                                         const int64_t* d_req_kw_off, int64_t nreq, const int64_t* d_text_req,
+                                         const int64_t* d_text_doc, int64_t ntext, void* stream, cdb_device_spans* out);
+void cdb_device_spans_free(cdb_device_spans* s);
 void cdb_spans_free(cdb_spans* s);
 /* database.cpp:78-90: writes text with left/right spliced around the spans into out (capacity out_cap);
  * returns the rendered length (also when out is too small or NULL). */

@@ -284,6 +284,14 @@ class Ref:
         self._lib.ref_export_sa(self._h, None, None, None, None, buf.ctypes.data)
         return buf[: size.value].astype(np.uint64), int(bits.value), int(mask.value), int(w.value)
 
+    def export_sa_raw(self) -> tuple[np.ndarray, int, int, int]:
+        """-> (raw sa in its own element width, bits1, mask, width) — no widening copy (for arrays of many GB)"""
+        w, bits, mask, size = C.c_int(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._lib.ref_export_sa(self._h, C.byref(w), C.byref(bits), C.byref(mask), C.byref(size), None)
+        buf = np.zeros(max(size.value, 1), np.uint32 if w.value == 4 else np.uint64)
+        self._lib.ref_export_sa(self._h, None, None, None, None, buf.ctypes.data)
+        return buf[: size.value], int(bits.value), int(mask.value), int(w.value)
+
     def query(self, kw: bytes) -> np.ndarray:
         out = C.POINTER(C.c_int64)()
         err = C.create_string_buffer(512)

@@ -143,3 +143,47 @@ def utf8_fast(char_lens, seed: int):
     off = start[cend]
     ids = np.arange(len(char_lens), dtype=np.int64) * 5 + 3
     return text, off, ids
+
+
+MAX_CHARS = 21_000  # <= 63 KB even if every code point took 3 bytes
+
+
+def utf8_corpus_on_device(target_bytes: int, seed: int, device_index: int = 0):
+    """Documents of 1..MAX_CHARS code points, 70 % one-byte (0x20..0x7E), 15 % two-byte, 15 % three-byte sequences
+    (SURVEY.md 8d config 5), generated with torch on the GPU -> (text uint8 [n + 64], doc_off int64 [nd + 1], ids)."""
+    import torch
+    dev = torch.device("cuda", device_index)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    nd = int(target_bytes / (1.45 * (MAX_CHARS + 1) / 2)) + 1
+    char_lens = torch.randint(1, MAX_CHARS + 1, (nd,), device=dev, generator=g)
+    nchar = int(char_lens.sum())
+    u = torch.rand(nchar, device=dev, generator=g)
+    cls = (1 + (u >= 0.70).to(torch.int8) + (u >= 0.85).to(torch.int8))
+    del u
+    start = torch.zeros(nchar + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cls, 0, out=start[1:])
+    n = int(start[-1])
+    text = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    s = start[:-1]
+    one = s[cls == 1]
+    text[one] = torch.randint(0x20, 0x7F, (one.numel(),), device=dev, generator=g).to(torch.uint8)
+    del one
+    two = s[cls == 2]
+    cp2 = torch.randint(0x80, 0x800, (two.numel(),), device=dev, generator=g)
+    text[two] = (0xC0 | (cp2 >> 6)).to(torch.uint8)
+    text[two + 1] = (0x80 | (cp2 & 0x3F)).to(torch.uint8)
+    del two, cp2
+    three = s[cls == 3]
+    cp3 = torch.randint(0x800, 0xD800, (three.numel(),), device=dev, generator=g)
+    text[three] = (0xE0 | (cp3 >> 12)).to(torch.uint8)
+    text[three + 1] = (0x80 | ((cp3 >> 6) & 0x3F)).to(torch.uint8)
+    text[three + 2] = (0x80 | (cp3 & 0x3F)).to(torch.uint8)
+    del three, cp3, cls, s
+    cend = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(char_lens, 0, out=cend[1:])
+    doc_off = start[cend].contiguous()
+    del start, cend
+    ids = torch.arange(nd, dtype=torch.int64, device=dev) * 7 + 1_000_003
+    torch.cuda.empty_cache()
+    return text, doc_off, ids, nd, n

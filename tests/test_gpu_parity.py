@@ -146,7 +146,7 @@ def test_brute_force_property_medium():
 
 
 def test_highlight_spans_match_reference(golden):
-    """K8: spans from SA positions == ac_automaton::render's spans (database.cpp:58-77)."""
+    """K8: device spans == ac_automaton::render's spans (database.cpp:58-77)."""
     hl = cases.highlight_cases()
     rend, roff = golden["highlight/rendered"], golden["highlight/rendered_off"]
     texts = [t for _k, t in hl]
@@ -370,15 +370,12 @@ def test_prefix_directory_on_and_off(monkeypatch):
         ix.close()
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "auto"])
-def test_highlight_spans_both_enumerations(mode, monkeypatch):
-    """Spans from suffix-array positions (CDB_SPANS_SCAN=0), from a direct scan of the requested documents (=1) and
-    with the cost-based choice must all equal the reference highlighter's spans (database.cpp:58-77)."""
-    if mode != "auto":
-        monkeypatch.setenv("CDB_SPANS_SCAN", mode)
+def test_highlight_spans_single_request_entry():
+    """cdb_locate_spans (one keyword set, several documents, duplicates and arbitrary order) == the reference
+    highlighter's spans (database.cpp:58-77) and its rendered text."""
     text, off, ids = corpora.ragged(1500, 120, seed=81, alphabet=b"abc")
     ix = build(text, off, ids)
-    kwsets = [[b"ab"], [b"a", b"bca"], [b"abc", b"cab", b"bb"], [b"c" * 5], [b"zz"], [b"abcabc", b"b"]]
+    kwsets = [[b"ab"], [b"a", b"bca"], [b"abc", b"cab", b"bb"], [b"c" * 5], [b"zz"], [b"abcabc", b"b"], [b"abcabcabca", b"ca"]]
     docs = [0, 7, 7, 1499, 3, 250, 1000]
     for kws in kwsets:
         got = ix.spans(kws, docs)
@@ -387,6 +384,45 @@ def test_highlight_spans_both_enumerations(mode, monkeypatch):
             assert np.array_equal(sp, oracle.port.spans(kws, t)), (kws, d)
             if oracle.ref_available():
                 assert cdb.splice(t, sp, b"<", b">") == oracle.ref_render(kws, t, b"<", b">")
+    with pytest.raises(RuntimeError, match="Empty keywords are not allowed"):
+        ix.spans([b"a", b""], [0])
+    with pytest.raises(RuntimeError, match="out of range"):
+        ix.spans([b"a"], [1500])
+    assert [len(x) for x in ix.spans([], [0, 1])] == [0, 0] and ix.spans([b"a"], []) == []
+    ix.close()
+
+
+def test_highlight_spans_batch_matches_reference():
+    """cdb_locate_spans_batch: many requests, each with its own keyword set, each highlighted in its own documents, in one
+    launch sequence — short documents (one thread each), documents longer than 1024 bytes (one warp each, spans that
+    straddle the 32-position steps), keywords longer than the 8-byte compare window, overlapping / touching / nested
+    occurrences.  Every text must equal ac_automaton::render's spans (src/database.cpp:58-77)."""
+    rng = np.random.default_rng(91)
+    docs_b = [bytes(rng.integers(ord("a"), ord("c") + 1, size=int(n), dtype=np.uint8))
+              for n in list(rng.integers(0, 200, size=600)) + [1024, 1025, 3000, 20000, 70000]]
+    docs_b += [b"ab" * 700, b"a" * 2100, b"abcabcabcabc" * 300, b""]
+    text, off, ids = corpora.from_docs(docs_b, id_base=10)
+    ix = build(text, off, ids)
+    nd = len(docs_b)
+    reqs = [[b"ab"], [b"a", b"bca"], [b"abc", b"cab", b"bb"], [b"ccccc"], [b"zz"], [b"abcabc", b"b"], [b"abcabcabca", b"ca"],
+            [b"a"], [b"aa", b"aaa"], [b"abab", b"ba"], [b"abcabcabcabcabc"], [b"c", b"cc", b"ccc", b"bccb"]]
+    texts = []
+    for r in range(len(reqs)):
+        for d in list(rng.integers(0, 600, size=40)) + list(range(600, nd)):
+            texts.append((r, int(d)))
+    rng.shuffle(texts)
+    got = ix.spans_batch(reqs, texts)
+    assert len(got) == len(texts)
+    for (r, d), sp in zip(texts, got):
+        assert np.array_equal(sp, oracle.port.spans(reqs[r], docs_b[d])), (reqs[r], d, len(docs_b[d]))
+    # spot check against the reference's own renderer
+    if oracle.ref_available():
+        for (r, d), sp in list(zip(texts, got))[:60]:
+            assert cdb.splice(docs_b[d], sp, b"<b>", b"</b>") == oracle.ref_render(reqs[r], docs_b[d], b"<b>", b"</b>")
+    with pytest.raises(RuntimeError, match="out of range"):
+        ix.spans_batch(reqs, [(0, nd)])
+    with pytest.raises(RuntimeError, match="out of range"):
+        ix.spans_batch(reqs, [(len(reqs), 0)])
     ix.close()
 
 
