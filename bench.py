@@ -206,6 +206,61 @@ def sharded_row_parity(sh, text, ids, w, snd, pat, poff, rank, world, nsample=48
             "how": "gather_rows on rank 0 vs per-shard brute-force scans (torch) concatenated in rank order"}
 
 
+def spans_leg(ix, last, text, ids, d_pat, d_poff, npat, w, dev, hbm_peak, pat, poff, max_docs=32, steps=3):
+    """cfg3's highlight part: for every keyword of the batch, merged highlight spans inside its first
+    <= 32 hit documents — one cdb_locate_spans_batch_device call per step (10^6 requests, ~3.2e7 texts), results resident
+    in HBM.  The doc index of an id comes from a side map, as an integration keeps one."""
+    import torch
+    import oracle
+    L = w["doclen"]
+    row_off = last.row_off
+    rowlen = row_off[1:] - row_off[:-1]
+    take = torch.clamp(rowlen, max=max_docs)
+    ntext = int(take.sum())
+    text_req = torch.repeat_interleave(torch.arange(npat, device=dev), take)
+    starts = torch.cumsum(take, 0) - take
+    within = torch.arange(ntext, device=dev) - starts[text_req]
+    hit_ids = last.pairs[row_off[:-1][text_req] + within, 0].contiguous()
+    sorted_ids, perm = torch.sort(ids)  # id -> doc index (ids are unique)
+    text_doc = perm[torch.searchsorted(sorted_ids, hit_ids)].contiguous()
+    del sorted_ids, perm, within, starts, hit_ids
+    req_kw_off = torch.arange(npat + 1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        return ix.spans_batch_device(d_pat.data_ptr(), d_poff.data_ptr(), npat, req_kw_off.data_ptr(), npat, text_req.data_ptr(),
+                                     text_doc.data_ptr(), ntext, stream)
+
+    sp = call()
+    total_spans = sp.total_spans
+    # parity on a sample of the texts: spans == the reference highlighter's (oracle port of database.cpp:58-77)
+    soff = torch.as_tensor(DevArray(sp.span_off, ntext + 1), device=dev)
+    spans = torch.as_tensor(DevArray(sp.spans, 2 * max(total_spans, 1)), device=dev).view(-1, 2)
+    ok = True
+    for t in range(0, ntext, max(1, ntext // 200)):
+        d, q = int(text_doc[t]), int(text_req[t])
+        doc = text[d * L:(d + 1) * L].cpu().numpy().tobytes()
+        got = spans[int(soff[t]):int(soff[t + 1])].cpu().numpy()
+        ok = ok and np.array_equal(got, oracle.port.spans([bytes(pat[poff[q]:poff[q + 1]])], doc))
+    ix.device_spans_free(sp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ix.device_spans_free(call())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # algorithmic bytes: every text's document read once + its (request, doc) pair + keyword, 16 B per span written
+    alg = ntext * (L + 16 + w["m"] + 8) + 16 * total_spans
+    return {"texts_per_step": ntext, "spans_per_step": int(total_spans), "ms_per_step": ms, "texts_per_sec": ntext / (ms / 1e3),
+            "spans_per_sec": total_spans / (ms / 1e3), "algorithmic_bytes_per_step": alg,
+            "achieved_GBps": alg / (ms / 1e3) / 1e9, "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / hbm_peak,
+            "parity_with_oracle": "ok" if ok else "MISMATCH",
+            "what": f"merged highlight spans of every keyword in its first <= {max_docs} hit documents, one batched call"}
+
+
+
 def secondary_workloads(sh, ix, text, snd, w, dev, hbm_peak):
     """Extra, driver-visible numbers beside the headline (N = 1): W8s on the same index — 8-byte keywords sampled from
     the corpus, longer than the prefix directory, so the search refines by binary search — and the cfg2
@@ -523,6 +578,12 @@ def run_ours(args):
     _p, _o, last = step()  # one more (untimed) step whose result is kept for the whole-job totals
     global_pairs = int(last.global_row_off[-1])
     global_occ = int(last.occurrences.sum())
+    spans_info = None
+    if world == 1 and args.spans:
+        try:
+            spans_info = spans_leg(ix, last, text, ids, d_pat, d_poff, npat, w, dev, hbm_peak, pat, poff)
+        except Exception as e:  # noqa: BLE001 - must not take the bench line down
+            spans_info = {"error": repr(e)[:300]}
     del last
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -672,6 +733,7 @@ def run_ours(args):
                       "compulsory_bytes": n_shard * (1 + width),
                       "frac_of_hbm_peak": n_shard * (1 + width) / 1e9 / (bst["total_ms"] / 1e3) / hbm_peak},
             "pairs_per_step": global_pairs, "occurrences_per_step": global_occ,
+            "spans": spans_info,
             "parity_sharded": parity_sharded,
             "extras": extras,
         }
@@ -757,6 +819,7 @@ def main():
     ap.add_argument("--no-rebuild", dest="rebuild", action="store_false",
                     help="skip the second (warm) build of the same corpus (build.rebuild_ms)")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip cdb_verify_sa after the build")
+    ap.add_argument("--no-spans", dest="spans", action="store_false", help="skip the highlight-span leg")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary workloads (W8s, cfg2)")
     ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")
     args = ap.parse_args()

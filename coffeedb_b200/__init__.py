@@ -25,7 +25,7 @@ CSRC = os.path.join(HERE, "csrc")
 # every symbol include/coffeedb_b200.h declares
 EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
-    "cdb_build", "cdb_build_device", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
+    "cdb_build", "cdb_build_device", "cdb_save", "cdb_build_or_load", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
     "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
@@ -90,6 +90,8 @@ def lib():
         L.cdb_add.argtypes = [vp, C.c_int64, vp, C.c_int64]
         L.cdb_add_many.argtypes = [vp, vp, vp, vp, C.c_int64]
         L.cdb_build.argtypes = [vp]
+        L.cdb_save.argtypes = [vp, C.c_char_p]
+        L.cdb_build_or_load.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32)]
         L.cdb_build_device.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.cdb_info.argtypes = [vp, i64p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.cdb_prefix_directory.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i64p]
@@ -183,6 +185,16 @@ class StringIndex:
     def build(self):
         """string_index::build (src/index.cpp:178-236)"""
         _check(self._L.cdb_build(self._h))
+
+    def save(self, path: str):
+        """Writes the built suffix array to `path`, keyed by a hash of the corpus."""
+        _check(self._L.cdb_save(self._h, os.fsencode(path)))
+
+    def build_or_load(self, path: str) -> bool:
+        """build(), reading the suffix array back from `path` when the file matches the staged corpus.  -> loaded?"""
+        loaded = C.c_int32(0)
+        _check(self._L.cdb_build_or_load(self._h, os.fsencode(path), C.byref(loaded)))
+        return bool(loaded.value)
 
     def query(self, keyword: bytes) -> list[tuple[int, int]]:
         """string_index::query (src/index.cpp:237-326): [(id, count)] in ascending doc index.  One keyword through

@@ -13,6 +13,7 @@
 #include "../host/micro_batcher.hpp"
 #include "index.cuh"
 #include "locate.cuh"
+#include "persist.cuh"
 #include "verify.cuh"
 
 namespace cdb {
@@ -314,10 +315,7 @@ cdb_status cdb_add_many(cdb_index* h, const int64_t* ids, const void* text, cons
     CDB_CATCH
 }
 
-cdb_status cdb_build(cdb_index* h) {
-    CDB_TRY
-    Index* ix = reinterpret_cast<Index*>(h);
-    if (!ix) throw Error(CDB_ERR_ARG, "cdb_build: index is NULL");
+static void build_from_staging(Index* ix, const SavedArraySource* saved) {
     if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
     require_device();
     if (ix->device < 0) CDB_CUDA(cudaGetDevice(&ix->device));
@@ -340,7 +338,7 @@ cdb_status cdb_build(cdb_index* h) {
         ix->d_off = (const i64*)ix->own_off;
         ix->d_ids = (const i64*)ix->own_ids;
         ix->nd = nd;
-        build_index(*ix, st);
+        build_index(*ix, st, saved);
     } catch (...) {
         cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
@@ -352,6 +350,35 @@ cdb_status cdb_build(cdb_index* h) {
         std::vector<u8>().swap(ix->h_text);
         ix->host_dropped = true;
     }
+}
+
+cdb_status cdb_build(cdb_index* h) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix) throw Error(CDB_ERR_ARG, "cdb_build: index is NULL");
+    build_from_staging(ix, nullptr);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_build_or_load(cdb_index* h, const char* path, int32_t* loaded) {
+    CDB_TRY
+    Index* ix = reinterpret_cast<Index*>(h);
+    if (!ix || !path) throw Error(CDB_ERR_ARG, "cdb_build_or_load: bad argument");
+    SavedArrayFile src(path);
+    build_from_staging(ix, &src);
+    if (loaded) *loaded = ix->loaded_from_file ? 1 : 0;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_save(const cdb_index* h, const char* path) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !path) throw Error(CDB_ERR_ARG, "cdb_save: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    DeviceSetter ds(ix->device);
+    save_index(*ix, path, thread_ctx(ix->device).stream);
     return CDB_OK;
     CDB_CATCH
 }

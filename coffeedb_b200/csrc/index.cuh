@@ -54,6 +54,7 @@ struct Index {
     // build statistics
     double build_ms = 0, sort_ms = 0;
     i64 rounds = 0, chunks = 0;
+    bool loaded_from_file = false;  // the last build read a saved array instead of sorting (cdb_build_or_load)
     // cdb_query's coalescing queue (capi.cu), created on first use
     mutable std::mutex batcher_mu;
     mutable std::shared_ptr<void> batcher;
@@ -62,7 +63,15 @@ struct Index {
     void free_device();
 };
 
-void build_index(Index& ix, cudaStream_t st);
+// A saved suffix array that may stand in for the sort (persist.cu): try_load is called once the geometry of the staged
+// corpus is known (n, widths, flags) and returns true after it has filled ix.d_sa from the file.
+struct SavedArraySource {
+    virtual bool try_load(Index& ix, cudaStream_t st) const = 0;
+    virtual ~SavedArraySource() {}
+};
+void build_index(Index& ix, cudaStream_t st, const SavedArraySource* saved = nullptr);
+// sa_build.cu: 64-bit hash of the corpus the index was built from (text, doc_off, ids)
+u64 corpus_hash(const Index& ix, i64 n, cudaStream_t st);
 // locate.cu: fills ix.d_ptab (after the suffix array is complete)
 void build_prefix_table(Index& ix, cudaStream_t st);
 

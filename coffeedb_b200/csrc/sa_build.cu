@@ -808,7 +808,57 @@ static void apply_signed_radix_layout(Index& ix, cudaStream_t st) {
     CDB_CUDA(cudaStreamSynchronize(st));
 }
 
-void build_index(Index& ix, cudaStream_t st) {
+// 64-bit corpus hash (text, doc_off, ids): sum over all 8-byte words of mix(word, position) — order-independent, so
+// it is one grid-stride pass with a warp-reduced atomic per warp.  Keys a saved suffix array to its corpus (persist.cu).
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__global__ void hash_words_kernel(const u64* __restrict__ w, u64 nwords, u64 salt, unsigned long long* __restrict__ acc) {
+    u64 h = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (u64)gridDim.x * blockDim.x)
+        h += mix64(ld_stream_u64(w + i) ^ mix64(i + salt));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(acc, (unsigned long long)h);
+}
+
+__global__ void hash_tail_kernel(const u8* __restrict__ text, i64 from, i64 n, unsigned long long* __restrict__ acc) {
+    u64 h = 0;
+    for (i64 i = from + threadIdx.x; i < n; i += blockDim.x) h += mix64((u64)text[i] ^ mix64((u64)i + 0x7e57ull));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(acc, (unsigned long long)h);
+}
+
+u64 corpus_hash(const Index& ix, i64 n, cudaStream_t st) {
+    DevBuf<unsigned long long> acc(1, st);
+    CDB_CUDA(cudaMemsetAsync(acc.p, 0, 8, st));
+    auto words = [&](const void* p, u64 nwords, u64 salt) {
+        if (!nwords) return;
+        const int g = (int)std::min<i64>(ceil_div((i64)nwords, 256), kNumSMs * 8);
+        hash_words_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const u64*>(p), nwords, salt, acc.p);
+        CDB_LAUNCH_CHECK();
+    };
+    words(ix.d_text, (u64)(n >> 3), 0x1000000000000000ull);  // text is 16-byte aligned
+    if (n & 7) {
+        hash_tail_kernel<<<1, 32, 0, st>>>(ix.d_text, n & ~(i64)7, n, acc.p);
+        CDB_LAUNCH_CHECK();
+    }
+    words(ix.d_off, (u64)ix.nd + 1, 0x2000000000000000ull);
+    if (ix.d_ids) words(ix.d_ids, (u64)ix.nd, 0x3000000000000000ull);
+    unsigned long long h = 0;
+    CDB_CUDA(cudaMemcpyAsync(&h, acc.p, 8, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    return (u64)h ^ mix64((u64)n * 1315423911ull + (u64)ix.nd);
+}
+
+void build_index(Index& ix, cudaStream_t st, const SavedArraySource* saved) {
     cudaEvent_t e0, e1;
     CDB_CUDA(cudaEventCreate(&e0));
     CDB_CUDA(cudaEventCreate(&e1));
@@ -867,15 +917,21 @@ void build_index(Index& ix, cudaStream_t st) {
         int b = bits_for((u64)sigma);  // symbols 0..sigma
         int S = 64 / b;
         if (S > EX_MAXS) S = EX_MAXS;
-        if (ix.width == 4)
-            build_typed<u32>(ix, tab, b, S, st);
-        else
-            build_typed<u64>(ix, tab, b, S, st);
-        if (ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size) {
+        ix.loaded_from_file = false;
+        if (saved && saved->try_load(ix, st)) {
+            // the saved array is the finished one (note-N1 layout included); only the prefix directory is rebuilt
+            ix.loaded_from_file = true;
+        } else {
             if (ix.width == 4)
-                apply_signed_radix_layout<u32>(ix, st);
+                build_typed<u32>(ix, tab, b, S, st);
             else
-                apply_signed_radix_layout<u64>(ix, st);
+                build_typed<u64>(ix, tab, b, S, st);
+            if (ix.mixed && ix.opt.compat_signed && ix.n > ix.chuck_size) {
+                if (ix.width == 4)
+                    apply_signed_radix_layout<u32>(ix, st);
+                else
+                    apply_signed_radix_layout<u64>(ix, st);
+            }
         }
         build_prefix_table(ix, st);
     }

@@ -111,6 +111,14 @@ cdb_status cdb_add_many(cdb_index* idx, const int64_t* ids, const void* text, co
 /* string_index::build() (src/index.cpp:178-236): uploads the staged text and constructs the packed suffix
  * array on the device.  Element = (offset_in_doc << bits) | doc_index, 4 bytes wide iff bits1+bits2 <= 32. */
 cdb_status cdb_build(cdb_index* idx);
+/* Suffix-array persistence (no reference counterpart: the reference rebuilds its index from the raw/ files at every
+ * start and every `build`, src/server.cpp:43-44, src/database.cpp:170-282 — build time is restart latency).
+ * cdb_save writes the finished packed array to `path`, keyed by a 64-bit hash of the corpus (text, doc_off, ids), the
+ * geometry and the compat flag.  cdb_build_or_load is cdb_build for the staged corpus, except that a file at `path`
+ * whose key matches is read back instead of sorting; a missing, stale or truncated file means a normal build.
+ * *loaded (may be NULL) = 1 when the array came from the file. */
+cdb_status cdb_save(const cdb_index* idx, const char* path);
+cdb_status cdb_build_or_load(cdb_index* idx, const char* path, int32_t* loaded);
 /* Same, from a corpus already resident in device memory (text[n], doc_off[nd+1], ids[nd] are BORROWED and
  * must outlive the index).  `stream` is a cudaStream_t (NULL = default stream).
  * Contract of the borrowed buffers: doc_off[0] == 0 and doc_off is non-decreasing; d_text is 16-byte aligned and has at

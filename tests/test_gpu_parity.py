@@ -669,3 +669,55 @@ def test_verifier_rejects_plain_order_where_reference_is_signed():
     assert not np.array_equal(plain.export_sa(), ref.export_sa())
     plain.close()
     ref.close()
+
+
+# ---- suffix-array persistence ---------------------------------------------------------------------------
+def test_save_and_build_or_load(tmp_path):
+    """cdb_save + cdb_build_or_load: the same corpus reads the array back (bit-identical, same answers, no sort rounds);
+    a changed corpus, a changed compat flag or a truncated file falls back to a normal build."""
+    text, off, ids = corpora.utf8ish(2500, 300, seed=95)  # note-N1 layout: the saved array includes the rotations
+    path = str(tmp_path / "val.cdbsa")
+    a = build(text, off, ids)
+    a.save(path)
+    sa = a.export_sa()
+    pats = [b"a", b"ab", b"\xc3", b"the", b" "]
+    want = a.locate_batch(pats)
+    a.close()
+    b = cdb.StringIndex()
+    b.add_many(ids, text, off)
+    assert b.build_or_load(path) is True
+    assert np.array_equal(b.export_sa(), sa) and b.verify_sa()["ok"]
+    got = b.locate_batch(pats)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    b.close()
+    # one byte of the corpus changed -> stale file -> normal build of the new corpus
+    text2 = text.copy()
+    text2[len(text2) // 2] ^= 1
+    c = cdb.StringIndex()
+    c.add_many(ids, text2, off)
+    assert c.build_or_load(path) is False
+    sa2, _b1, _w = oracle.port.build_sa(text2, off)
+    assert np.array_equal(c.export_sa(), sa2)
+    c.close()
+    # different ids (same text) also change the key
+    d = cdb.StringIndex()
+    d.add_many(ids + 1, text, off)
+    assert d.build_or_load(path) is False
+    d.close()
+    # other compat flag -> different layout -> not loaded
+    e = cdb.StringIndex(compat_signed=False)
+    e.add_many(ids, text, off)
+    assert e.build_or_load(path) is False
+    e.close()
+    # truncated file -> normal build, same result
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[: len(raw) // 2])
+    f = cdb.StringIndex()
+    f.add_many(ids, text, off)
+    assert f.build_or_load(path) is False and np.array_equal(f.export_sa(), sa)
+    f.close()
+    # no file at all
+    g = cdb.StringIndex()
+    g.add_many(ids, text, off)
+    assert g.build_or_load(str(tmp_path / "missing.cdbsa")) is False and np.array_equal(g.export_sa(), sa)
+    g.close()
