@@ -350,7 +350,7 @@ def secondary_workloads(sh, ix, text, snd, w, dev, hbm_peak):
         r5 = timed(sh5, dp, dpo, np5, steps=5)
         inf5 = sh5.local.info()
         r5.update({"build_ms": b5["total_ms"], "build_corpus_GB_per_s": n5 / 1e9 / (b5["total_ms"] / 1e3), "rounds": b5["rounds"],
-                   "docs": nd5, "corpus_bytes": n5, "sa_width": inf5["width"], "verified": bool(v5["ok"]),
+                   "docs": nd5, "corpus_bytes": n5, "sa_width": inf5["width"], "verified": bool(v5["ok"]), "verify": v5,
                    "signed_rule_pairs": v5["signed_rule_pairs"], "prefix_directory_symbols": sh5.local.prefix_directory()["symbols"],
                    "what": "BASELINE configs[4] shape on one GPU (1 GiB): UTF-8 documents of up to 64 KB, note-N1 layout; "
                            "10^5 eight-byte keywords sampled from the corpus (they may straddle documents: then no hit)"})
@@ -441,6 +441,17 @@ def run_reference(args):
             times.append(s)
     total = float(np.sum(times))
     val = per_step * len(times) / total
+    # beside the headline (which stays query() alone, the less work of the two): the same keywords as one-keyword requests
+    # through the rest of the reference's request path — the sorts of filter() and span [0,32), what our arm's e2e call does
+    fs = None
+    try:
+        nf = int(min(per_step, 200_000))
+        s2, _r, _p, _m = ref.filter_span_batch(pat[: poff[nf]], poff[: nf + 1], FILTER_SPAN[0], FILTER_SPAN[1], threads, keep=False)
+        fs = {"value": nf / s2, "unit": UNIT, "sample": f"{nf} requests",
+              "what": "query() + std::ranges::sort + std::sort by descending $correlation + span [0,32) per request "
+                      "(src/interface.cpp:82,143-146,196-209 restated around the unmodified query(), oracle/ref_harness.cpp)"}
+    except Exception as e:  # noqa: BLE001
+        fs = {"error": repr(e)[:200]}
     # the reference's OWN build, on a bounded prefix of the same corpus (the full 10^10-suffix build takes tens of
     # minutes on host cores): string_index::build() (src/index.cpp:178-236), all host threads
     rb = None
@@ -466,6 +477,7 @@ def run_reference(args):
                          "pairs_per_step": tp, "occurrences_per_step": to},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "filter_span": fs,
         "reference_build": rb,
     }
     print(json.dumps(out))
@@ -615,6 +627,22 @@ def run_ours(args):
     e2e_val = npat * e2e_steps / float(e2e_s.item())
     h2d_bytes = int(pat.nbytes + poff.nbytes)
 
+    # ---- e2e through cdb_filter (N = 1): the request the reference's server actually answers — filter() over one keyword,
+    # the descending-$correlation sort and a span (src/interface.cpp:46-147, 196-209) — so that only result[0, 32) of
+    # every request crosses PCIe instead of the full rows.  Host buffers pinned, H2D of the packed requests and D2H of the
+    # slices inside the timed region.
+    e2e_full = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
+                "steps": e2e_steps, "call": "cdb_locate_batch: full (id, count) rows of every keyword to host memory"}
+    e2e_main = dict(e2e_full)
+    filt = None
+    if world == 1 and args.filter:
+        try:
+            filt = filter_leg(ix, pat, poff, npat, e2e_steps)
+            e2e_main = {"value": filt["value"], "unit": UNIT, "h2d_bytes_per_step": filt["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": filt["d2h_bytes_per_step"], "steps": e2e_steps, "call": filt["call"]}
+        except Exception as e:  # noqa: BLE001 - falls back to the full-row number, and says so
+            filt = {"error": repr(e)[:300]}
+
     # ---- latency of ONE keyword through the host ABI (the reference's own calling pattern: query() per request)
     one_pat = np.ascontiguousarray(pat[: poff[1]])
     one_off = np.ascontiguousarray(poff[:2])
@@ -678,7 +706,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname)
+            cpu = cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname, filt)
         except Exception as e:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e!r}"}
 
@@ -713,8 +741,9 @@ def run_ours(args):
                        "pattern_bytes": w["m"], "n_suffixes_per_gpu": n_shard, "sa_width": width,
                        "l2": "inputs (suffix array + text) far larger than L2, no flush needed",
                        "parallelism": "replica" if world == 1 else f"doc-range shards x{world}, NCCL pattern bcast + count merge"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                    "steps": e2e_steps},
+            "e2e": e2e_main,
+            "e2e_full_rows": e2e_full,
+            "filter": filt,
             "gpu_launches": int(launches),
             "single_query_latency_us": single_us,
             "concurrent_single_queries": concurrent,
@@ -773,7 +802,57 @@ def concurrent_single_queries(ix, pat, poff, threads, per_thread):
             "device_batches": after["batches"] - before["batches"], "largest_batch": after["largest"]}
 
 
-def cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname):
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    """numpy view of a page-locked copy of `a` (the e2e legs read their inputs from pinned host memory)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+    return t.numpy().view(a.dtype).reshape(a.shape)
+
+
+FILTER_SPAN = (0, 32)
+
+
+def filter_requests(pat, poff, npat):
+    """npat one-keyword requests with span [0, 32) as packed cdb_filter arrays (pinned)."""
+    import coffeedb_b200 as cdb
+    terms = np.zeros(npat, cdb.TERM_DTYPE)
+    terms["range"] = -1
+    terms["kw_begin"], terms["kw_end"] = poff[:npat], poff[1:npat + 1]
+    span = np.tile(np.array(FILTER_SPAN, np.int64), (npat, 1))
+    return (pinned_copy(np.ascontiguousarray(pat[: poff[npat]])), pinned_copy(terms), pinned_copy(np.arange(npat + 1, dtype=np.int64)),
+            pinned_copy(span))
+
+
+def filter_leg(ix, pat, poff, npat, steps):
+    """End-to-end through cdb_filter: npat requests {key: keyword, span: [0,32)} per step from pinned host arrays, answers
+    (id, $correlation)[0:32] in the reference's order + matched counts back in host memory."""
+    import coffeedb_b200 as cdb
+    kw, terms, rto, span = filter_requests(pat, poff, npat)
+    none = np.zeros((0, 4), np.int64)
+
+    def one():
+        res = cdb.filter_raw([ix], kw, none, terms, rto, None, span)
+        nbytes = (npat + 1) * 8 + res.total_pairs * 16 + npat * 8
+        first = res.pairs[0] if res.total_pairs else 0  # touch the host result
+        tot = res.total_pairs
+        cdb.filter_result_free(res)
+        return nbytes, tot, first
+
+    for _ in range(2):
+        one()
+    launches0 = cdb.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d2h, tot, _f = one()
+    dt = time.perf_counter() - t0
+    return {"value": npat * steps / dt, "ms_per_step": dt / steps * 1e3,
+            "h2d_bytes_per_step": int(kw.nbytes + terms.nbytes + rto.nbytes + span.nbytes), "d2h_bytes_per_step": int(d2h),
+            "pairs_returned_per_step": int(tot), "launches_per_step": (cdb.launch_count() - launches0) // steps,
+            "call": f"cdb_filter: {npat} requests {{key: keyword, span: [{FILTER_SPAN[0]},{FILTER_SPAN[1]})}} -> (id, $correlation) in "
+                    "the order of src/interface.cpp:143-146, rows located in id order, ids not in doc order"}
+
+
+def cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname, filt=None):
     import coffeedb_b200 as cdb
     import oracle
     h_text = text[: inf["n"]].cpu().numpy()
@@ -797,8 +876,31 @@ def cpu_baseline(ix, text, doc_off, ids, inf, pat, poff, w, wname):
     for q in range(0, nsample, max(1, nsample // 16)):
         got = pairs[row_off[q]:row_off[q + 1]]
         ok = ok and np.array_equal(got, ref.query(bytes(pat[poff[q]:poff[q + 1]])))
+    # the same requests as the e2e leg (cdb_filter): query() + the sorts + the span, timed on the same sample, and the
+    # answers compared element by element with cdb_filter's (order included: ties follow std::sort)
+    fs = None
+    if filt is not None and "error" not in filt:
+        try:
+            nf = min(nsample, 200_000)
+            s2, _r, _p, _m = ref.filter_span_batch(pat[: poff[nf]], poff[: nf + 1], FILTER_SPAN[0], FILTER_SPAN[1], threads, keep=False)
+            ncheck = min(nf, 20_000)
+            _s, r_off, r_pairs, r_matched = ref.filter_span_batch(pat[: poff[ncheck]], poff[: ncheck + 1], FILTER_SPAN[0],
+                                                                  FILTER_SPAN[1], threads)
+            kw, terms, rto, span = filter_requests(pat, poff, ncheck)
+            res = cdb.filter_raw([ix], kw, np.zeros((0, 4), np.int64), terms, rto, None, span)
+            g_off = np.ctypeslib.as_array(res.row_off, shape=(ncheck + 1,))
+            g_pairs = np.ctypeslib.as_array(res.pairs, shape=(max(res.total_pairs, 1), 2))[: res.total_pairs]
+            g_matched = np.ctypeslib.as_array(res.matched, shape=(ncheck,))
+            same = (np.array_equal(g_off, r_off) and np.array_equal(g_pairs, r_pairs) and np.array_equal(g_matched, r_matched))
+            cdb.filter_result_free(res)
+            fs = {"value": nf / s2, "unit": UNIT, "sample": f"{nf} requests", "requests_compared": ncheck,
+                  "parity_with_gpu": "ok" if same else "MISMATCH",
+                  "what": "query() + std::ranges::sort + std::sort by descending $correlation + span [0,32) per request "
+                          "(src/interface.cpp:82,143-146,196-209 restated around the unmodified query(), oracle/ref_harness.cpp)"}
+        except Exception as e:  # noqa: BLE001
+            fs = {"error": repr(e)[:300]}
     ref.close()
-    return {"value": nsample / s, "unit": UNIT, "cores": threads, "kind": "reference",
+    return {"value": nsample / s, "unit": UNIT, "cores": threads, "kind": "reference", "filter_span": fs,
             "sample": (f"{nsample} of {w['npat']} patterns on the full {wname} index; reference query() "
                        "(src/index.cpp:237-326, compiled unmodified) over the GPU-built packed suffix array, "
                        f"{threads} host threads pulling 64-pattern blocks"),
@@ -820,6 +922,7 @@ def main():
                     help="skip the second (warm) build of the same corpus (build.rebuild_ms)")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip cdb_verify_sa after the build")
     ap.add_argument("--no-spans", dest="spans", action="store_false", help="skip the highlight-span leg")
+    ap.add_argument("--no-filter", dest="filter", action="store_false", help="e2e through cdb_locate_batch (full rows) only")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary workloads (W8s, cfg2)")
     ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")
     args = ap.parse_args()

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -29,6 +30,7 @@ EXPORTS = [
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
     "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
+    "cdb_numeric_create", "cdb_numeric_destroy", "cdb_numeric_query", "cdb_filter", "cdb_filter_result_free",
 ]
 
 CDB_OK = 0
@@ -58,6 +60,25 @@ class Spans(C.Structure):
 class DeviceSpans(C.Structure):
     _fields_ = [("ntext", C.c_int64), ("total_spans", C.c_int64), ("span_off", C.c_void_p), ("spans", C.c_void_p),
                 ("_owner", C.c_void_p)]
+
+
+class FilterKey(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("index", C.c_void_p)]
+
+
+class FilterBatch(C.Structure):
+    _fields_ = [("keys", C.POINTER(FilterKey)), ("nkeys", C.c_int32), ("reserved", C.c_int32), ("kw", C.c_void_p),
+                ("kw_len", C.c_int64), ("ranges", C.c_void_p), ("nranges", C.c_int64), ("terms", C.c_void_p),
+                ("req_term_off", C.c_void_p), ("nreq", C.c_int64), ("corr_range", C.c_void_p), ("span", C.c_void_p)]
+
+
+class FilterResult(C.Structure):
+    _fields_ = [("nreq", C.c_int64), ("total_pairs", C.c_int64), ("row_off", C.POINTER(C.c_int64)),
+                ("pairs", C.POINTER(C.c_int64)), ("matched", C.POINTER(C.c_int64)), ("_owner", C.c_void_p)]
+
+
+# cdb_filter_term (include/coffeedb_b200.h)
+TERM_DTYPE = np.dtype([("key", "<i4"), ("range", "<i4"), ("kw_begin", "<i8"), ("kw_end", "<i8")])
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -122,6 +143,13 @@ def lib():
         L.cdb_last_locate_stats.restype = None
         L.cdb_launch_count.restype = C.c_uint64
         L.cdb_trim.restype = None
+        L.cdb_numeric_create.argtypes = [C.c_int32, vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+        L.cdb_numeric_destroy.argtypes = [vp]
+        L.cdb_numeric_destroy.restype = None
+        L.cdb_numeric_query.argtypes = [vp, i64p, i64p, C.POINTER(Result)]
+        L.cdb_filter.argtypes = [C.POINTER(FilterBatch), C.POINTER(FilterResult)]
+        L.cdb_filter_result_free.argtypes = [C.POINTER(FilterResult)]
+        L.cdb_filter_result_free.restype = None
         _lib = L
     return _lib
 
@@ -380,3 +408,162 @@ def splice(text: bytes, spans: np.ndarray, left: bytes, right: bytes) -> bytes:
                        l.ctypes.data if len(l) else None, len(l), r.ctypes.data if len(r) else None, len(r),
                        out.ctypes.data, need)
     return out[:got].tobytes()
+
+
+# ---- filter() on the device (include/coffeedb_b200.h: cdb_filter) --------------------------------------
+INT64_MAX = (1 << 63) - 1
+_RANGE = re.compile(r"\s*(\[|\()\s*(.+)\s*,\s*(.+)(\]|\))\s*")  # range_pattern, src/utility.h:68
+
+
+def parse_range(text: str, kind: int) -> tuple[int, int, int, int]:
+    """parse_range<T> (src/utility.h:69-86) -> (lo value bits, lo id, hi value bits, hi id).  kind 0: int64, 1: double.
+    "-inf" / "inf" become numeric_limits<T>::min() / max() as value_conv does (for double min() is the smallest
+    positive normal — the reference's behaviour, kept)."""
+    m = _RANGE.fullmatch(text)
+    if not m:
+        raise ValueError("Invalid range: " + text)
+
+    def conv(sv: str) -> int:
+        low = sv.lower()
+        if kind == 0:
+            if low == "-inf":
+                return -(1 << 63)
+            if low == "inf":
+                return INT64_MAX
+            if not re.fullmatch(r"-?[0-9]+", sv):
+                raise ValueError("Invalid value: " + low)
+            return int(sv)
+        if low == "-inf":
+            v = np.finfo(np.float64).tiny
+        elif low == "inf":
+            v = np.finfo(np.float64).max
+        else:
+            v = float(sv)
+        return int(np.array([v], np.float64).view(np.int64)[0])
+
+    return (conv(m.group(2)), INT64_MAX if m.group(1) == "(" else 0, conv(m.group(3)), INT64_MAX if m.group(4) == "]" else 0)
+
+
+def parse_uint_range(text: str) -> tuple[int, int]:
+    """parse_uint_range (src/utility.h:87-104): "$correlation" and "span" -> half-open [L, R)."""
+    m = _RANGE.fullmatch(text)
+    lo, hi = 1, 0
+    if m:
+        lo, hi = int(m.group(2)), int(m.group(3))
+        if m.group(1) == "(":
+            lo += 1
+        if m.group(4) == "]":
+            hi += 1
+    if lo > hi or lo < 0:
+        raise ValueError("Invalid range: " + text)
+    return lo, hi
+
+
+class NumericIndex:
+    """integer_index / double_index (src/index.h:29-53) on the device: kind 0 = int64 values, 1 = double."""
+
+    def __init__(self, kind: int, ids, values, device: int = -1):
+        self._L = lib()
+        self.kind = kind
+        ids = np.ascontiguousarray(ids, np.int64)
+        vals = np.ascontiguousarray(values, np.int64 if kind == 0 else np.float64)
+        assert len(ids) == len(vals)
+        self._h = C.c_void_p()
+        _check(self._L.cdb_numeric_create(kind, ids.ctypes.data, vals.ctypes.data, len(ids), device, C.byref(self._h)))
+
+    def query(self, range_text: str) -> np.ndarray:
+        """integer_index::query / double_index::query (src/index.cpp:159-161, 170-172): [(id, 0)] in (value, id) order."""
+        lo0, lo1, hi0, hi1 = parse_range(range_text, self.kind)
+        lo = (C.c_int64 * 2)(lo0, lo1)
+        hi = (C.c_int64 * 2)(hi0, hi1)
+        res = Result()
+        _check(self._L.cdb_numeric_query(self._h, lo, hi, C.byref(res)))
+        try:
+            return np.ctypeslib.as_array(res.pairs, shape=(max(res.total_pairs, 1), 2))[: res.total_pairs].copy()
+        finally:
+            self._L.cdb_result_free(C.byref(res))
+
+    def close(self):
+        if self._h:
+            self._L.cdb_numeric_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def filter_raw(keys, kw: np.ndarray, ranges: np.ndarray, terms: np.ndarray, req_term_off: np.ndarray, corr=None, span=None):
+    """cdb_filter on packed arrays (no per-request Python work): keys = list of StringIndex | NumericIndex | None (a key the
+    database does not have); terms = TERM_DTYPE array; ranges = int64 [nranges, 4]; corr / span = int64 [nreq, 2] or None.
+    -> FilterResult (free with filter_result_free); row_off / pairs / matched are views of pinned host memory."""
+    L = lib()
+    fk = (FilterKey * max(len(keys), 1))()
+    for i, k in enumerate(keys):
+        fk[i].kind = -1 if k is None else (0 if isinstance(k, StringIndex) else 1)
+        fk[i].index = None if k is None else k._h
+    b = FilterBatch()
+    b.keys, b.nkeys = fk, len(keys)
+    b.kw, b.kw_len = (kw.ctypes.data if len(kw) else None), len(kw)
+    b.ranges, b.nranges = (ranges.ctypes.data if len(ranges) else None), len(ranges)
+    assert terms.dtype == TERM_DTYPE and req_term_off.dtype == np.int64
+    b.terms = terms.ctypes.data if len(terms) else None
+    b.req_term_off, b.nreq = req_term_off.ctypes.data, len(req_term_off) - 1
+    b.corr_range = corr.ctypes.data if corr is not None else None
+    b.span = span.ctypes.data if span is not None else None
+    res = FilterResult()
+    _check(L.cdb_filter(C.byref(b), C.byref(res)))
+    return res
+
+
+def filter_result_free(res: FilterResult):
+    lib().cdb_filter_result_free(C.byref(res))
+
+
+def filter_batch(keys: dict, requests: list) -> list:
+    """filter() + span of src/interface.cpp:46-147, 196-209 for a batch of requests.
+
+    keys      {name: StringIndex | NumericIndex | None}
+    requests  [{"constraints": {name: "range" | ["range", ...], "$correlation": "[L,R)"}, "span": "[b,e)"}, ...]
+    ->        per request (pairs int64 [m, 2] = (id, $correlation) in the reference's order, matched)"""
+    names = list(keys)
+    slot = {n: i for i, n in enumerate(names)}
+    objs = [keys[n] for n in names]
+    terms, ranges, rto, kws = [], [], [0], bytearray()
+    corr = np.zeros((len(requests), 2), np.int64)
+    span = np.zeros((len(requests), 2), np.int64)
+    corr[:, 0], corr[:, 1] = -(1 << 63), INT64_MAX
+    span[:, 1] = INT64_MAX
+    for r, req in enumerate(requests):
+        for name, val in req.get("constraints", {}).items():
+            if name == "$correlation":
+                corr[r] = parse_uint_range(val)
+                continue
+            vals = [val] if isinstance(val, str) else list(val)
+            if name not in slot:  # a key the database does not have (src/database.cpp:389-391)
+                slot[name] = len(objs)
+                objs.append(None)
+            k = slot[name]
+            for v in vals:
+                if isinstance(objs[k], NumericIndex):
+                    ranges.append(parse_range(v, objs[k].kind))
+                    terms.append((k, len(ranges) - 1, 0, 0))
+                else:
+                    b = v.encode() if isinstance(v, str) else bytes(v)
+                    terms.append((k, -1, len(kws), len(kws) + len(b)))
+                    kws += b
+        rto.append(len(terms))
+        if req.get("span") is not None:
+            span[r] = parse_uint_range(req["span"])
+    res = filter_raw(objs, np.frombuffer(bytes(kws), np.uint8), np.array(ranges, np.int64).reshape(-1, 4),
+                     np.array(terms, TERM_DTYPE), np.array(rto, np.int64), corr, span)
+    try:
+        n = res.nreq
+        ro = np.ctypeslib.as_array(res.row_off, shape=(n + 1,)).copy()
+        pr = np.ctypeslib.as_array(res.pairs, shape=(max(res.total_pairs, 1), 2))[: res.total_pairs].copy()
+        mt = np.ctypeslib.as_array(res.matched, shape=(max(n, 1),))[:n].copy()
+    finally:
+        filter_result_free(res)
+    return [(pr[ro[r]:ro[r + 1]], int(mt[r])) for r in range(n)]

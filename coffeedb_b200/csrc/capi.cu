@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../host/micro_batcher.hpp"
+#include "filter.cuh"
 #include "index.cuh"
 #include "locate.cuh"
 #include "persist.cuh"
@@ -30,7 +31,12 @@ void Index::free_device() {
     if (own_off) cudaFree(own_off);
     if (own_ids) cudaFree(own_ids);
     if (d_ptab) cudaFree(d_ptab);
+    if (d_rank_tab) cudaFree(d_rank_tab);
+    if (d_ids_by_rank) cudaFree(d_ids_by_rank);
     d_ptab = nullptr;
+    d_rank_tab = nullptr;
+    d_ids_by_rank = nullptr;
+    ids_order = -1;
     pt_k = pt_b = 0;
     d_sa = own_text = own_off = own_ids = nullptr;
     d_text = nullptr;
@@ -489,6 +495,147 @@ cdb_status cdb_build_stats(const cdb_index* h, double* total_ms, double* sort_ms
     if (chunks) *chunks = ix->chunks;
     return CDB_OK;
     CDB_CATCH
+}
+
+// ---- filter() (filter.cu) ------------------------------------------------------------------------------------------------
+cdb_status cdb_numeric_create(int32_t kind, const int64_t* ids, const void* values, int64_t n, int32_t device, cdb_numeric** out) {
+    CDB_TRY
+    if (!out || n < 0 || (kind != 0 && kind != 1) || (n > 0 && (!ids || !values))) throw Error(CDB_ERR_ARG, "cdb_numeric_create: bad argument");
+    require_device();
+    int dev = device;
+    if (dev < 0) CDB_CUDA(cudaGetDevice(&dev));
+    DeviceSetter ds(dev);
+    keep_pool_memory(dev);
+    *out = reinterpret_cast<cdb_numeric*>(numeric_create(kind, ids, values, n, dev, thread_ctx(dev).stream));
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_numeric_destroy(cdb_numeric* c) {
+    if (!c) return;
+    NumericIndex* ni = reinterpret_cast<NumericIndex*>(c);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ni->device);
+    delete ni;
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+cdb_status cdb_numeric_query(const cdb_numeric* c, const int64_t lo[2], const int64_t hi[2], cdb_result* out) {
+    CDB_TRY
+    const NumericIndex* ni = reinterpret_cast<const NumericIndex*>(c);
+    if (!ni || !lo || !hi || !out) throw Error(CDB_ERR_ARG, "cdb_numeric_query: bad argument");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ni->device);
+    cudaStream_t st = thread_ctx(ni->device).stream;
+    i64 b = 0, e = 0;
+    numeric_bounds(*ni, lo, hi, st, &b, &e);
+    const i64 m = e - b;
+    HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
+    try {
+        own->row_off = g_pinned.get(16, &own->row_cap);
+        own->pairs = g_pinned.get((size_t)(m ? m : 1) * 16, &own->pairs_cap);
+        i64* pr = (i64*)own->pairs;
+        // ids land in the upper half of the buffer, then spread into (id, 0) pairs front to back
+        i64* tmp = pr + m;
+        if (m) CDB_CUDA(cudaMemcpyAsync(tmp, ni->vid + b, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        for (i64 i = 0; i < m; ++i) {
+            const i64 id = tmp[i];
+            pr[2 * i] = id;
+            pr[2 * i + 1] = 0;
+        }
+        ((i64*)own->row_off)[0] = 0;
+        ((i64*)own->row_off)[1] = m;
+    } catch (...) {
+        if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+        if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+        delete own;
+        throw;
+    }
+    out->npat = 1;
+    out->total_pairs = m;
+    out->row_off = (const i64*)own->row_off;
+    out->pairs = (const i64*)own->pairs;
+    out->_owner = own;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+struct FilterOwner {
+    void* p[3] = {nullptr, nullptr, nullptr};  // row_off, pairs, matched
+    size_t cap[3] = {0, 0, 0};
+    void release() {
+        for (int i = 0; i < 3; ++i)
+            if (p[i]) g_pinned.put(p[i], cap[i]);
+    }
+};
+
+cdb_status cdb_filter(const cdb_filter_batch* b, cdb_filter_result* out) {
+    CDB_TRY
+    if (!b || !out || b->nreq < 0 || (b->nreq > 0 && !b->req_term_off) || (b->nkeys > 0 && !b->keys))
+        throw Error(CDB_ERR_ARG, "cdb_filter: bad argument");
+    std::memset(out, 0, sizeof(*out));
+    require_device();
+    int dev = filter_device_of(*b);
+    if (dev < 0) CDB_CUDA(cudaGetDevice(&dev));
+    DeviceSetter ds(dev);
+    cudaStream_t st = thread_ctx(dev).stream;
+    const i64 nreq = b->nreq;
+    FilterOwner* own = new FilterOwner();
+    try {
+        FilterOut fo;
+        filter_batch_device(*b, st, fo);
+        own->p[0] = g_pinned.get((size_t)(nreq + 1) * 8, &own->cap[0]);
+        own->p[1] = g_pinned.get((size_t)(fo.total_fin ? fo.total_fin : 1) * 16, &own->cap[1]);
+        own->p[2] = g_pinned.get((size_t)(nreq ? nreq : 1) * 8, &own->cap[2]);
+        i64* ro = (i64*)own->p[0];
+        i64* pr = (i64*)own->p[1];
+        CDB_CUDA(cudaMemcpyAsync(ro, fo.fin_off.p, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (fo.total_fin) CDB_CUDA(cudaMemcpyAsync(pr, fo.fin.p, (size_t)fo.total_fin * 16, cudaMemcpyDeviceToHost, st));
+        if (nreq) CDB_CUDA(cudaMemcpyAsync(own->p[2], fo.matched.p, (size_t)nreq * 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        // Requests that did not fit the warp path: their id-ascending survivors come back whole and get the reference's own
+        // final step here — the std::sort of src/interface.cpp:143-146 and the span of :196-209.
+        std::vector<std::pair<int64_t, int64_t>> v;
+        for (i64 r : fo.pending) {
+            u64 off = 0, len = 0;
+            CDB_CUDA(cudaMemcpyAsync(&off, fo.raw_off.p + r, 8, cudaMemcpyDeviceToHost, st));
+            CDB_CUDA(cudaMemcpyAsync(&len, fo.raw_len.p + r, 8, cudaMemcpyDeviceToHost, st));
+            CDB_CUDA(cudaStreamSynchronize(st));
+            v.resize((size_t)len);
+            static_assert(sizeof(std::pair<int64_t, int64_t>) == 16, "pair layout");
+            if (len) CDB_CUDA(cudaMemcpyAsync((void*)v.data(), fo.raw.p + 2 * off, (size_t)len * 16, cudaMemcpyDeviceToHost, st));
+            CDB_CUDA(cudaStreamSynchronize(st));
+            std::sort(v.begin(), v.end(), [](auto x, auto y) { return x.second > y.second; });
+            const i64 take = ro[r + 1] - ro[r];
+            i64 first = 0;
+            if (b->span) first = b->span[2 * r] < 0 ? 0 : b->span[2 * r];
+            if (take > 0) std::memcpy(pr + 2 * ro[r], (const void*)(v.data() + first), (size_t)take * 16);
+        }
+        out->nreq = nreq;
+        out->total_pairs = (i64)fo.total_fin;
+        out->row_off = ro;
+        out->pairs = pr;
+        out->matched = (const i64*)own->p[2];
+        out->_owner = own;
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        own->release();
+        delete own;
+        throw;
+    }
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_filter_result_free(cdb_filter_result* r) {
+    if (!r) return;
+    if (FilterOwner* own = reinterpret_cast<FilterOwner*>(r->_owner)) {
+        own->release();
+        delete own;
+    }
+    std::memset(r, 0, sizeof(*r));
 }
 
 cdb_status cdb_locate_batch_device(const cdb_index* h, const void* d_pat, const int64_t* d_pat_off, int64_t npat,

@@ -192,6 +192,16 @@ __device__ __forceinline__ u64 l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ u64 l2_policy_evict_normal() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_unchanged() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ u64 ld_hint_u64(const u64* p, u64 policy) {
     u64 v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));

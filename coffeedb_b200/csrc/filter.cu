@@ -1,0 +1,835 @@
+// filter() on the device — replaces the set algebra of src/interface.cpp:46-147 for a whole batch of
+// requests, so that only the requested slice of every answer leaves the GPU.
+//
+//   per string key     the keywords of all requests go through ONE batched locate in id order (locate.cu, id_order):
+//                      row = string_index::query(keyword) sorted by id, which is what interface.cpp:82,88 sorts it into
+//   size_kernel        one thread per request: entries to merge, class (small: a warp in shared memory; big: a CTA in
+//                      global scratch; numeric-only: a scan of the column), output allocation
+//   filter_kernel      one warp (or CTA) per request.  The term rows are merged by ranking — every entry finds its place
+//                      with one binary search per other row, ordered by (id, term) — then equal ids are folded: counts
+//                      added (the OR of interface.cpp:89-111 and the AND of :119-133 both add), the set of keys that
+//                      contributed recorded; an id survives when every string key contributed, every numeric key holds it
+//                      inside one of its ranges (numeric_query, src/index.cpp:63-74, as a membership test on the
+//                      id-ordered copy of the column) and the sum passes the $correlation range (:136-142).
+//                      Final order (:143-146): std::sort by descending $correlation is unstable, ties are the rule, and a
+//                      span cuts the result afterwards — so the permutation libstdc++ applies to the id-ascending input
+//                      is reproduced exactly: all sums equal -> a table of that permutation for every length (built once
+//                      with the real std::sort), otherwise lane 0 runs the restated introsort (host/std_sort_order.hpp)
+//                      over 16-bit handles in shared memory.  Then result[span0, span1) is written.
+//   numscan kernels    requests without a string key: ordered compaction of the first numeric key's column.
+//   Requests that do not fit the warp path keep their id-ascending survivors for the caller's one std::sort
+//   (capi.cu: cdb_filter) — VERDICT r1 item 4: "keep that one std::sort on the host over the reduced list".
+// Integer work throughout; bound by the locate underneath it and by the PCIe copy of the slices.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "../host/std_sort_order.hpp"
+#include "filter.cuh"
+#include "locate.cuh"
+#include "primitives.cuh"
+#include "radix_sort.cuh"
+
+namespace cdb {
+
+constexpr int kFCap = 1024;      // entries one warp merges in shared memory; also the longest row of the permutation table
+constexpr int kFMaxTerms = 64;   // terms per request
+constexpr int kFMaxKeys = 32;    // keys per batch (a bit mask per id)
+constexpr int kFWarps = 4;       // requests per CTA on the warp path
+
+// ---- numeric columns ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 num_key(i64 bits, int kind) {
+    const u64 u = (u64)bits;
+    if (kind == 0) return u ^ (1ull << 63);
+    if (u == (1ull << 63)) return 1ull << 63;             // -0.0 == +0.0 for operator<
+    return (u >> 63) ? ~u : (u | (1ull << 63));
+}
+// std::pair<T, int64_t>::operator< on (value key, id)
+__host__ __device__ __forceinline__ bool pair_less(u64 k1, i64 i1, u64 k2, i64 i2) { return k1 < k2 || (k1 == k2 && i1 < i2); }
+
+NumericIndex::~NumericIndex() {
+    if (vkey) cudaFree(vkey);
+    if (vid) cudaFree(vid);
+    if (ikey) cudaFree(ikey);
+    if (iid) cudaFree(iid);
+}
+
+__global__ void numeric_keys_kernel(const i64* __restrict__ ids, const i64* __restrict__ vals, i64 n, int kind,
+                                    u64* __restrict__ idkey, u64* __restrict__ valkey) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        idkey[i] = (u64)ids[i] ^ (1ull << 63);
+        valkey[i] = num_key(vals[i], kind);
+    }
+}
+__global__ void unflip_ids_kernel(const u64* __restrict__ k, i64 n, i64* __restrict__ ids) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = (i64)(k[i] ^ (1ull << 63));
+}
+
+NumericIndex* numeric_create(int kind, const i64* ids, const void* values, i64 n, int device, cudaStream_t st) {
+    std::unique_ptr<NumericIndex> c(new NumericIndex());
+    c->device = device;
+    c->kind = kind;
+    c->n = n;
+    const size_t m = (size_t)(n > 0 ? n : 1);
+    CDB_CUDA(cudaMalloc((void**)&c->vkey, m * 8));
+    CDB_CUDA(cudaMalloc((void**)&c->vid, m * 8));
+    CDB_CUDA(cudaMalloc((void**)&c->ikey, m * 8));
+    CDB_CUDA(cudaMalloc((void**)&c->iid, m * 8));
+    if (n == 0) return c.release();
+    BigBuf<u64> a(m), b(m), va(m), vb(m);
+    BigBuf<i64> raw_ids(m), raw_vals(m);
+    CDB_CUDA(cudaMemcpyAsync(raw_ids.p, ids, m * 8, cudaMemcpyHostToDevice, st));
+    CDB_CUDA(cudaMemcpyAsync(raw_vals.p, values, m * 8, cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)ceil_div(n, 256);
+    numeric_keys_kernel<<<grid, 256, 0, st>>>(raw_ids.p, raw_vals.p, n, kind, a.p, va.p);
+    CDB_LAUNCH_CHECK();
+    // id order: sort (id key, value key) by id ...
+    int cur = rs::radix_sort_pairs<u64>(a.p, b.p, va.p, vb.p, (u64)n, 0, 64, st);
+    u64* idk = cur ? b.p : a.p;
+    u64* vk = cur ? vb.p : va.p;
+    unflip_ids_kernel<<<grid, 256, 0, st>>>(idk, n, c->iid);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaMemcpyAsync(c->ikey, vk, m * 8, cudaMemcpyDeviceToDevice, st));
+    // ... then stably by value: (value, id) order, the reference's std::sort of pairs (src/index.cpp:155-158)
+    u64* idk2 = cur ? a.p : b.p;
+    u64* vk2 = cur ? va.p : vb.p;
+    cur = rs::radix_sort_pairs<u64>(vk, vk2, idk, idk2, (u64)n, 0, 64, st);
+    CDB_CUDA(cudaMemcpyAsync(c->vkey, cur ? vk2 : vk, m * 8, cudaMemcpyDeviceToDevice, st));
+    unflip_ids_kernel<<<grid, 256, 0, st>>>(cur ? idk2 : idk, n, c->vid);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA(cudaStreamSynchronize(st));
+    return c.release();
+}
+
+// first position of the (value, id) order that is not < (k, id): std::lower_bound of src/index.cpp:66-67
+__device__ __forceinline__ i64 vorder_lower_bound(const u64* __restrict__ vkey, const i64* __restrict__ vid, i64 n, u64 k, i64 id) {
+    i64 lo = 0, hi = n;
+    while (lo < hi) {
+        const i64 mid = lo + (hi - lo) / 2;
+        if (pair_less(__ldg(vkey + mid), __ldg(vid + mid), k, id))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void numeric_bounds_kernel(const u64* vkey, const i64* vid, i64 n, u64 lk, i64 lid, u64 hk, i64 hid, i64* out2) {
+    out2[0] = vorder_lower_bound(vkey, vid, n, lk, lid);
+    out2[1] = vorder_lower_bound(vkey, vid, n, hk, hid);
+}
+
+void numeric_bounds(const NumericIndex& c, const i64 lo[2], const i64 hi[2], cudaStream_t st, i64* begin, i64* end) {
+    DevBuf<i64> d(2, st);
+    numeric_bounds_kernel<<<1, 1, 0, st>>>(c.vkey, c.vid, c.n, num_key(lo[0], c.kind), lo[1], num_key(hi[0], c.kind), hi[1], d.p);
+    CDB_LAUNCH_CHECK();
+    i64 h[2];
+    CDB_CUDA(cudaMemcpyAsync(h, d.p, 16, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    *begin = h[0];
+    *end = h[1] > h[0] ? h[1] : h[0];  // an inverted range is empty (std::vector::reserve of a negative size aside)
+}
+
+// ---- the permutation table --------------------------------------------------------------------------------------------
+// pi[n*(n-1)/2 + j] = which element of an id-ascending answer of n equal $correlations std::sort moves to position j.
+static const u16* sort_table(int device, cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<int, u16*> tabs;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = tabs.find(device);
+    if (it != tabs.end()) return it->second;
+    std::vector<u16> h((size_t)kFCap * (kFCap + 1) / 2 + 1);
+    std::vector<std::pair<int64_t, int64_t>> v;
+    for (int n = 1; n <= kFCap; ++n) {
+        v.resize(n);
+        for (int i = 0; i < n; ++i) v[i] = {i, 1};
+        std::sort(v.begin(), v.end(), [](auto x, auto y) { return x.second > y.second; });  // src/interface.cpp:143-146
+        u16* row = h.data() + (size_t)n * (n - 1) / 2;
+        for (int j = 0; j < n; ++j) row[j] = (u16)v[j].first;
+    }
+    u16* d = nullptr;
+    CDB_CUDA(cudaMalloc((void**)&d, h.size() * 2));
+    CDB_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    tabs[device] = d;
+    return d;
+}
+
+// ---- device view of a batch -----------------------------------------------------------------------------------------------
+struct FKeyDev {
+    int kind;  // 0 string, 1 numeric, -1 unknown
+    int nkind; // numeric: 0 int64, 1 double
+    const i64* row_off;  // string: this batch's id-ordered rows
+    const i64* pairs;
+    const u64* vkey;     // numeric
+    const i64* vid;
+    const u64* ikey;
+    const i64* iid;
+    i64 nn;
+};
+struct FArgs {
+    const FKeyDev* keys;
+    int nkeys;
+    const cdb_filter_term* terms;
+    const i64* term_row;  // string terms: row of the keyword inside its key's locate result
+    const i64* ranges;
+    i64 nranges;
+    const i64* req_term_off;
+    i64 nreq;
+    const i64* corr;  // or nullptr
+    const i64* span;  // or nullptr
+    // per request
+    u64* T;        // entries to merge (string terms)
+    u8* cls;       // 0 nothing matches, 1 warp path, 2 CTA path, 3 numeric-only
+    u64* alloc;    // pairs reserved in raw[]
+    u64* tbig;     // scratch entries (CTA path)
+    int* err;      // 1: too many terms / keys, 2: bad key or range index
+    // results
+    const u64* raw_off;
+    i64* raw;
+    u64* raw_len;
+    u64* fin_len;
+    u64* matched;
+    const u16* pi;
+};
+
+enum { CLS_NONE = 0, CLS_WARP = 1, CLS_CTA = 2, CLS_NUM = 3 };
+
+__device__ __forceinline__ void request_span(const FArgs& A, i64 r, u64 n, u64* sb, u64* se) {
+    u64 b = 0, e = n;
+    if (A.span) {
+        const i64 s0 = A.span[2 * r], s1 = A.span[2 * r + 1];
+        b = s0 < 0 ? 0 : (u64)s0;
+        e = s1 < 0 ? 0 : ((u64)s1 < n ? (u64)s1 : n);
+        if (b >= n || e < b) b = e = 0;  // src/interface.cpp:198-200
+    }
+    *sb = b;
+    *se = e;
+}
+
+__global__ void __launch_bounds__(256) size_kernel(FArgs A) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.nreq) return;
+    const i64 t0 = A.req_term_off[r], t1 = A.req_term_off[r + 1];
+    u64 T = 0, numspan = 0;
+    bool dead = t1 <= t0, bad = false;
+    int nstr = 0, firstnum = -1;
+    if (t1 - t0 > kFMaxTerms) {
+        atomicExch(A.err, 1);
+        bad = true;
+    }
+    for (i64 t = t0; t < t1 && !bad; ++t) {
+        const int k = A.terms[t].key;
+        if (k < 0 || k >= A.nkeys) {
+            atomicExch(A.err, 2);
+            bad = true;
+            break;
+        }
+        const FKeyDev& K = A.keys[k];
+        if (K.kind < 0) {
+            dead = true;
+        } else if (K.kind == 0) {
+            const i64 row = A.term_row[t];
+            T += (u64)(K.row_off[row + 1] - K.row_off[row]);
+            ++nstr;
+        } else {
+            const int g = A.terms[t].range;
+            if (g < 0 || g >= A.nranges) {
+                atomicExch(A.err, 2);
+                bad = true;
+                break;
+            }
+            if (firstnum < 0) firstnum = k;
+            if (k == firstnum) {
+                const i64* R = A.ranges + 4 * (i64)g;
+                const i64 b = vorder_lower_bound(K.vkey, K.vid, K.nn, num_key(R[0], K.nkind), R[1]);
+                const i64 e = vorder_lower_bound(K.vkey, K.vid, K.nn, num_key(R[2], K.nkind), R[3]);
+                if (e > b) numspan += (u64)(e - b);
+            }
+        }
+    }
+    u8 cls = CLS_NONE;
+    u64 alloc = 0, tbig = 0;
+    if (!dead && !bad) {
+        if (nstr == 0) {
+            cls = CLS_NUM;
+            const u64 nn = (u64)A.keys[firstnum].nn;
+            alloc = numspan < nn ? numspan : nn;
+        } else if (T <= (u64)kFCap) {
+            cls = CLS_WARP;
+            u64 sb, se;
+            request_span(A, r, T, &sb, &se);
+            alloc = se - sb;
+        } else {
+            cls = CLS_CTA;
+            alloc = T;
+            tbig = T;
+        }
+    }
+    A.T[r] = T;
+    A.cls[r] = cls;
+    A.alloc[r] = alloc;
+    A.tbig[r] = tbig;
+}
+
+// ---- the merge ------------------------------------------------------------------------------------------------------
+struct TermMeta {
+    int nstr, K, nnum;
+    u64 base[kFMaxTerms + 1];      // start of every string term's entries in the concatenation
+    const i64* row[kFMaxTerms];    // its (id, count) pairs
+    u8 ks[kFMaxTerms];             // ordinal of its key among the request's string keys
+    int numkey[kFMaxKeys];         // numeric key slots of the request
+};
+
+template <bool BIG>
+struct Grp {
+    static constexpr int NT = BIG ? 256 : 32;
+    __device__ static __forceinline__ int tid() { return BIG ? (int)threadIdx.x : (int)(threadIdx.x & 31); }
+    __device__ static __forceinline__ void sync() {
+        if (BIG)
+            __syncthreads();
+        else
+            __syncwarp();
+    }
+    // exclusive scan of one value per thread over the group; *total = sum.  ws: 8 ints of shared memory (BIG only)
+    __device__ static __forceinline__ int excl_scan(int v, int* total, int* ws) {
+        const int lane = threadIdx.x & 31;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (!BIG) {
+            *total = __shfl_sync(0xffffffffu, incl, 31);
+            return incl - v;
+        }
+        const int warp = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int s = ws[w];
+            if (w < warp) woff += s;
+            tot += s;
+        }
+        *total = tot;
+        return woff + incl - v;
+    }
+};
+
+// does every numeric key of the request hold `id` inside one of its ranges?  (skip: a key already tested by the caller)
+__device__ __forceinline__ bool numeric_ok(const FArgs& A, const TermMeta& tm, i64 t0, i64 t1, i64 id, int skip) {
+    for (int j = 0; j < tm.nnum; ++j) {
+        const int k = tm.numkey[j];
+        if (k == skip) continue;
+        const FKeyDev& K = A.keys[k];
+        i64 lo = 0, hi = K.nn;
+        while (lo < hi) {
+            const i64 mid = lo + (hi - lo) / 2;
+            if (__ldg(K.iid + mid) < id)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo >= K.nn || __ldg(K.iid + lo) != id) return false;
+        const u64 kv = __ldg(K.ikey + lo);
+        bool ok = false;
+        for (i64 t = t0; t < t1 && !ok; ++t) {
+            if (A.terms[t].key != k) continue;
+            const i64* R = A.ranges + 4 * (i64)A.terms[t].range;
+            ok = !pair_less(kv, id, num_key(R[0], K.nkind), R[1]) && pair_less(kv, id, num_key(R[2], K.nkind), R[3]);
+        }
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// thread 0 of the group fills tm from the request's terms
+__device__ __forceinline__ void fill_meta(const FArgs& A, i64 t0, i64 t1, TermMeta& tm) {
+    int keyslot[kFMaxKeys];
+    int K = 0, nstr = 0, nnum = 0;
+    u64 base = 0;
+    for (i64 t = t0; t < t1; ++t) {
+        const int k = A.terms[t].key;
+        const FKeyDev& F = A.keys[k];
+        if (F.kind == 0) {
+            int o = 0;
+            while (o < K && keyslot[o] != k) ++o;
+            if (o == K) keyslot[K++] = k;
+            const i64 row = A.term_row[t];
+            tm.base[nstr] = base;
+            tm.row[nstr] = F.pairs + 2 * F.row_off[row];
+            tm.ks[nstr] = (u8)o;
+            base += (u64)(F.row_off[row + 1] - F.row_off[row]);
+            ++nstr;
+        } else if (F.kind == 1) {
+            int o = 0;
+            while (o < nnum && tm.numkey[o] != k) ++o;
+            if (o == nnum) tm.numkey[nnum++] = k;
+        }
+    }
+    tm.base[nstr] = base;
+    tm.nstr = nstr;
+    tm.K = K;
+    tm.nnum = nnum;
+}
+
+template <bool BIG, typename CntT>
+__device__ __forceinline__ void filter_request(const FArgs& A, i64 r, i64* key, CntT* cnt, u8* ks, u16* perm, TermMeta& tm, int* ws) {
+    typedef Grp<BIG> G;
+    const int tid = G::tid();
+    const i64 t0 = A.req_term_off[r], t1 = A.req_term_off[r + 1];
+    if (tid == 0) fill_meta(A, t0, t1, tm);
+    G::sync();
+    const u64 T = tm.base[tm.nstr];
+    const int nstr = tm.nstr;
+    // ---- merge by ranking: entry (term j, index i) goes to i + sum over the other terms of the entries ordered before it
+    for (u64 e = tid; e < T; e += G::NT) {
+        int j = 0;
+        while (e >= tm.base[j + 1]) ++j;
+        const u64 i = e - tm.base[j];
+        const longlong2 v = *reinterpret_cast<const longlong2*>(tm.row[j] + 2 * i);
+        u64 pos = i;
+        for (int b = 0; b < nstr; ++b) {
+            if (b == j) continue;
+            const i64* rb = tm.row[b];
+            u64 lo = 0, hi = tm.base[b + 1] - tm.base[b];
+            while (lo < hi) {  // b < j: entries with id <= v.x come first; b > j: entries with id < v.x
+                const u64 mid = lo + (hi - lo) / 2;
+                const i64 x = __ldg(rb + 2 * mid);
+                if (x < v.x || (b < j && x == v.x))
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            pos += lo;
+        }
+        key[pos] = v.x;
+        cnt[pos] = (CntT)v.y;
+        ks[pos] = tm.ks[j];
+    }
+    G::sync();
+    // ---- fold equal ids, test the keys, compact in place (a survivor never moves to a higher index)
+    i64 cL = 0, cR = 0;
+    const bool has_corr = A.corr != nullptr;
+    if (has_corr) {
+        cL = A.corr[2 * r];
+        cR = A.corr[2 * r + 1];
+    }
+    u64 n = 0;
+    for (u64 base = 0; base < T; base += G::NT) {
+        const u64 i = base + tid;
+        bool keep = false;
+        i64 id = 0, sum = 0;
+        if (i < T) {
+            id = key[i];
+            if (i == 0 || key[i - 1] != id) {
+                u32 mask = 0;
+                for (u64 j = i; j < T && key[j] == id; ++j) {
+                    sum += (i64)cnt[j];
+                    mask |= 1u << ks[j];
+                }
+                keep = __popc(mask) == tm.K;
+                if (keep && has_corr) keep = sum >= cL && sum < cR;
+                if (keep && tm.nnum) keep = numeric_ok(A, tm, t0, t1, id, -1);
+            }
+        }
+        int total;
+        const int pos = G::excl_scan(keep ? 1 : 0, &total, ws);
+        G::sync();
+        if (keep) {
+            key[n + pos] = id;
+            cnt[n + pos] = (CntT)sum;
+        }
+        G::sync();
+        n += (u64)total;
+    }
+    // ---- final order and span
+    u64 sb, se;
+    request_span(A, r, n, &sb, &se);
+    i64* out = A.raw + 2 * A.raw_off[r];
+    if (tid == 0) {
+        A.matched[r] = n;
+        A.fin_len[r] = se - sb;
+    }
+    if (BIG) {  // the caller runs the one std::sort over these survivors
+        for (u64 i = tid; i < n; i += G::NT) *reinterpret_cast<longlong2*>(out + 2 * i) = make_longlong2(key[i], (i64)cnt[i]);
+        if (tid == 0) A.raw_len[r] = n;
+        return;
+    }
+    if (tid == 0) A.raw_len[r] = se - sb;
+    if (se <= sb) return;
+    CntT mn = ~(CntT)0, mx = 0;
+    for (u64 i = tid; i < n; i += G::NT) {
+        const CntT c = cnt[i];
+        mn = c < mn ? c : mn;
+        mx = c > mx ? c : mx;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const CntT a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (mn == mx) {
+        const u16* src = A.pi + n * (n - 1) / 2;
+        for (u64 j = sb + tid; j < se; j += G::NT) {
+            const u16 s = src[j];
+            *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = make_longlong2(key[s], (i64)cnt[s]);
+        }
+    } else {
+        for (u64 i = tid; i < n; i += G::NT) perm[i] = (u16)i;
+        G::sync();
+        if (tid == 0)
+            coffeedb_b200::sort_order::std_sort_order(perm, (int)n, [cnt](u16 a, u16 b) { return cnt[a] > cnt[b]; });
+        G::sync();
+        for (u64 j = sb + tid; j < se; j += G::NT) {
+            const u16 s = perm[j];
+            *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = make_longlong2(key[s], (i64)cnt[s]);
+        }
+    }
+}
+
+struct WarpScratch {
+    i64 key[kFCap];
+    u32 cnt[kFCap];
+    u16 perm[kFCap];
+    u8 ks[kFCap];
+    TermMeta tm;
+};
+
+__global__ void __launch_bounds__(kFWarps * 32) filter_warp_kernel(FArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const i64 r = (i64)blockIdx.x * kFWarps + warp;
+    if (r >= A.nreq) return;
+    const u8 cls = A.cls[r];
+    if (cls == CLS_NONE) {
+        if ((threadIdx.x & 31) == 0) {
+            A.matched[r] = 0;
+            A.fin_len[r] = 0;
+            A.raw_len[r] = 0;
+        }
+        return;
+    }
+    if (cls != CLS_WARP) return;
+    WarpScratch& s = reinterpret_cast<WarpScratch*>(smem_raw)[warp];
+    filter_request<false, u32>(A, r, s.key, s.cnt, s.ks, s.perm, s.tm, nullptr);
+}
+
+__global__ void __launch_bounds__(256) filter_cta_kernel(FArgs A, const i64* __restrict__ list, const u64* __restrict__ scr_off,
+                                                         i64* scr_key, i64* scr_cnt, u8* scr_ks) {
+    __shared__ TermMeta tm;
+    __shared__ int ws[8];
+    const i64 r = list[blockIdx.x];
+    const u64 o = scr_off[r];
+    filter_request<true, i64>(A, r, scr_key + o, scr_cnt + o, scr_ks + o, nullptr, tm, ws);
+}
+
+// ---- requests without a string key: ordered compaction of the first numeric key's column (id order) ---------------------
+constexpr int kNsIpt = 8;
+constexpr int kNsTile = 256 * kNsIpt;
+
+__device__ __forceinline__ bool numscan_pass(const FArgs& A, const TermMeta& tm, i64 t0, i64 t1, int k0, i64 i) {
+    const FKeyDev& K = A.keys[k0];
+    const i64 id = K.iid[i];
+    const u64 kv = K.ikey[i];
+    bool ok = false;
+    for (i64 t = t0; t < t1 && !ok; ++t) {
+        if (A.terms[t].key != k0) continue;
+        const i64* R = A.ranges + 4 * (i64)A.terms[t].range;
+        ok = !pair_less(kv, id, num_key(R[0], K.nkind), R[1]) && pair_less(kv, id, num_key(R[2], K.nkind), R[3]);
+    }
+    if (ok && tm.nnum > 1) ok = numeric_ok(A, tm, t0, t1, id, k0);
+    return ok;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) numscan_kernel(FArgs A, i64 r, u64* __restrict__ blk) {
+    __shared__ TermMeta tm;
+    __shared__ u64 wsum[32];
+    const i64 t0 = A.req_term_off[r], t1 = A.req_term_off[r + 1];
+    if (threadIdx.x == 0) fill_meta(A, t0, t1, tm);
+    __syncthreads();
+    const int k0 = A.terms[t0].key;  // CLS_NUM: every term is numeric; the first one names the scanned column
+    const i64 nn = A.keys[k0].nn;
+    bool corr_ok = true;
+    if (A.corr) corr_ok = 0 >= A.corr[2 * r] && 0 < A.corr[2 * r + 1];  // every $correlation is 0 (src/index.cpp:71)
+    const i64 first = (i64)blockIdx.x * kNsTile + (i64)threadIdx.x * kNsIpt;
+    bool pass[kNsIpt];
+    u64 c = 0;
+#pragma unroll
+    for (int u = 0; u < kNsIpt; ++u) {
+        const i64 i = first + u;
+        pass[u] = corr_ok && i < nn && numscan_pass(A, tm, t0, t1, k0, i);
+        c += pass[u] ? 1 : 0;
+    }
+    u64 tot;
+    u64 ex = prim::block_exclusive_scan_u64(c, &tot, wsum);
+    if (!EMIT) {
+        if (threadIdx.x == 0) blk[blockIdx.x] = tot;
+        return;
+    }
+    i64* out = A.raw + 2 * (A.raw_off[r] + blk[blockIdx.x] + ex);
+#pragma unroll
+    for (int u = 0; u < kNsIpt; ++u) {
+        if (pass[u]) {
+            *reinterpret_cast<longlong2*>(out) = make_longlong2(A.keys[k0].iid[first + u], 0);
+            out += 2;
+        }
+    }
+}
+
+__global__ void numscan_finish_kernel(FArgs A, i64 r, const u64* __restrict__ total) {
+    const u64 n = *total;
+    u64 sb, se;
+    request_span(A, r, n, &sb, &se);
+    A.matched[r] = n;
+    A.raw_len[r] = n;
+    A.fin_len[r] = se - sb;
+}
+
+// ---- per string key: the keywords of its terms as one locate batch ------------------------------------------------------
+__global__ void key_terms_kernel(const cdb_filter_term* __restrict__ terms, i64 nterm, int k, u64* __restrict__ isk, u64* __restrict__ len) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nterm) return;
+    const bool mine = terms[t].key == k;
+    const i64 l = terms[t].kw_end - terms[t].kw_begin;
+    isk[t] = mine ? 1 : 0;
+    len[t] = mine && l > 0 ? (u64)l : 0;  // an empty keyword stays empty: the search reports it (src/index.cpp:239-241)
+}
+__global__ void key_pack_kernel(const cdb_filter_term* __restrict__ terms, i64 nterm, int k, const u64* __restrict__ rowidx,
+                                const u64* __restrict__ boff, const u8* __restrict__ kw, i64 kw_len, u8* __restrict__ pat,
+                                i64* __restrict__ poff, i64* __restrict__ term_row, int* __restrict__ err) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nterm || terms[t].key != k) return;
+    const u64 row = rowidx[t];
+    poff[row] = (i64)boff[t];
+    term_row[t] = (i64)row;
+    const i64 b = terms[t].kw_begin, e = terms[t].kw_end;
+    if (e > b && (b < 0 || e > kw_len)) {
+        atomicExch(err, 2);
+        return;
+    }
+    for (i64 i = b; i < e; ++i) pat[boff[t] + (u64)(i - b)] = kw[i];
+}
+
+// copies the finished rows (warp path) from their reserved slots into the compact result; pending rows keep their holes
+__global__ void __launch_bounds__(256) compact_kernel(FArgs A, const u64* __restrict__ fin_off, i64* __restrict__ fin) {
+    const int lane = threadIdx.x & 31;
+    const i64 r = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= A.nreq || A.cls[r] != CLS_WARP) return;
+    const u64 n = fin_off[r + 1] - fin_off[r];
+    const longlong2* src = reinterpret_cast<const longlong2*>(A.raw + 2 * A.raw_off[r]);
+    longlong2* dst = reinterpret_cast<longlong2*>(fin + 2 * fin_off[r]);
+    for (u64 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+int filter_device_of(const cdb_filter_batch& b) {
+    int dev = -1;
+    for (int k = 0; k < b.nkeys; ++k) {
+        int d = -1;
+        if (b.keys[k].kind == 0 && b.keys[k].index) d = reinterpret_cast<const Index*>(b.keys[k].index)->device;
+        if (b.keys[k].kind == 1 && b.keys[k].index) d = reinterpret_cast<const NumericIndex*>(b.keys[k].index)->device;
+        if (d < 0) continue;
+        if (dev >= 0 && d != dev) throw Error(CDB_ERR_ARG, "cdb_filter: the keys of a batch must live on one device");
+        dev = d;
+    }
+    return dev;
+}
+
+void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& o) {
+    const i64 nreq = b.nreq;
+    const i64 nterm = nreq ? b.req_term_off[nreq] - b.req_term_off[0] : 0;
+    if (b.nkeys < 0 || b.nkeys > kFMaxKeys) throw Error(CDB_ERR_ARG, "cdb_filter: at most 32 keys per batch");
+    if (nreq && b.req_term_off[0] != 0) throw Error(CDB_ERR_ARG, "cdb_filter: req_term_off[0] must be 0");
+    o.nreq = nreq;
+    o.pending.clear();
+    o.fin_off.alloc((size_t)nreq + 1, st);
+    o.matched.alloc((size_t)nreq, st);
+    o.raw_off.alloc((size_t)nreq + 1, st);
+    o.raw_len.alloc((size_t)nreq, st);
+    if (nreq == 0) {
+        CDB_CUDA(cudaMemsetAsync(o.fin_off.p, 0, 8, st));
+        CDB_CUDA(cudaMemsetAsync(o.raw_off.p, 0, 8, st));
+        o.total_fin = 0;
+        CDB_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    // ---- the batch on the device
+    DevBuf<cdb_filter_term> d_terms((size_t)nterm, st);
+    DevBuf<i64> d_rto((size_t)nreq + 1, st), d_ranges((size_t)b.nranges * 4, st), d_corr, d_span, d_term_row((size_t)nterm, st);
+    DevBuf<u8> d_kw((size_t)b.kw_len + 8, st);
+    if (nterm) CDB_CUDA(cudaMemcpyAsync(d_terms.p, b.terms, (size_t)nterm * sizeof(cdb_filter_term), cudaMemcpyHostToDevice, st));
+    CDB_CUDA(cudaMemcpyAsync(d_rto.p, b.req_term_off, (size_t)(nreq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (b.nranges) CDB_CUDA(cudaMemcpyAsync(d_ranges.p, b.ranges, (size_t)b.nranges * 32, cudaMemcpyHostToDevice, st));
+    if (b.kw_len) CDB_CUDA(cudaMemcpyAsync(d_kw.p, b.kw, (size_t)b.kw_len, cudaMemcpyHostToDevice, st));
+    if (b.corr_range) {
+        d_corr.alloc((size_t)nreq * 2, st);
+        CDB_CUDA(cudaMemcpyAsync(d_corr.p, b.corr_range, (size_t)nreq * 16, cudaMemcpyHostToDevice, st));
+    }
+    if (b.span) {
+        d_span.alloc((size_t)nreq * 2, st);
+        CDB_CUDA(cudaMemcpyAsync(d_span.p, b.span, (size_t)nreq * 16, cudaMemcpyHostToDevice, st));
+    }
+    CDB_CUDA(cudaMemsetAsync(d_term_row.p, 0, d_term_row.bytes(), st));
+    DevBuf<int> d_err(1, st);
+    CDB_CUDA(cudaMemsetAsync(d_err.p, 0, 4, st));
+    // ---- one id-ordered locate per string key
+    std::vector<FKeyDev> hkeys((size_t)std::max(b.nkeys, 1));
+    std::vector<cdb_device_result> results((size_t)b.nkeys);
+    for (auto& r : results) std::memset(&r, 0, sizeof(r));
+    auto free_results = [&] {
+        for (auto& r : results) cdb_device_result_free(&r);
+    };
+    try {
+        const unsigned tgrid = (unsigned)ceil_div(nterm > 0 ? nterm : 1, 256);
+        for (int k = 0; k < b.nkeys; ++k) {
+            FKeyDev& F = hkeys[k];
+            std::memset(&F, 0, sizeof(F));
+            F.kind = b.keys[k].index ? b.keys[k].kind : -1;
+            if (F.kind == 1) {
+                const NumericIndex* c = reinterpret_cast<const NumericIndex*>(b.keys[k].index);
+                F.nkind = c->kind;
+                F.vkey = c->vkey;
+                F.vid = c->vid;
+                F.ikey = c->ikey;
+                F.iid = c->iid;
+                F.nn = c->n;
+            } else if (F.kind == 0) {
+                const Index* ix = reinterpret_cast<const Index*>(b.keys[k].index);
+                if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+                DevBuf<u64> isk((size_t)nterm + 1, st), len((size_t)nterm + 1, st);
+                key_terms_kernel<<<tgrid, 256, 0, st>>>(d_terms.p, nterm, k, isk.p, len.p);
+                CDB_LAUNCH_CHECK();
+                prim::exclusive_scan<u64>(isk.p, isk.p, (u64)nterm, st);
+                prim::exclusive_scan<u64>(len.p, len.p, (u64)nterm, st);
+                u64 h2[2];
+                CDB_CUDA(cudaMemcpyAsync(&h2[0], isk.p + nterm, 8, cudaMemcpyDeviceToHost, st));
+                CDB_CUDA(cudaMemcpyAsync(&h2[1], len.p + nterm, 8, cudaMemcpyDeviceToHost, st));
+                CDB_CUDA(cudaStreamSynchronize(st));
+                const i64 nkw = (i64)h2[0];
+                if (nkw == 0) {
+                    F.kind = -2;  // a string key no term names: never dereferenced
+                    continue;
+                }
+                DevBuf<u8> pat((size_t)h2[1] + 8, st);
+                DevBuf<i64> poff((size_t)nkw + 1, st);
+                key_pack_kernel<<<tgrid, 256, 0, st>>>(d_terms.p, nterm, k, isk.p, len.p, d_kw.p, b.kw_len, pat.p, poff.p, d_term_row.p,
+                                                       d_err.p);
+                CDB_LAUNCH_CHECK();
+                CDB_CUDA(cudaMemcpyAsync(poff.p + nkw, len.p + nterm, 8, cudaMemcpyDeviceToDevice, st));
+                locate_device(*ix, pat.p, poff.p, nkw, st, &results[k], /*id_order=*/true);  // throws on an empty keyword
+                F.row_off = results[k].row_off;
+                F.pairs = results[k].pairs;
+            }
+        }
+        DevBuf<FKeyDev> d_keys(hkeys.size(), st);
+        CDB_CUDA(cudaMemcpyAsync(d_keys.p, hkeys.data(), hkeys.size() * sizeof(FKeyDev), cudaMemcpyHostToDevice, st));
+        // ---- sizes and classes
+        DevBuf<u64> d_T((size_t)nreq, st), d_alloc((size_t)nreq + 1, st), d_tbig((size_t)nreq + 1, st), d_fin_len((size_t)nreq + 1, st);
+        DevBuf<u8> d_cls((size_t)nreq, st);
+        FArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.keys = d_keys.p;
+        A.nkeys = b.nkeys;
+        A.terms = d_terms.p;
+        A.term_row = d_term_row.p;
+        A.ranges = d_ranges.p;
+        A.nranges = b.nranges;
+        A.req_term_off = d_rto.p;
+        A.nreq = nreq;
+        A.corr = b.corr_range ? d_corr.p : nullptr;
+        A.span = b.span ? d_span.p : nullptr;
+        A.T = d_T.p;
+        A.cls = d_cls.p;
+        A.alloc = d_alloc.p;
+        A.tbig = d_tbig.p;
+        A.err = d_err.p;
+        const unsigned rgrid = (unsigned)ceil_div(nreq, 256);
+        size_kernel<<<rgrid, 256, 0, st>>>(A);
+        CDB_LAUNCH_CHECK();
+        prim::exclusive_scan<u64>(d_alloc.p, o.raw_off.p, (u64)nreq, st);
+        prim::exclusive_scan<u64>(d_tbig.p, d_tbig.p, (u64)nreq, st);
+        std::vector<u8> hcls((size_t)nreq);
+        u64 tot[2];
+        int herr = 0;
+        CDB_CUDA(cudaMemcpyAsync(hcls.data(), d_cls.p, (size_t)nreq, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaMemcpyAsync(&tot[0], o.raw_off.p + nreq, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaMemcpyAsync(&tot[1], d_tbig.p + nreq, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        if (herr == 1) throw Error(CDB_ERR_ARG, "cdb_filter: a request has more than 64 terms");
+        if (herr) throw Error(CDB_ERR_ARG, "cdb_filter: a term names a key, range or keyword outside the batch");
+        std::vector<i64> big, num;
+        for (i64 r = 0; r < nreq; ++r) {
+            if (hcls[r] == CLS_CTA) big.push_back(r);
+            if (hcls[r] == CLS_NUM) num.push_back(r);
+        }
+        o.raw.alloc((size_t)tot[0] * 2, st);
+        A.raw_off = o.raw_off.p;
+        A.raw = o.raw.p;
+        A.raw_len = o.raw_len.p;
+        A.fin_len = d_fin_len.p;
+        A.matched = o.matched.p;
+        A.pi = sort_table(filter_device_of(b), st);
+        // ---- the merges
+        {
+            const size_t smem = sizeof(WarpScratch) * kFWarps;
+            CDB_CUDA(cudaFuncSetAttribute(filter_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            filter_warp_kernel<<<(unsigned)ceil_div(nreq, kFWarps), kFWarps * 32, smem, st>>>(A);
+            CDB_LAUNCH_CHECK();
+        }
+        DevBuf<i64> d_big, scr_key, scr_cnt;
+        DevBuf<u8> scr_ks;
+        if (!big.empty()) {
+            d_big.alloc(big.size(), st);
+            scr_key.alloc((size_t)tot[1], st);
+            scr_cnt.alloc((size_t)tot[1], st);
+            scr_ks.alloc((size_t)tot[1], st);
+            CDB_CUDA(cudaMemcpyAsync(d_big.p, big.data(), big.size() * 8, cudaMemcpyHostToDevice, st));
+            filter_cta_kernel<<<(unsigned)big.size(), 256, 0, st>>>(A, d_big.p, d_tbig.p, scr_key.p, scr_cnt.p, scr_ks.p);
+            CDB_LAUNCH_CHECK();
+        }
+        for (i64 r : num) {
+            const int k0 = b.terms[b.req_term_off[r]].key;
+            const i64 nn = hkeys[k0].nn;
+            const u64 nb = (u64)ceil_div(nn > 0 ? nn : 1, kNsTile);
+            DevBuf<u64> blk((size_t)nb + 1, st);
+            numscan_kernel<false><<<(unsigned)nb, 256, 0, st>>>(A, r, blk.p);
+            CDB_LAUNCH_CHECK();
+            prim::scan_blocksums_kernel<<<1, 1024, 0, st>>>(blk.p, nb);
+            CDB_LAUNCH_CHECK();
+            numscan_kernel<true><<<(unsigned)nb, 256, 0, st>>>(A, r, blk.p);
+            CDB_LAUNCH_CHECK();
+            numscan_finish_kernel<<<1, 1, 0, st>>>(A, r, blk.p + nb);
+            CDB_LAUNCH_CHECK();
+        }
+        // ---- compact result: finished rows move to their final place, pending rows (CTA path, numeric-only) keep a hole
+        prim::exclusive_scan<u64>(d_fin_len.p, o.fin_off.p, (u64)nreq, st);
+        CDB_CUDA(cudaMemcpyAsync(&o.total_fin, o.fin_off.p + nreq, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));  // also: big / hcls stay alive until their uploads are done
+        o.fin.alloc((size_t)o.total_fin * 2, st);
+        compact_kernel<<<(unsigned)ceil_div(nreq * 32, 256), 256, 0, st>>>(A, o.fin_off.p, o.fin.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaStreamSynchronize(st));  // the temporaries of this call go back to the pool after their last use
+        o.pending = big;
+        o.pending.insert(o.pending.end(), num.begin(), num.end());
+        std::sort(o.pending.begin(), o.pending.end());
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        free_results();
+        throw;
+    }
+    free_results();
+}
+
+}  // namespace cdb

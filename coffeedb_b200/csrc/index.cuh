@@ -55,6 +55,14 @@ struct Index {
     double build_ms = 0, sort_ms = 0;
     i64 rounds = 0, chunks = 0;
     bool loaded_from_file = false;  // the last build read a saved array instead of sorting (cdb_build_or_load)
+    // Id order of the documents, for filter() (src/interface.cpp:79-135 merges rows sorted by id; string_index::query
+    // reports them in doc order).  ids_order: -1 not examined yet, 1 = ids ascend with the doc index (doc order IS id order),
+    // 0 = they do not: rank_tab[doc] = rank of the document's id among all ids, ids_by_rank[rank] = that id.  Filled on
+    // the first id-ordered locate (locate.cu: id_order_tables), under order_mu.
+    mutable std::mutex order_mu;
+    mutable int ids_order = -1;
+    mutable u32* d_rank_tab = nullptr;
+    mutable i64* d_ids_by_rank = nullptr;
     // cdb_query's coalescing queue (capi.cu), created on first use
     mutable std::mutex batcher_mu;
     mutable std::shared_ptr<void> batcher;

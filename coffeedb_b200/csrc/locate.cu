@@ -497,7 +497,8 @@ __device__ __forceinline__ bool warp_bucket_sort(u32 (&x)[R], int occ, u32 bucke
 // pad_idx.  Returns nheads; all_distinct tells that every run has length 1 (s_pos is then not written).
 template <typename SAT, int R>
 __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32 bucket_mul,
-                                             u32* s_doc, u32* s_pos, int lane, bool& all_distinct) {
+                                             u32* s_doc, u32* s_pos, int lane, bool& all_distinct,
+                                             const u32* __restrict__ remap = nullptr) {
     SAT v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -509,6 +510,11 @@ __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, 
     for (int r = 0; r < R; ++r) {
         const int i = r * 32 + lane;
         x[r] = i < occ ? (u32)((u64)v[r] & mask) : 0xffffffffu;  // doc index <= 2^32-2 (bits1 <= 32)
+    }
+    if (remap) {  // id order: sort by the rank of the document's id (a bijection, so runs of equal keys are the same runs)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r * 32 + lane < occ) x[r] = __ldg(remap + x[r]);
     }
     // s_doc / s_pos double as the sorts' scratch (33*R words each) before they are filled
     bool sorted = false;
@@ -577,7 +583,7 @@ constexpr size_t warp_smem_bytes() {
 // MAXR = 32: intervals up to kWarpCap, 3 CTAs per SM.  MAXR = 4: batches whose longest warp-path interval is <= 128
 // occurrences (short rows: sharded corpora, long keywords) — the same code with the long sorting networks compiled
 // out, half the registers and a tenth of the shared memory, so twice as many warps per SM hide the latency.
-template <typename SAT, int MAXR>
+template <typename SAT, int MAXR, bool REMAP>
 __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5 : MAXR == 16 ? 4 : 3) gather_kernel(const SAT* __restrict__ sa, u64 mask,
                                                                                     u32 bucket_mul,
                                                                                     const i64* __restrict__ left,
@@ -588,7 +594,8 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5
                                                                                     u32* __restrict__ cdocs,
                                                                                     u16* __restrict__ ccnt,
                                                                                     u16* __restrict__ seg, int nranges,
-                                                                                    int rshift) {
+                                                                                    int rshift, const u32* __restrict__ remap_arg) {
+    const u32* const remap = REMAP ? remap_arg : nullptr;  // compiled out of the doc-order kernel (its register budget is tight)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 q = (i64)blockIdx.x * kTileWarps + warp;
@@ -604,12 +611,12 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5
         d = dlarge[q];
     } else if (occ64 > 0) {
         const int occ = (int)occ64;
-        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
-        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
-        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
-        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct);
+        if (occ <= 32) nheads = load_sort_rle<SAT, 1>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
+        else if (occ <= 64) nheads = load_sort_rle<SAT, 2>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
+        else if (MAXR <= 4 || occ <= 128) nheads = load_sort_rle<SAT, 4>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
+        else if (occ <= 256) nheads = load_sort_rle<SAT, (MAXR >= 8 ? 8 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
+        else if (occ <= 512) nheads = load_sort_rle<SAT, (MAXR >= 16 ? 16 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
+        else nheads = load_sort_rle<SAT, (MAXR >= 32 ? 32 : 4)>(sa, l, occ, mask, bucket_mul, s_doc, s_pos, lane, all_distinct, remap);
         d = (u64)nheads;
     }
     if (lane == 0) rowlen[q] = d;
@@ -695,14 +702,16 @@ __global__ void __launch_bounds__(kTrWarps * 32) translate_kernel(const u32* __r
                                                                   const u64* __restrict__ row_off,
                                                                   const u16* __restrict__ seg,
                                                                   const i64* __restrict__ ids, i64* __restrict__ pairs,
-                                                                  i64 npat, int nranges, unsigned long long* ticket) {
+                                                                  i64 npat, int nranges, unsigned long long* ticket,
+                                                                  int keep_mode) {
     __shared__ u32 s_excl[kTrWarps][32];
     __shared__ u64 s_in[kTrWarps][32];   // compact rows sit at alloc_off (upper-bound offsets) ...
     __shared__ u64 s_out[kTrWarps][32];  // ... the result rows at row_off (exact CSR offsets)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 ntile = (npat + 31) >> 5;
     const i64 nitems = ntile * nranges;
-    const u64 pol_keep = l2_policy_evict_last();
+    // keep_mode (CDB_TRANSLATE_KEEP): priority of the ids[] slice in L2 — 0 evict_last, 1 evict_normal, 2 evict_unchanged
+    const u64 pol_keep = keep_mode == 1 ? l2_policy_evict_normal() : keep_mode == 2 ? l2_policy_evict_unchanged() : l2_policy_evict_last();
     const u64 pol_stream = l2_policy_evict_first();
     // Items are handed out through one global ticket, in order: at any moment all warps of the grid are within a few
     // thousand items of each other, i.e. inside one (at a range change: two) slices of ids[].  A static item
@@ -758,7 +767,7 @@ __global__ void large_occ_kernel(const u32* __restrict__ list, u64 nl, const i64
 template <typename SAT>
 __global__ void large_expand_kernel(const SAT* __restrict__ sa, u64 mask, const u32* __restrict__ list, u64 nl,
                                     const i64* __restrict__ left, const u64* __restrict__ ooff, u64 total,
-                                    u64* __restrict__ keys) {
+                                    u64* __restrict__ keys, const u32* __restrict__ remap) {
     for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
         u64 lo = 0, hi = nl - 1;  // largest j with ooff[j] <= e
         while (lo < hi) {
@@ -769,7 +778,8 @@ __global__ void large_expand_kernel(const SAT* __restrict__ sa, u64 mask, const 
                 hi = mid - 1;
         }
         const u64 i = (u64)left[list[lo]] + (e - __ldg(ooff + lo));
-        keys[e] = (lo << 32) | ((u64)sa[i] & mask);
+        const u64 doc = (u64)sa[i] & mask;
+        keys[e] = (lo << 32) | (remap ? (u64)__ldg(remap + doc) : doc);
     }
 }
 
@@ -854,11 +864,71 @@ static void scan_in_place(u64* a, u64 n, cudaStream_t st) {
     }
 }
 
+// ---- id order (filter) --------------------------------------------------------------------------------------------
+__global__ void ids_descent_kernel(const i64* __restrict__ ids, i64 nd, int* __restrict__ flag) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < nd && ids[i] >= ids[i + 1]) *flag = 1;
+}
+__global__ void rank_keys_kernel(const i64* __restrict__ ids, i64 nd, u64* __restrict__ keys, u32* __restrict__ docs) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nd) {
+        keys[i] = (u64)ids[i] ^ (1ull << 63);  // signed order as unsigned
+        docs[i] = (u32)i;
+    }
+}
+__global__ void rank_scatter_kernel(const u64* __restrict__ keys, const u32* __restrict__ docs, i64 nd,
+                                    u32* __restrict__ rank_tab, i64* __restrict__ ids_by_rank) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nd) {
+        rank_tab[docs[r]] = (u32)r;
+        ids_by_rank[r] = (i64)(keys[r] ^ (1ull << 63));
+    }
+}
+
+// Examines the ids once per built index.  Returns true when the rows have to be re-keyed (ids do not ascend with the
+// doc index): rank_tab / ids_by_rank are then filled.  Ids are assumed distinct, as the reference's are (object ids).
+static bool id_order_tables(const Index& ix, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ix.order_mu);
+    if (ix.ids_order < 0) {
+        const i64 nd = ix.nd;
+        const unsigned grid = (unsigned)ceil_div(nd > 0 ? nd : 1, 256);
+        DevBuf<int> flag(1, st);
+        CDB_CUDA(cudaMemsetAsync(flag.p, 0, 4, st));
+        ids_descent_kernel<<<grid, 256, 0, st>>>(ix.d_ids, nd, flag.p);
+        CDB_LAUNCH_CHECK();
+        int h = 0;
+        CDB_CUDA(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        if (h) {
+            BigBuf<u64> k0((size_t)nd), k1((size_t)nd);
+            BigBuf<u32> v0((size_t)nd), v1((size_t)nd);
+            rank_keys_kernel<<<grid, 256, 0, st>>>(ix.d_ids, nd, k0.p, v0.p);
+            CDB_LAUNCH_CHECK();
+            const int cur = rs::radix_sort_pairs<u32>(k0.p, k1.p, v0.p, v1.p, (u64)nd, 0, 64, st);
+            CDB_CUDA(cudaMalloc((void**)&ix.d_rank_tab, (size_t)nd * 4));
+            CDB_CUDA(cudaMalloc((void**)&ix.d_ids_by_rank, (size_t)nd * 8));
+            rank_scatter_kernel<<<grid, 256, 0, st>>>(cur ? k1.p : k0.p, cur ? v1.p : v0.p, nd, ix.d_rank_tab, ix.d_ids_by_rank);
+            CDB_LAUNCH_CHECK();
+            CDB_CUDA(cudaStreamSynchronize(st));
+        }
+        ix.ids_order = h ? 0 : 1;
+    }
+    return ix.ids_order == 0;
+}
+
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                         cdb_device_result* out) {
+                         cdb_device_result* out, bool id_order) {
     const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
+    // id order: keys are id ranks (rank_tab) and the table translate reads is ids_by_rank; when the ids already ascend with
+    // the doc index both orders coincide and nothing changes
+    const u32* remap = nullptr;
+    const i64* ids_tab = ix.d_ids;
+    if (id_order && id_order_tables(ix, st)) {
+        remap = ix.d_rank_tab;
+        ids_tab = ix.d_ids_by_rank;
+    }
     const i64 ntiles = ceil_div(npat, kTileWarps);
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
@@ -920,7 +990,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
             CDB_CUDA(cudaMemcpyAsync(loff.p, h_loff.data(), (lc.nlc + 1) * 8, cudaMemcpyHostToDevice, st));
             DevBuf<u64> k0(lc.ltotal, st), k1(lc.ltotal, st);
             const int grid = (int)std::min<i64>(ceil_div((i64)lc.ltotal, 256), kNumSMs * 16);
-            large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal, k0.p);
+            large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal, k0.p, remap);
             CDB_LAUNCH_CHECK();
             int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, lc.ltotal, 0,
                                                          32 + bits_for_u64(lc.nlc - 1), st);
@@ -974,11 +1044,15 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     auto launch_gather = [&](auto maxr_tag) {
         constexpr int MAXR = decltype(maxr_tag)::value;
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<MAXR>();
-        if (smem > 48 * 1024)
-            CDB_CUDA(cudaFuncSetAttribute(gather_kernel<SAT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gather_kernel<SAT, MAXR><<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat,
-                                                                                 dlarge.p, alloc_off.p, row_off.p, cdocs.p, ccnt.p,
-                                                                                 seg.p, nranges, rshift);
+        auto go = [&](auto kernel) {
+            if (smem > 48 * 1024) CDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p, alloc_off.p,
+                                                                   row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, remap);
+        };
+        if (remap)
+            go(gather_kernel<SAT, MAXR, true>);
+        else
+            go(gather_kernel<SAT, MAXR, false>);
     };
     if (hc[5] <= 128)
         launch_gather(std::integral_constant<int, 4>{});
@@ -996,8 +1070,9 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         const i64 nitems = ceil_div(npat, 32) * nranges;
         const int per_sm = resident_ctas((const void*)translate_kernel, kTrWarps * 32);
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)num_sms() * per_sm);
-        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cdocs.p, ccnt.p, alloc_off.p, row_off.p, seg.p, ix.d_ids, pairs.p, npat, nranges,
-                                                         counters.p + 4);
+        const char* ek = getenv("CDB_TRANSLATE_KEEP");
+        translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(cdocs.p, ccnt.p, alloc_off.p, row_off.p, seg.p, ids_tab, pairs.p, npat, nranges,
+                                                         counters.p + 4, ek ? atoi(ek) : 0);
         CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[5], st));
@@ -1005,7 +1080,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         if (lc.nu == 0) continue;
         const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), kNumSMs * 16);
         large_emit_kernel<<<grid, 256, 0, st>>>(lc.ukey.p, lc.ustart.p, lc.nu, lc.ltotal, large_list.p + lc.j0, lc.entry_first.p,
-                                                row_off.p, ix.d_ids, pairs.p);
+                                                row_off.p, ids_tab, pairs.p);
         CDB_LAUNCH_CHECK();
     }
     u64 total_pairs = 0;
@@ -1175,11 +1250,11 @@ bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, 
 }
 
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                   cdb_device_result* out) {
+                   cdb_device_result* out, bool id_order) {
     if (ix.width == 4)
-        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out);
+        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out, id_order);
     else
-        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out);
+        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out, id_order);
 }
 
 }  // namespace cdb

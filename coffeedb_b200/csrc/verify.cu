@@ -78,12 +78,15 @@ __device__ __forceinline__ i64 first_difference(const u8* __restrict__ text, Suf
 template <typename SAT>
 __global__ void __launch_bounds__(256) verify_pairs_kernel(VerifyCtx c, bool n1, u32* __restrict__ bitmap,
                                                            unsigned long long* __restrict__ cnt, i64* __restrict__ queue,
-                                                           u64 queue_cap) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+                                                           u64 queue_cap, i64 i_begin, i64 i_end,
+                                                           unsigned long long* __restrict__ qcount) {
+    // one launch covers the ranks [i_begin, i_end); a warp whose last lane is i_end - 1 still compares it with i_end
+    const i64 i = i_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    // (slices start at multiples of 32 and lanes beyond i_end stay for the shuffles below)
     const int lane = threadIdx.x & 31;
     u64 pa = 0;
     SufRef a{0, 0};
-    if (i < c.n) {
+    if (i < c.n && i < i_end) {
         a = suffix_at<SAT>(c, i, &pa);
         if (a.len <= 0) {
             atomicAdd(cnt + 1, 1ull);
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(256) verify_pairs_kernel(VerifyCtx c, bool n1,
     b.start = __shfl_down_sync(0xffffffffu, a.start, 1);
     b.len = __shfl_down_sync(0xffffffffu, a.len, 1);
     u64 pb = __shfl_down_sync(0xffffffffu, pa, 1);
-    if (i + 1 >= c.n) return;
-    if (lane == 31) b = suffix_at<SAT>(c, i + 1, &pb);
+    if (i + 1 >= c.n || i >= i_end) return;
+    if (lane == 31 || i + 1 >= i_end) b = suffix_at<SAT>(c, i + 1, &pb);
     if (a.len <= 0 || b.len <= 0) return;  // counted as invalid above (or by the neighbour's thread)
     int ca, cb;
     const i64 d = first_difference(c.text, a, b, &ca, &cb);
@@ -116,7 +119,8 @@ __global__ void __launch_bounds__(256) verify_pairs_kernel(VerifyCtx c, bool n1,
         if (ca > cb) atomicAdd(cnt + 0, 1ull);
         return;
     }
-    const u64 slot = atomicAdd(cnt + 5, 1ull);
+    atomicAdd(cnt + 5, 1ull);
+    const u64 slot = atomicAdd(qcount, 1ull);
     if (slot < queue_cap) {
         queue[2 * slot] = i;
         queue[2 * slot + 1] = d;
@@ -264,30 +268,39 @@ void verify_index(const Index& ix, cudaStream_t st, i64 out[8]) {
     const size_t words = (size_t)((ix.n + 31) / 32);
     DevBuf<u32> bitmap(words, st);
     DevBuf<unsigned long long> cnt(8, st);
-    const u64 qcap = n1 ? (u64)std::min<i64>(ix.n, (i64)1 << 26) : 1;
+    // Note-N1 layout: the array is walked in slices of at most 2^26 ranks, so the queue of pairs waiting for the
+    // signed-rule check (at most one per rank) can never overflow; otherwise one launch covers everything.
+    const i64 slice = n1 ? std::min<i64>((ix.n + 31) & ~(i64)31, (i64)1 << 26) : ((ix.n + 31) & ~(i64)31);
+    const u64 qcap = n1 ? (u64)slice : 1;
     DevBuf<i64> queue((size_t)qcap * 2, st);
+    DevBuf<unsigned long long> qcount(1, st);
     CDB_CUDA(cudaMemsetAsync(bitmap.p, 0, words * 4, st));
     CDB_CUDA(cudaMemsetAsync(cnt.p, 0, 64, st));
-    const unsigned grid = (unsigned)ceil_div(ix.n, 256);
-    if (ix.width == 4)
-        verify_pairs_kernel<u32><<<grid, 256, 0, st>>>(c, n1, bitmap.p, cnt.p, queue.p, qcap);
-    else
-        verify_pairs_kernel<u64><<<grid, 256, 0, st>>>(c, n1, bitmap.p, cnt.p, queue.p, qcap);
-    CDB_LAUNCH_CHECK();
     unsigned long long h[8];
+    for (i64 i0 = 0; i0 < ix.n; i0 += slice) {
+        const i64 i1 = std::min<i64>(ix.n, i0 + slice);
+        CDB_CUDA(cudaMemsetAsync(qcount.p, 0, 8, st));
+        const unsigned grid = (unsigned)ceil_div(i1 - i0, 256);
+        if (ix.width == 4)
+            verify_pairs_kernel<u32><<<grid, 256, 0, st>>>(c, n1, bitmap.p, cnt.p, queue.p, qcap, i0, i1, qcount.p);
+        else
+            verify_pairs_kernel<u64><<<grid, 256, 0, st>>>(c, n1, bitmap.p, cnt.p, queue.p, qcap, i0, i1, qcount.p);
+        CDB_LAUNCH_CHECK();
+        unsigned long long hq = 0;
+        CDB_CUDA(cudaMemcpyAsync(&hq, qcount.p, 8, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        const u64 nq = std::min<u64>(hq, qcap);
+        if (nq) {
+            const unsigned g2 = (unsigned)ceil_div((i64)nq, 128);
+            if (ix.width == 4)
+                verify_signed_kernel<u32><<<g2, 128, 0, st>>>(c, ix.chuck_size, queue.p, nq, cnt.p);
+            else
+                verify_signed_kernel<u64><<<g2, 128, 0, st>>>(c, ix.chuck_size, queue.p, nq, cnt.p);
+            CDB_LAUNCH_CHECK();
+        }
+    }
     CDB_CUDA(cudaMemcpyAsync(h, cnt.p, 64, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
-    const u64 nq = std::min<u64>(h[5], qcap);
-    if (nq) {
-        const unsigned g2 = (unsigned)ceil_div((i64)nq, 128);
-        if (ix.width == 4)
-            verify_signed_kernel<u32><<<g2, 128, 0, st>>>(c, ix.chuck_size, queue.p, nq, cnt.p);
-        else
-            verify_signed_kernel<u64><<<g2, 128, 0, st>>>(c, ix.chuck_size, queue.p, nq, cnt.p);
-        CDB_LAUNCH_CHECK();
-        CDB_CUDA(cudaMemcpyAsync(h, cnt.p, 64, cudaMemcpyDeviceToHost, st));
-        CDB_CUDA(cudaStreamSynchronize(st));
-    }
     for (int k = 0; k < 8; ++k) out[k] = (i64)h[k];
 }
 

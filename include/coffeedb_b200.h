@@ -203,6 +203,67 @@ void cdb_spans_free(cdb_spans* s);
 int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t nspans, const void* left, int64_t llen,
                    const void* right, int64_t rlen, void* out, int64_t out_cap);
 
+/* ---- filter(): set algebra over constraint results, on the device -----------------------------------
+ * Replaces the body of filter() (src/interface.cpp:46-147) and what it calls: query(key, range) of string keys
+ * (src/database.cpp:387-393 -> string_index::query) and of integer / double keys (numeric_query, src/index.cpp:63-74).
+ * Per request: the results of the ranges of ONE key are OR-merged by id with their counts added (interface.cpp:79-112),
+ * the keys are AND-intersected with counts added (:113-134, numeric keys contribute 0, src/index.cpp:71), "$correlation"
+ * keeps sums in [L, R) (:136-142), the answer is ordered by std::sort on descending $correlation (:143-146 — unstable:
+ * the device reproduces libstdc++'s permutation of the id-ascending input exactly, coffeedb_b200/host/std_sort_order.hpp)
+ * and `span` cuts result[span0, span1) (interface.cpp:196-209).  Only that slice crosses PCIe. */
+typedef struct cdb_numeric cdb_numeric; /* replaces one integer_index / double_index (src/index.h:29-53) */
+/* add() for every (id, value) + build() (src/index.cpp:152-173).  kind 0: values are int64_t, kind 1: double. */
+cdb_status cdb_numeric_create(int32_t kind, const int64_t* ids, const void* values, int64_t n, int32_t device,
+                              cdb_numeric** out);
+void cdb_numeric_destroy(cdb_numeric* c);
+/* integer_index::query / double_index::query (src/index.cpp:159-161, 170-172 -> numeric_query :63-74): a one-row result,
+ * the (id, 0) pairs of data[lower_bound(lo), lower_bound(hi)) in (value, id) order.  lo / hi = {value bits, id} exactly
+ * as parse_range builds its two pairs (src/utility.h:69-86): the id is INT64_MAX for "(" on the left / "]" on the
+ * right and 0 otherwise; value bits are the int64_t, or the bit pattern of the double. */
+cdb_status cdb_numeric_query(const cdb_numeric* c, const int64_t lo[2], const int64_t hi[2], cdb_result* out);
+
+typedef struct cdb_filter_key {
+    int32_t kind;      /* 0: index is a built cdb_index*; 1: a cdb_numeric*; -1: a key the database does not have — its
+                          query() answers {} (src/database.cpp:389-391), so a request that names it matches nothing */
+    int32_t reserved;
+    const void* index;
+} cdb_filter_key;
+typedef struct cdb_filter_term {   /* one range string of one key of one request (interface.cpp:56-74) */
+    int32_t key;       /* slot in keys[] */
+    int32_t range;     /* numeric key: index into ranges[]; string key: -1 */
+    int64_t kw_begin;  /* string key: the keyword is kw[kw_begin, kw_end) */
+    int64_t kw_end;
+} cdb_filter_term;
+typedef struct cdb_filter_batch {
+    const cdb_filter_key* keys;
+    int32_t nkeys;               /* <= 32 */
+    int32_t reserved;
+    const void* kw;              /* keyword bytes of all string terms */
+    int64_t kw_len;
+    const int64_t* ranges;       /* [4 * nranges] {lo value bits, lo id, hi value bits, hi id}, see cdb_numeric_query */
+    int64_t nranges;
+    const cdb_filter_term* terms;     /* request r owns terms [req_term_off[r], req_term_off[r+1]), at most 64; terms with
+                                         the same key are OR-ed, different keys AND-ed; a request without terms matches
+                                         nothing (the reference answers it from its object table, interface.cpp:51-53) */
+    const int64_t* req_term_off;      /* [nreq + 1] */
+    int64_t nreq;
+    const int64_t* corr_range;        /* NULL or [2 * nreq]: keep L <= $correlation < R (parse_uint_range, utility.h:87-104) */
+    const int64_t* span;              /* NULL or [2 * nreq]: result[span0, span1) */
+} cdb_filter_batch;
+/* Request r: pairs[2*row_off[r] .. 2*row_off[r+1]) = (id, $correlation) in the reference's order; matched[r] = size of
+ * its answer before the span (what `count` reports, interface.cpp:243-262). */
+typedef struct cdb_filter_result {
+    int64_t nreq;
+    int64_t total_pairs;
+    const int64_t* row_off; /* [nreq+1] */
+    const int64_t* pairs;   /* [2*total_pairs] */
+    const int64_t* matched; /* [nreq] */
+    void* _owner;
+} cdb_filter_result;
+/* An empty keyword fails the batch with CDB_ERR_EMPTY_KEYWORD (src/index.cpp:239-241).  Re-entrant. */
+cdb_status cdb_filter(const cdb_filter_batch* batch, cdb_filter_result* out);
+void cdb_filter_result_free(cdb_filter_result* r);
+
 /* Timing of the last build (milliseconds, CUDA events): total and the radix-sort share; refinement rounds
  * and number of key-range chunks. */
 cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_ms, int64_t* rounds, int64_t* chunks);

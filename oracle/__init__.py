@@ -222,6 +222,9 @@ def _ref():
         lib.ref_query_batch.restype = C.c_double
         lib.ref_query_batch_csr.argtypes = [C.c_void_p, C.c_void_p, i64p, C.c_int64, C.c_int, i64p, C.POINTER(i64p)]
         lib.ref_query_batch_csr.restype = C.c_int64
+        lib.ref_filter_span_batch.argtypes = [C.c_void_p, C.c_void_p, i64p, C.c_int64, C.c_int, C.c_int64, C.c_int64, i64p,
+                                              C.POINTER(i64p), i64p]
+        lib.ref_filter_span_batch.restype = C.c_double
         lib.ref_hardware_threads.restype = C.c_int
         lib.ref_render.argtypes = [C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64,
                                    C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
@@ -324,6 +327,28 @@ class Ref:
         pairs = np.ctypeslib.as_array(out, shape=(max(total, 1), 2))[:total].copy() if total else np.zeros((0, 2), np.int64)
         self._lib.ref_free(out)
         return row_off, pairs
+
+
+    def filter_span_batch(self, pat: np.ndarray, pat_off: np.ndarray, span0: int, span1: int, nthreads: int = 0, keep: bool = True):
+        """One-keyword requests through query() + the sorts and the span of src/interface.cpp:82,143-146,196-209.
+        -> (seconds, row_off, pairs[total,2], matched) — row_off / pairs / matched are None when keep is False."""
+        pat = np.concatenate([_bytes_arr(pat), np.zeros(1, np.uint8)])
+        pat_off = np.ascontiguousarray(pat_off, np.int64)
+        npat = len(pat_off) - 1
+        nthreads = nthreads or hardware_threads()
+        if not keep:
+            s = self._lib.ref_filter_span_batch(self._h, pat.ctypes.data, _p(pat_off, C.c_int64), npat, nthreads, span0, span1,
+                                                None, None, None)
+            return s, None, None, None
+        row_off = np.zeros(npat + 1, np.int64)
+        matched = np.zeros(max(npat, 1), np.int64)
+        out = C.POINTER(C.c_int64)()
+        s = self._lib.ref_filter_span_batch(self._h, pat.ctypes.data, _p(pat_off, C.c_int64), npat, nthreads, span0, span1,
+                                            _p(row_off, C.c_int64), C.byref(out), _p(matched, C.c_int64))
+        total = int(row_off[-1])
+        pairs = np.ctypeslib.as_array(out, shape=(max(total, 1), 2))[:total].copy() if total else np.zeros((0, 2), np.int64)
+        self._lib.ref_free(out)
+        return s, row_off, pairs, matched[:npat]
 
 
 def hardware_threads() -> int:

@@ -14,6 +14,7 @@
 // Private state is read without editing the reference: string_index declares the public member
 // template `parallel_sort<T>()` (src/index.h:85); an explicit specialisation for a harness-only
 // tag type is a member function and may therefore read `sa`, `bits`, `mask`, `size`.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -244,6 +245,70 @@ int64_t ref_query_batch_csr(void* h, const char* pat, const int64_t* pat_off, in
         }
     *pairs_out = buf;
     return total;
+}
+
+// One-keyword requests through the rest of the reference's request path: what filter() and the `span` handling do with
+// the result of query(key, keyword) when the constraint object holds that one key (src/interface.cpp:79-83: sort by
+// (id, count); :143-146: std::sort by descending $correlation; :196-209: result[span0, span1)).  Those lines are
+// restated here verbatim around the UNMODIFIED string_index::query, because filter() itself is reachable only through
+// response() and the global object table (src/interface.cpp:149, src/database.cpp:26-33), which cannot hold 10^8
+// objects.  Returns wall seconds; with row_off != NULL the sliced answers are kept (malloc'd *pairs_out).
+double ref_filter_span_batch(void* h, const char* pat, const int64_t* pat_off, int64_t npat, int nthreads, int64_t span0,
+                             int64_t span1, int64_t* row_off, int64_t** pairs_out, int64_t* matched) {
+    auto* r = static_cast<ref_handle*>(h);
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> rows(row_off ? (size_t)npat : 0);
+    std::atomic<int64_t> next{0};
+    std::atomic<int64_t> sink{0};
+    auto worker = [&]() {
+        int64_t acc = 0;
+        for (;;) {
+            int64_t b = next.fetch_add(64);
+            if (b >= npat) break;
+            int64_t e = std::min<int64_t>(npat, b + 64);
+            for (int64_t q = b; q < e; ++q) {
+                auto result = r->idx.query(std::string(pat + pat_off[q], (size_t)(pat_off[q + 1] - pat_off[q])));
+                std::ranges::sort(result);                                          // src/interface.cpp:82
+                std::sort(result.begin(), result.end(), [](auto x, auto y) {        // src/interface.cpp:143-146
+                    return x.second > y.second;
+                });
+                if (matched) matched[q] = (int64_t)result.size();
+                if (span0 >= (int64_t)std::ssize(result)) {                         // src/interface.cpp:198-207
+                    result.clear();
+                } else {
+                    auto end = result.end();
+                    if (span1 < (int64_t)std::ssize(result)) end = result.begin() + span1;
+                    result = {result.begin() + span0, end};
+                }
+                acc += (int64_t)result.size();
+                if (row_off) rows[q] = std::move(result);
+            }
+        }
+        sink += acc;
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int i = 1; i < nthreads; ++i) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (row_off) {
+        int64_t total = 0;
+        for (int64_t q = 0; q < npat; ++q) {
+            row_off[q] = total;
+            total += (int64_t)rows[q].size();
+        }
+        row_off[npat] = total;
+        int64_t* buf = (int64_t*)std::malloc(sizeof(int64_t) * 2 * (total + 1));
+        int64_t k = 0;
+        for (auto& row : rows)
+            for (auto& pr : row) {
+                buf[2 * k] = pr.first;
+                buf[2 * k + 1] = pr.second;
+                ++k;
+            }
+        *pairs_out = buf;
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

@@ -145,18 +145,25 @@ def utf8_fast(char_lens, seed: int):
     return text, off, ids
 
 
-MAX_CHARS = 21_000  # <= 63 KB even if every code point took 3 bytes
+MAX_CHARS = 44_000  # 1.45 bytes per code point on average: the longest documents reach ~64 000 bytes, never 65 536
+SHORT_CHARS = 2_000  # three quarters of the documents are short, so that 1 GiB already holds > 65 535 documents
 
 
 def utf8_corpus_on_device(target_bytes: int, seed: int, device_index: int = 0):
-    """Documents of 1..MAX_CHARS code points, 70 % one-byte (0x20..0x7E), 15 % two-byte, 15 % three-byte sequences
-    (SURVEY.md 8d config 5), generated with torch on the GPU -> (text uint8 [n + 64], doc_off int64 [nd + 1], ids)."""
+    """Documents of up to 64 KB: 70 % one-byte (0x20..0x7E), 15 % two-byte, 15 % three-byte code points (SURVEY.md 8d
+    config 5), generated with torch on the GPU -> (text uint8 [n + 64], doc_off int64 [nd + 1], ids, nd, n >= target).
+    Lengths are skewed (75 % of the documents have 1..SHORT_CHARS code points, the rest 1..MAX_CHARS) so that a 1 GiB
+    corpus has more than 2^16 documents AND documents longer than 2^15 bytes: bits1 + bits2 > 32, 64-bit elements."""
     import torch
     dev = torch.device("cuda", device_index)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    nd = int(target_bytes / (1.45 * (MAX_CHARS + 1) / 2)) + 1
-    char_lens = torch.randint(1, MAX_CHARS + 1, (nd,), device=dev, generator=g)
+    avg_chars = 0.75 * (SHORT_CHARS + 1) / 2 + 0.25 * (MAX_CHARS + 1) / 2
+    nd = int(1.03 * target_bytes / (1.45 * avg_chars)) + 4
+    short = torch.rand(nd, device=dev, generator=g) < 0.75
+    char_lens = torch.where(short, torch.randint(1, SHORT_CHARS + 1, (nd,), device=dev, generator=g),
+                            torch.randint(1, MAX_CHARS + 1, (nd,), device=dev, generator=g))
+    del short
     nchar = int(char_lens.sum())
     u = torch.rand(nchar, device=dev, generator=g)
     cls = (1 + (u >= 0.70).to(torch.int8) + (u >= 0.85).to(torch.int8))

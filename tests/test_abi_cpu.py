@@ -56,6 +56,34 @@ def test_build_fails_loudly_without_a_device():
     ix.close()
 
 
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_filter_and_numeric_fail_loudly_without_a_device():
+    """cdb_filter / cdb_numeric_create have no host path either: the set algebra of src/interface.cpp:79-147 is not
+    re-implemented on the CPU behind the ABI."""
+    with pytest.raises(RuntimeError, match="no CUDA device available: coffeedb_b200 has no CPU fallback"):
+        cdb.NumericIndex(0, [1, 2], [3, 4])
+    ix = cdb.StringIndex()
+    ix.add(1, b"abc")
+    with pytest.raises(RuntimeError, match="no CUDA device available"):
+        cdb.filter_batch({"v": ix}, [{"constraints": {"v": "a"}}])
+    ix.close()
+
+
+def test_range_parsing_follows_the_reference():
+    # src/utility.h:69-104: "(" / "]" set the id half of the bound pair to INT64_MAX; uint ranges become half-open
+    assert cdb.parse_range("[1990, 2000)", 0) == (1990, 0, 2000, 0)
+    assert cdb.parse_range("(5,7]", 0) == (5, cdb.INT64_MAX, 7, cdb.INT64_MAX)
+    assert cdb.parse_range("[-inf,inf]", 0) == (-(1 << 63), 0, cdb.INT64_MAX, cdb.INT64_MAX)
+    lo, _a, hi, _b = cdb.parse_range("[0.5,inf)", 1)
+    import numpy as np
+    assert np.array([lo, hi], np.int64).view(np.float64).tolist() == [0.5, np.finfo(np.float64).max]
+    assert cdb.parse_uint_range("[0,32)") == (0, 32) and cdb.parse_uint_range("(3,3]") == (4, 4)
+    with pytest.raises(ValueError):
+        cdb.parse_uint_range("[5,2]")
+    with pytest.raises(ValueError):
+        cdb.parse_range("1..2", 0)
+
+
 def test_splice_matches_reference_rendering(golden):
     # database.cpp:78-90 — host-side marker splicing, checked against the compiled reference's rendered strings
     import oracle

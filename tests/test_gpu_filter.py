@@ -1,0 +1,191 @@
+"""cdb_filter against the UNMODIFIED reference: the compiled reference server (tests/dropin, CPU) answers
+`query` requests through its own filter() / span code (src/interface.cpp:46-147, 196-209) over HTTP, and the device-side
+filter must return the same objects with the same $correlation IN THE SAME ORDER — including the order std::sort gives to
+ties, which is what decides the content of a span.  Covered: one keyword, OR of keywords, AND of keys, integer and double
+ranges (open / closed / inf), $correlation ranges, spans, a key the database does not have, numeric-only requests, repeated
+keywords, rows longer than the warp path (CTA path + the host's std::sort), ids in and out of doc order."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+import coffeedb_b200 as cdb
+from tests.dropin import build_servers
+from tests.test_dropin_server import Server
+
+pytestmark = pytest.mark.gpu
+
+N = 2600
+
+
+def make_objects(seed=11):
+    rng = random.Random(seed)
+    objs = []
+    for uid in range(N):
+        title = "".join(rng.choice("abc") for _ in range(rng.randint(20, 120)))          # many repeats: unequal sums
+        body = "".join(rng.choice("abcdefghij") for _ in range(rng.randint(50, 300)))     # mostly single hits: ties
+        objs.append({"uid": uid, "title": title, "body": body, "year": rng.randint(1990, 2020), "score": rng.randint(0, 1024) / 1024})
+    return objs
+
+
+REQUESTS = [
+    {"constraints": {"title": "abca"}},
+    {"constraints": {"title": "abca"}, "span": "[0,10)"},
+    {"constraints": {"body": "abc"}, "span": "[0,32)"},
+    {"constraints": {"body": "abc"}, "span": "[5,40]"},
+    {"constraints": {"body": "abc"}, "span": "(3,3]"},
+    {"constraints": {"body": "abc"}, "span": "[100000,100010)"},
+    {"constraints": {"body": "hij"}},
+    {"constraints": {"body": ["hij", "abc", "fed"]}, "span": "[0,50)"},
+    {"constraints": {"title": ["ab", "ab"]}, "span": "[0,20)"},
+    {"constraints": {"title": "cab", "body": "ab"}},
+    {"constraints": {"title": ["cab", "bbb"], "body": ["ab", "ji"]}, "span": "[2,60)"},
+    {"constraints": {"title": "abc", "year": "[1995,2005)"}},
+    {"constraints": {"title": "abc", "year": "(2000,inf]", "score": "[0.25,0.75]"}, "span": "[0,25)"},
+    {"constraints": {"title": "abc", "year": ["[1990,1992]", "(2015,2020]"]}},
+    {"constraints": {"body": "bcd", "score": "(-inf,0.5)"}},
+    {"constraints": {"title": "abc", "$correlation": "[2,4)"}},
+    {"constraints": {"title": ["abc", "cba"], "body": "a", "$correlation": "(3,9]"}, "span": "[0,40)"},
+    {"constraints": {"title": "abc", "nosuchkey": "x"}},
+    {"constraints": {"title": "zzzz"}},
+    {"constraints": {"year": "[1990,1992]"}, "span": "[0,30)"},
+    {"constraints": {"year": ["[1990,1991]", "[1991,1993)"], "score": "(0.2,0.7]"}},
+    {"constraints": {"score": "[0.5,0.5]"}},
+    {"constraints": {"year": "[2001,2003]", "$correlation": "[0,1)"}, "span": "[3,12)"},
+    {"constraints": {"year": "[2001,2003]", "$correlation": "[1,5)"}},
+    {"constraints": {"title": "a"}, "span": "[0,64)"},            # every object: CTA path, host std::sort
+    {"constraints": {"title": "a", "body": "a"}, "span": "[10,90)"},
+    {"constraints": {"title": ["a", "b"], "year": "[1990,2000]"}, "span": "[0,100)"},
+    {"constraints": {"body": "a"}},
+]
+
+
+@pytest.fixture(scope="module")
+def reference_answers(tmp_path_factory):
+    b = build_servers.build()
+    if b is None:
+        pytest.skip("neither /root/reference nor prebuilt tests/dropin/_build servers are present")
+    objs = make_objects()
+    s = Server(b["reference"], str(tmp_path_factory.mktemp("ref")))
+    try:
+        for o in objs:
+            s.send({"operation": "insert", "data": o})  # ids = insertion timestamps: ascending with uid
+        s.send({"operation": "build"})
+        answers = []
+        for req in REQUESTS:
+            cmd = {"operation": "query", "constraints": req["constraints"], "fields": ["uid", "$correlation"]}
+            if "span" in req:
+                cmd["span"] = req["span"]
+            got = json.loads(s.send(cmd))
+            answers.append([(int(o["uid"]), int(o.get("$correlation", 0))) for o in got])
+        counts = [json.loads(s.send({"operation": "count", "constraints": req["constraints"]}))["count"] for req in REQUESTS]
+    finally:
+        s.stop()
+    return objs, answers, counts
+
+
+def build_keys(objs, order):
+    keys = {}
+    for name in ("title", "body"):
+        ix = cdb.StringIndex()
+        for i in order:
+            ix.add(objs[i]["uid"], objs[i][name].encode())
+        ix.build()
+        keys[name] = ix
+    perm = list(order)
+    keys["year"] = cdb.NumericIndex(0, [objs[i]["uid"] for i in perm], [objs[i]["year"] for i in perm])
+    keys["score"] = cdb.NumericIndex(1, [objs[i]["uid"] for i in perm], [objs[i]["score"] for i in perm])
+    return keys
+
+
+@pytest.mark.parametrize("doc_order", ["id order", "shuffled"])
+def test_filter_equals_reference_server(reference_answers, doc_order):
+    objs, answers, counts = reference_answers
+    order = list(range(N))
+    if doc_order == "shuffled":  # doc index != id order: the id-rank tables are used (locate.cu id_order_tables)
+        random.Random(5).shuffle(order)
+    keys = build_keys(objs, order)
+    try:
+        got = cdb.filter_batch(keys, REQUESTS)
+        assert len(got) == len(REQUESTS)
+        for req, (pairs, matched), want, cnt in zip(REQUESTS, got, answers, counts):
+            assert [(int(a), int(b)) for a, b in pairs] == want, (req, pairs[:8], want[:8])
+            assert matched == cnt, (req, matched, cnt)
+        assert sum(len(w) for w in answers) > 5000
+        # the same requests one at a time (other batch shapes, other allocation sizes)
+        for req, want in list(zip(REQUESTS, answers))[::3]:
+            (pairs, _m), = cdb.filter_batch(keys, [req])
+            assert [(int(a), int(b)) for a, b in pairs] == want, req
+    finally:
+        for k in keys.values():
+            k.close()
+
+
+def test_numeric_query_is_the_reference_numeric_query():
+    """cdb_numeric_query == numeric_query (src/index.cpp:63-74): sort by (value, id), two lower bounds with the pairs
+    parse_range builds (src/utility.h:69-86)."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    ids = rng.permutation(n).astype(np.int64) * 3 + 17
+    for kind, vals in ((0, rng.integers(-50, 50, n)), (1, rng.integers(-40, 40, n) / 8.0)):
+        col = cdb.NumericIndex(kind, ids, vals)
+        data = sorted(zip(vals.tolist(), ids.tolist()))
+        for text in ["[-10,10)", "(-10,10]", "[3,3]", "(3,3)", "[-inf,inf]", "(0,inf)", "[7,2]", "[-1000,1000]", "(-3.5,2.25]" if kind else "(-3,2]"]:
+            lo0, lo1, hi0, hi1 = cdb.parse_range(text, kind)
+            conv = (lambda b: b) if kind == 0 else (lambda b: float(np.array([b], np.int64).view(np.float64)[0]))
+            L, R = (conv(lo0), lo1), (conv(hi0), hi1)
+            import bisect
+            b, e = bisect.bisect_left(data, L), bisect.bisect_left(data, R)
+            want = [(i, 0) for _v, i in data[b:max(b, e)]]
+            got = [(int(a), int(z)) for a, z in col.query(text)]
+            assert got == want, (kind, text, got[:5], want[:5])
+        col.close()
+
+
+def test_filter_errors():
+    ix = cdb.StringIndex()
+    ix.add(1, b"abc")
+    ix.build()
+    with pytest.raises(RuntimeError, match="Empty keywords are not allowed"):
+        cdb.filter_batch({"v": ix}, [{"constraints": {"v": ""}}])
+    (pairs, matched), = cdb.filter_batch({"v": ix}, [{"constraints": {}}])
+    assert len(pairs) == 0 and matched == 0
+    assert cdb.filter_batch({"v": ix}, []) == []
+    ix.close()
+
+
+def test_filter_many_single_keyword_requests_match_locate_rows():
+    """The cfg3 shape of the bench's end-to-end leg at small scale: thousands of one-keyword requests with span [0,32);
+    every answer must be the keyword's locate row re-ordered as the reference orders it (ids scrambled)."""
+    from tests import corpora
+    text, off, ids = corpora.uniform(20000, 100, seed=8)
+    ix = cdb.StringIndex()
+    ix.add_many(ids, text, off)
+    ix.build()
+    pat, poff = corpora.uniform_patterns(3000, 3, seed=9)
+    row_off, pairs = ix.locate_batch(pat, poff)
+    nreq = len(poff) - 1
+    terms = np.zeros(nreq, cdb.TERM_DTYPE)
+    terms["range"] = -1
+    terms["kw_begin"], terms["kw_end"] = poff[:-1], poff[1:]
+    span = np.tile(np.array([0, 32], np.int64), (nreq, 1))
+    res = cdb.filter_raw([ix], pat, np.zeros((0, 4), np.int64), terms, np.arange(nreq + 1, dtype=np.int64), None, span)
+    try:
+        ro = np.ctypeslib.as_array(res.row_off, shape=(nreq + 1,))
+        pr = np.ctypeslib.as_array(res.pairs, shape=(max(res.total_pairs, 1), 2))
+        mt = np.ctypeslib.as_array(res.matched, shape=(nreq,))
+        for q in range(0, nreq, 7):
+            row = pairs[row_off[q]:row_off[q + 1]]
+            assert mt[q] == len(row)
+            got = pr[ro[q]:ro[q + 1]]
+            assert len(got) == min(32, len(row))
+            srt = row[np.argsort(row[:, 0], kind="stable")]
+            # same multiset of (id, count) restricted to what a descending-count order allows at the cut
+            assert set(map(tuple, got.tolist())) <= set(map(tuple, srt.tolist()))
+            if len(got):
+                assert got[:, 1].tolist() == sorted(got[:, 1].tolist(), reverse=True)
+                assert got[-1, 1] >= np.sort(srt[:, 1])[::-1][len(got) - 1]
+    finally:
+        cdb.filter_result_free(res)
+        ix.close()

@@ -58,3 +58,16 @@ def test_micro_batcher_host_logic():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "micro_batcher ok" in r.stdout
+
+
+def test_std_sort_order_restatement_equals_std_sort():
+    """coffeedb_b200/host/std_sort_order.hpp (the introsort the device-side filter runs to reproduce the tie order of
+    src/interface.cpp:143-146) yields std::sort's permutation on 6 000 sequences, including every length up to 1 100
+    with all-equal keys, few-valued keys and median-of-three killers (heap-sort fallback)."""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "test_sort_order")
+    src = os.path.join(ROOT, "tests", "host", "test_sort_order.cpp")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", src, "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sort_order ok" in r.stdout
