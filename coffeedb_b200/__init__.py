@@ -25,7 +25,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 # every symbol include/coffeedb_b200.h declares
 EXPORTS = [
-    "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many",
+    "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many", "cdb_staging_stats",
     "cdb_build", "cdb_build_device", "cdb_save", "cdb_build_or_load", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
@@ -110,6 +110,7 @@ def lib():
         L.cdb_destroy.restype = None
         L.cdb_add.argtypes = [vp, C.c_int64, vp, C.c_int64]
         L.cdb_add_many.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.cdb_staging_stats.argtypes = [vp, i64p, i64p]
         L.cdb_build.argtypes = [vp]
         L.cdb_save.argtypes = [vp, C.c_char_p]
         L.cdb_build_or_load.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32)]
@@ -209,6 +210,12 @@ class StringIndex:
         doc_off = np.ascontiguousarray(doc_off, np.int64)
         _check(self._L.cdb_add_many(self._h, ids.ctypes.data, text.ctypes.data if len(text) else None,
                                     doc_off.ctypes.data, len(ids)))
+
+    def staging_stats(self) -> dict:
+        """Bytes of text staged by add() and how many of them already have a device copy."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(self._L.cdb_staging_stats(self._h, C.byref(a), C.byref(b)))
+        return {"staged": a.value, "on_device": b.value}
 
     def build(self):
         """string_index::build (src/index.cpp:178-236)"""

@@ -264,6 +264,7 @@ cdb_status cdb_create(const cdb_options* opts, cdb_index** out) {
         ix->opt.keep_host_copy = 0;
     }
     ix->device = ix->opt.device;
+    ix->h_text.set_device(ix->opt.device);
     *out = reinterpret_cast<cdb_index*>(ix);
     return CDB_OK;
     CDB_CATCH
@@ -284,10 +285,17 @@ cdb_status cdb_add(cdb_index* h, int64_t id, const void* value, int64_t len) {
     Index* ix = reinterpret_cast<Index*>(h);
     if (!ix || len < 0 || (len > 0 && !value)) throw Error(CDB_ERR_ARG, "cdb_add: bad argument");
     if (ix->host_dropped) throw Error(CDB_ERR_STATE, kAfterBuild);
-    ix->h_ids.push_back(id);
-    const u8* p = static_cast<const u8*>(value);
-    ix->h_text.insert(ix->h_text.end(), p, p + len);
-    ix->h_off.push_back((i64)ix->h_text.size());
+    const size_t text0 = ix->h_text.size(), ids0 = ix->h_ids.size(), off0 = ix->h_off.size();
+    try {
+        ix->h_text.append(static_cast<const u8*>(value), (size_t)len);
+        ix->h_ids.push_back(id);
+        ix->h_off.push_back((i64)ix->h_text.size());
+    } catch (...) {
+        ix->h_text.truncate(text0);
+        ix->h_ids.resize(ids0);
+        ix->h_off.resize(off0);
+        throw;
+    }
     return CDB_OK;
     CDB_CATCH
 }
@@ -307,16 +315,26 @@ cdb_status cdb_add_many(cdb_index* h, const int64_t* ids, const void* text, cons
     const size_t text0 = ix->h_text.size(), ids0 = ix->h_ids.size(), off0 = ix->h_off.size();
     try {
         const i64 base = (i64)text0 - doc_off[0];
-        if (doc_off[nd] > doc_off[0]) ix->h_text.insert(ix->h_text.end(), p + doc_off[0], p + doc_off[nd]);
+        if (doc_off[nd] > doc_off[0]) ix->h_text.append(p + doc_off[0], (size_t)(doc_off[nd] - doc_off[0]));
         ix->h_ids.insert(ix->h_ids.end(), ids, ids + nd);
         ix->h_off.reserve(off0 + (size_t)nd);
         for (i64 d = 1; d <= nd; ++d) ix->h_off.push_back(base + doc_off[d]);
     } catch (...) {  // out of host memory half way: roll back
-        ix->h_text.resize(text0);
+        ix->h_text.truncate(text0);
         ix->h_ids.resize(ids0);
         ix->h_off.resize(off0);
         throw;
     }
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_staging_stats(const cdb_index* h, int64_t* staged, int64_t* on_device) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix) throw Error(CDB_ERR_ARG, "cdb_staging_stats: index is NULL");
+    if (staged) *staged = ix->built ? ix->n : (i64)ix->h_text.size();
+    if (on_device) *on_device = ix->built ? ix->staged_on_device : (i64)ix->h_text.uploaded_bytes();
     return CDB_OK;
     CDB_CATCH
 }
@@ -337,9 +355,14 @@ static void build_from_staging(Index* ix, const SavedArraySource* saved) {
         CDB_CUDA(cudaMalloc(&ix->own_off, (size_t)(nd + 1) * 8));
         CDB_CUDA(cudaMalloc(&ix->own_ids, (size_t)(nd ? nd : 1) * 8));
         CDB_CUDA(cudaMemsetAsync((u8*)ix->own_text + n, 0, kTextPad, st));
-        if (n) CDB_CUDA(cudaMemcpyAsync(ix->own_text, ix->h_text.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+        // the chunks that filled up during cdb_add are already on the device: stitched together device-to-device; the
+        // last, partly filled one comes from the host
+        ix->staged_on_device = (i64)ix->h_text.uploaded_bytes();
+        ix->h_text.assemble(ix->own_text, st);
         CDB_CUDA(cudaMemcpyAsync(ix->own_off, ix->h_off.data(), (size_t)(nd + 1) * 8, cudaMemcpyHostToDevice, st));
         if (nd) CDB_CUDA(cudaMemcpyAsync(ix->own_ids, ix->h_ids.data(), (size_t)nd * 8, cudaMemcpyHostToDevice, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+        ix->h_text.release_device_copies();  // before the build sizes its workspace from the free memory
         ix->d_text = (const u8*)ix->own_text;
         ix->d_off = (const i64*)ix->own_off;
         ix->d_ids = (const i64*)ix->own_ids;
@@ -353,7 +376,7 @@ static void build_from_staging(Index* ix, const SavedArraySource* saved) {
     }
     cudaStreamDestroy(st);
     if (!ix->opt.keep_host_copy) {
-        std::vector<u8>().swap(ix->h_text);
+        ix->h_text.clear();
         ix->host_dropped = true;
     }
 }

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "staging.cuh"
 
 namespace cdb {
 
@@ -25,8 +26,9 @@ struct SymTab {
 struct Index {
     cdb_options opt{};
     int device = 0;
-    // host staging filled by cdb_add (src/index.cpp:174-177)
-    std::vector<u8> h_text;
+    // host staging filled by cdb_add (src/index.cpp:174-177): text in page-locked chunks that leave for the device as they
+    // fill up (staging.cuh), offsets and ids in plain vectors (16 B per document)
+    TextStaging h_text;
     std::vector<i64> h_off{0};
     std::vector<i64> h_ids;
     bool host_dropped = false;  // the staging copy was released after build (keep_host_copy == 0)
@@ -54,6 +56,7 @@ struct Index {
     // build statistics
     double build_ms = 0, sort_ms = 0;
     i64 rounds = 0, chunks = 0;
+    i64 staged_on_device = 0;       // bytes of text that were already in HBM when the last cdb_build started (staging.cuh)
     bool loaded_from_file = false;  // the last build read a saved array instead of sorting (cdb_build_or_load)
     // Id order of the documents, for filter() (src/interface.cpp:79-135 merges rows sorted by id; string_index::query
     // reports them in doc order).  ids_order: -1 not examined yet, 1 = ids ascend with the doc index (doc order IS id order),

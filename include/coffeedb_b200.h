@@ -107,6 +107,11 @@ void cdb_destroy(cdb_index* idx);
 cdb_status cdb_add(cdb_index* idx, int64_t id, const void* value, int64_t len);
 /* nd add() calls at once: document d = text[doc_off[d], doc_off[d+1]). */
 cdb_status cdb_add_many(cdb_index* idx, const int64_t* ids, const void* text, const int64_t* doc_off, int64_t nd);
+/* Loader staging (replaces the std::string-per-field loading of src/database.cpp:173-275): cdb_add /
+ * cdb_add_many append to page-locked chunks, and every chunk that fills up is sent to the device while the loader goes
+ * on, so cdb_build only stitches the chunks together.  staged = bytes of text added so far, on_device = how many of
+ * them already have a device copy (after cdb_build: how many had one when the build started). */
+cdb_status cdb_staging_stats(const cdb_index* idx, int64_t* staged, int64_t* on_device);
 
 /* string_index::build() (src/index.cpp:178-236): uploads the staged text and constructs the packed suffix
  * array on the device.  Element = (offset_in_doc << bits) | doc_index, 4 bytes wide iff bits1+bits2 <= 32. */

@@ -721,3 +721,30 @@ def test_save_and_build_or_load(tmp_path):
     g.add_many(ids, text, off)
     assert g.build_or_load(str(tmp_path / "missing.cdbsa")) is False and np.array_equal(g.export_sa(), sa)
     g.close()
+
+
+# ---- loader staging ------------------------------------------------------------------------------------
+def test_loader_staging_uploads_full_chunks_during_add():
+    """cdb_add streams into page-locked chunks (1, 2, 4 ... MB); full chunks are on the device before build() is called,
+    the build result is the reference's, and a rejected add_many leaves the staged text untouched."""
+    text, off, ids = corpora.uniform(60000, 100, seed=97)  # 6 MB: chunks of 1 + 2 MB fill up, the 4 MB one does not
+    ix = cdb.StringIndex()
+    half = 30000
+    for d in range(0, half):  # document by document, like the reference's loader (src/database.cpp:255-264)
+        ix.add(int(ids[d]), text[off[d]:off[d + 1]].tobytes())
+    st = ix.staging_stats()
+    assert st["staged"] == off[half] and st["on_device"] == (1 << 20)  # the 2 MB chunk is still filling
+    bad = off[half:].copy() - off[half]
+    bad[5] = bad[4] - 1  # decreasing offsets: rejected before anything is staged
+    with pytest.raises(RuntimeError, match="non-decreasing"):
+        ix.add_many(ids[half:], text[off[half]:], bad)
+    assert ix.staging_stats()["staged"] == off[half]
+    ix.add_many(ids[half:], text[off[half]:], off[half:] - off[half])
+    assert ix.staging_stats()["staged"] == len(text)
+    ix.build()
+    assert ix.staging_stats() == {"staged": len(text), "on_device": (1 << 20) + (2 << 20)}
+    sa, bits1, _w = oracle.port.build_sa(text, off)
+    assert np.array_equal(ix.export_sa(), sa)
+    kw = bytes(text[off[41000] + 3: off[41000] + 7])
+    assert np.array_equal(ix.query_array(kw), oracle.port.query(text, off, ids, sa, bits1, kw))
+    ix.close()
