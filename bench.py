@@ -845,7 +845,9 @@ def filter_leg(ix, pat, poff, npat, steps):
     for _ in range(steps):
         d2h, tot, _f = one()
     dt = time.perf_counter() - t0
+    lst = cdb.last_locate_stats()  # the id-ordered locate inside the last call
     return {"value": npat * steps / dt, "ms_per_step": dt / steps * 1e3,
+            "locate_phases_ms": {k: lst[k] for k in ("search_ms", "gather_ms", "translate_ms", "total_ms")},
             "h2d_bytes_per_step": int(kw.nbytes + terms.nbytes + rto.nbytes + span.nbytes), "d2h_bytes_per_step": int(d2h),
             "pairs_returned_per_step": int(tot), "launches_per_step": (cdb.launch_count() - launches0) // steps,
             "call": f"cdb_filter: {npat} requests {{key: keyword, span: [{FILTER_SPAN[0]},{FILTER_SPAN[1]})}} -> (id, $correlation) in "

@@ -49,7 +49,7 @@ class Result(C.Structure):
 class DeviceResult(C.Structure):
     _fields_ = [("npat", C.c_int64), ("total_pairs", C.c_int64), ("total_occurrences", C.c_int64),
                 ("row_off", C.c_void_p), ("pairs", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
-                ("_owner", C.c_void_p)]
+                ("stats32", C.c_void_p), ("_owner", C.c_void_p)]
 
 
 class Spans(C.Structure):

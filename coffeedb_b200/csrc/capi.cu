@@ -3,6 +3,7 @@
 // exact text (src/index.cpp:196,199,240).
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -15,6 +16,7 @@
 #include "index.cuh"
 #include "locate.cuh"
 #include "persist.cuh"
+#include "sharded.cuh"
 #include "verify.cuh"
 
 namespace cdb {
@@ -33,6 +35,8 @@ void Index::free_device() {
     if (d_ptab) cudaFree(d_ptab);
     if (d_rank_tab) cudaFree(d_rank_tab);
     if (d_ids_by_rank) cudaFree(d_ids_by_rank);
+    if (d_sa_rank) cudaFree(d_sa_rank);
+    d_sa_rank = nullptr;
     d_ptab = nullptr;
     d_rank_tab = nullptr;
     d_ids_by_rank = nullptr;
@@ -520,6 +524,91 @@ cdb_status cdb_build_stats(const cdb_index* h, double* total_ms, double* sort_ms
     CDB_CATCH
 }
 
+// ---- one index over several devices of this process (sharded.cu) -----------------------------------------------------------
+cdb_status cdb_sharded_create(const int32_t* devices, int32_t ndev, const cdb_options* opts, cdb_sharded** out) {
+    CDB_TRY
+    if (!out || !devices || ndev < 1 || ndev > 64) throw Error(CDB_ERR_ARG, "cdb_sharded_create: bad argument");
+    *out = reinterpret_cast<cdb_sharded*>(sharded_create(devices, ndev, opts));
+    return CDB_OK;
+    CDB_CATCH
+}
+
+void cdb_sharded_destroy(cdb_sharded* s) { sharded_destroy(reinterpret_cast<ShardedIndex*>(s)); }
+
+cdb_status cdb_sharded_add_many(cdb_sharded* h, const int64_t* ids, const void* text, const int64_t* doc_off, int64_t nd) {
+    CDB_TRY
+    if (!h || nd < 0 || (nd > 0 && (!ids || !doc_off))) throw Error(CDB_ERR_ARG, "cdb_sharded_add_many: bad argument");
+    if (nd == 0) return CDB_OK;
+    if (doc_off[0] < 0) throw Error(CDB_ERR_ARG, "cdb_sharded_add_many: doc_off[0] must be >= 0");
+    for (i64 d = 1; d <= nd; ++d)
+        if (doc_off[d] < doc_off[d - 1]) throw Error(CDB_ERR_ARG, "cdb_sharded_add_many: doc_off must be non-decreasing");
+    if (doc_off[nd] > doc_off[0] && !text) throw Error(CDB_ERR_ARG, "cdb_sharded_add_many: text is NULL");
+    sharded_add_many(reinterpret_cast<ShardedIndex*>(h), ids, static_cast<const u8*>(text), doc_off, nd);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_sharded_add(cdb_sharded* h, int64_t id, const void* value, int64_t len) {
+    const int64_t off[2] = {0, len};
+    if (len < 0) {
+        g_last_error = "cdb_sharded_add: bad argument";
+        return CDB_ERR_ARG;
+    }
+    return cdb_sharded_add_many(h, &id, value, off, 1);
+}
+
+cdb_status cdb_sharded_build(cdb_sharded* h) {
+    CDB_TRY
+    if (!h) throw Error(CDB_ERR_ARG, "cdb_sharded_build: index is NULL");
+    require_device();
+    sharded_build(reinterpret_cast<ShardedIndex*>(h));
+    return CDB_OK;
+    CDB_CATCH
+}
+
+int32_t cdb_sharded_count(const cdb_sharded* h) { return h ? sharded_count(reinterpret_cast<const ShardedIndex*>(h)) : 0; }
+
+cdb_status cdb_sharded_shard(const cdb_sharded* h, int32_t g, cdb_index** shard, int64_t* doc_begin, int64_t* doc_end) {
+    CDB_TRY
+    if (!h || !shard) throw Error(CDB_ERR_ARG, "cdb_sharded_shard: bad argument");
+    *shard = sharded_shard(reinterpret_cast<const ShardedIndex*>(h), g, doc_begin, doc_end);
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_sharded_locate_batch(const cdb_sharded* h, const void* pat, const int64_t* pat_off, int64_t npat, cdb_result* out) {
+    CDB_TRY
+    if (!h || !out || npat < 0 || (npat > 0 && !pat_off)) throw Error(CDB_ERR_ARG, "cdb_sharded_locate_batch: bad argument");
+    std::memset(out, 0, sizeof(*out));
+    for (i64 q = 0; q < npat; ++q)  // src/index.cpp:239-241
+        if (pat_off[q + 1] <= pat_off[q]) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
+    HostResultOwner* own = new HostResultOwner{nullptr, 0, nullptr, 0};
+    i64 total_pairs = 0, total_occ = 0;
+    try {
+        sharded_locate(const_cast<ShardedIndex*>(reinterpret_cast<const ShardedIndex*>(h)), static_cast<const u8*>(pat), pat_off, npat,
+                       [&](i64 total, i64** row_off, i64** pairs) {
+                           own->row_off = g_pinned.get((size_t)(npat + 1) * 8, &own->row_cap);
+                           own->pairs = g_pinned.get((size_t)(total ? total : 1) * 16, &own->pairs_cap);
+                           *row_off = (i64*)own->row_off;
+                           *pairs = (i64*)own->pairs;
+                       },
+                       &total_pairs, &total_occ);
+    } catch (...) {
+        if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+        if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+        delete own;
+        throw;
+    }
+    out->npat = npat;
+    out->total_pairs = total_pairs;
+    out->total_occurrences = total_occ;
+    out->row_off = (const i64*)own->row_off;
+    out->pairs = (const i64*)own->pairs;
+    out->_owner = own;
+    return CDB_OK;
+    CDB_CATCH
+}
+
 // ---- filter() (filter.cu) ------------------------------------------------------------------------------------------------
 cdb_status cdb_numeric_create(int32_t kind, const int64_t* ids, const void* values, int64_t n, int32_t device, cdb_numeric** out) {
     CDB_TRY
@@ -608,7 +697,10 @@ cdb_status cdb_filter(const cdb_filter_batch* b, cdb_filter_result* out) {
     FilterOwner* own = new FilterOwner();
     try {
         FilterOut fo;
+        const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
         filter_batch_device(*b, st, fo);
+        auto t1 = std::chrono::steady_clock::now();
         own->p[0] = g_pinned.get((size_t)(nreq + 1) * 8, &own->cap[0]);
         own->p[1] = g_pinned.get((size_t)(fo.total_fin ? fo.total_fin : 1) * 16, &own->cap[1]);
         own->p[2] = g_pinned.get((size_t)(nreq ? nreq : 1) * 8, &own->cap[2]);
@@ -618,6 +710,10 @@ cdb_status cdb_filter(const cdb_filter_batch* b, cdb_filter_result* out) {
         if (fo.total_fin) CDB_CUDA(cudaMemcpyAsync(pr, fo.fin.p, (size_t)fo.total_fin * 16, cudaMemcpyDeviceToHost, st));
         if (nreq) CDB_CUDA(cudaMemcpyAsync(own->p[2], fo.matched.p, (size_t)nreq * 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaStreamSynchronize(st));
+        if (dbg)
+            fprintf(stderr, "[cdb_filter] device %.3f ms, result buffers + copy to the host %.3f ms (%lld pairs)\n",
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), (long long)fo.total_fin);
         // Requests that did not fit the warp path: their id-ascending survivors come back whole and get the reference's own
         // final step here — the std::sort of src/interface.cpp:143-146 and the span of :196-209.
         std::vector<std::pair<int64_t, int64_t>> v;
@@ -690,6 +786,7 @@ void cdb_device_result_free(cdb_device_result* r) {
     if (r->pairs) cudaFreeAsync(r->pairs, st);
     if (r->left) cudaFreeAsync(r->left, st);
     if (r->right) cudaFreeAsync(r->right, st);
+    if (r->stats32) cudaFreeAsync(r->stats32, st);
     std::memset(r, 0, sizeof(*r));
 }
 

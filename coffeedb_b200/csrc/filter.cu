@@ -21,6 +21,8 @@
 //   (capi.cu: cdb_filter) — VERDICT r1 item 4: "keep that one std::sort on the host over the reduced list".
 // Integer work throughout; bound by the locate underneath it and by the PCIe copy of the slices.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -391,6 +393,51 @@ __device__ __forceinline__ void filter_request(const FArgs& A, i64 r, i64* key, 
     G::sync();
     const u64 T = tm.base[tm.nstr];
     const int nstr = tm.nstr;
+    const bool has_corr = A.corr != nullptr;
+    // ---- one keyword, no other condition (the usual request): the row IS the id-ascending answer.  Nothing is staged;
+    // the counts are read once to see whether they all tie, and the span is cut straight out of the row.
+    if (!BIG && nstr == 1 && tm.nnum == 0 && !has_corr) {
+        const i64* row = tm.row[0];
+        const u64 n = T;
+        u64 sb, se;
+        request_span(A, r, n, &sb, &se);
+        if (tid == 0) {
+            A.matched[r] = n;
+            A.fin_len[r] = se - sb;
+            A.raw_len[r] = se - sb;
+        }
+        if (se <= sb) return;
+        i64 mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
+        for (u64 i = tid; i < n; i += G::NT) {
+            const i64 c = __ldg(row + 2 * i + 1);
+            mn = c < mn ? c : mn;
+            mx = c > mx ? c : mx;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const i64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
+        }
+        i64* out = A.raw + 2 * A.raw_off[r];
+        if (mn == mx) {
+            const u16* src = A.pi + n * (n - 1) / 2;
+            for (u64 j = sb + tid; j < se; j += G::NT)
+                *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)src[j]);
+        } else {
+            for (u64 i = tid; i < n; i += G::NT) {
+                cnt[i] = (CntT)__ldg(row + 2 * i + 1);
+                perm[i] = (u16)i;
+            }
+            G::sync();
+            if (tid == 0)
+                coffeedb_b200::sort_order::std_sort_order(perm, (int)n, [cnt](u16 a, u16 b) { return cnt[a] > cnt[b]; });
+            G::sync();
+            for (u64 j = sb + tid; j < se; j += G::NT)
+                *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)perm[j]);
+        }
+        return;
+    }
     // ---- merge by ranking: entry (term j, index i) goes to i + sum over the other terms of the entries ordered before it
     for (u64 e = tid; e < T; e += G::NT) {
         int j = 0;
@@ -419,7 +466,6 @@ __device__ __forceinline__ void filter_request(const FArgs& A, i64 r, i64* key, 
     G::sync();
     // ---- fold equal ids, test the keys, compact in place (a survivor never moves to a higher index)
     i64 cL = 0, cR = 0;
-    const bool has_corr = A.corr != nullptr;
     if (has_corr) {
         cL = A.corr[2 * r];
         cR = A.corr[2 * r + 1];
@@ -647,6 +693,15 @@ int filter_device_of(const cdb_filter_batch& b) {
 }
 
 void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& o) {
+    const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cdb_filter] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     const i64 nreq = b.nreq;
     const i64 nterm = nreq ? b.req_term_off[nreq] - b.req_term_off[0] : 0;
     if (b.nkeys < 0 || b.nkeys > kFMaxKeys) throw Error(CDB_ERR_ARG, "cdb_filter: at most 32 keys per batch");
@@ -681,6 +736,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         CDB_CUDA(cudaMemcpyAsync(d_span.p, b.span, (size_t)nreq * 16, cudaMemcpyHostToDevice, st));
     }
     CDB_CUDA(cudaMemsetAsync(d_term_row.p, 0, d_term_row.bytes(), st));
+    lap("upload of the batch");
     DevBuf<int> d_err(1, st);
     CDB_CUDA(cudaMemsetAsync(d_err.p, 0, 4, st));
     // ---- one id-ordered locate per string key
@@ -727,9 +783,11 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
                                                        d_err.p);
                 CDB_LAUNCH_CHECK();
                 CDB_CUDA(cudaMemcpyAsync(poff.p + nkw, len.p + nterm, 8, cudaMemcpyDeviceToDevice, st));
+                lap("keywords of one key packed");
                 locate_device(*ix, pat.p, poff.p, nkw, st, &results[k], /*id_order=*/true);  // throws on an empty keyword
                 F.row_off = results[k].row_off;
                 F.pairs = results[k].pairs;
+                lap("locate in id order");
             }
         }
         DevBuf<FKeyDev> d_keys(hkeys.size(), st);
@@ -767,6 +825,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         CDB_CUDA(cudaMemcpyAsync(&tot[1], d_tbig.p + nreq, 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaStreamSynchronize(st));
+        lap("sizes and classes");
         if (herr == 1) throw Error(CDB_ERR_ARG, "cdb_filter: a request has more than 64 terms");
         if (herr) throw Error(CDB_ERR_ARG, "cdb_filter: a term names a key, range or keyword outside the batch");
         std::vector<i64> big, num;
@@ -788,6 +847,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
             filter_warp_kernel<<<(unsigned)ceil_div(nreq, kFWarps), kFWarps * 32, smem, st>>>(A);
             CDB_LAUNCH_CHECK();
         }
+        lap("warp-path merges");
         DevBuf<i64> d_big, scr_key, scr_cnt;
         DevBuf<u8> scr_ks;
         if (!big.empty()) {
@@ -813,6 +873,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
             numscan_finish_kernel<<<1, 1, 0, st>>>(A, r, blk.p + nb);
             CDB_LAUNCH_CHECK();
         }
+        lap("CTA-path merges, numeric scans");
         // ---- compact result: finished rows move to their final place, pending rows (CTA path, numeric-only) keep a hole
         prim::exclusive_scan<u64>(d_fin_len.p, o.fin_off.p, (u64)nreq, st);
         CDB_CUDA(cudaMemcpyAsync(&o.total_fin, o.fin_off.p + nreq, 8, cudaMemcpyDeviceToHost, st));
@@ -821,6 +882,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         compact_kernel<<<(unsigned)ceil_div(nreq * 32, 256), 256, 0, st>>>(A, o.fin_off.p, o.fin.p);
         CDB_LAUNCH_CHECK();
         CDB_CUDA(cudaStreamSynchronize(st));  // the temporaries of this call go back to the pool after their last use
+        lap("compaction");
         o.pending = big;
         o.pending.insert(o.pending.end(), num.begin(), num.end());
         std::sort(o.pending.begin(), o.pending.end());

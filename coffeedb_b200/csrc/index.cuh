@@ -66,6 +66,7 @@ struct Index {
     mutable int ids_order = -1;
     mutable u32* d_rank_tab = nullptr;
     mutable i64* d_ids_by_rank = nullptr;
+    mutable u32* d_sa_rank = nullptr;  // rank companion of the suffix array (locate.cu: id_order_tables), when memory allows
     // cdb_query's coalescing queue (capi.cu), created on first use
     mutable std::mutex batcher_mu;
     mutable std::shared_ptr<void> batcher;

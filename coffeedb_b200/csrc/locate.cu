@@ -598,15 +598,31 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5
     const u32* const remap = REMAP ? remap_arg : nullptr;  // compiled out of the doc-order kernel (its register budget is tight)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 q = (i64)blockIdx.x * kTileWarps + warp;
+    // Short-row variants (MAXR <= 8: the shards of a split corpus, long keywords) run as a persistent grid: a warp walks
+    // the patterns q, q + stride, ... and has the next pattern's interval and row offset in flight while it sorts the
+    // current one — with one CTA per 8 patterns the kernel was bound by CTA turnover and three dependent round trips
+    // per warp (0.94 ms per 10^6 rows of ~100 entries).  The long-row variants keep one pattern per warp.
+    constexpr bool LOOP = MAXR <= 8;
+    const i64 stride = LOOP ? (i64)gridDim.x * kTileWarps : npat;
+    i64 q = (i64)blockIdx.x * kTileWarps + warp;
     if (q >= npat) return;
     u32* s_doc = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<MAXR>());
     u32* s_pos = s_doc + 32 * MAXR + 32;
+    i64 l = left[q], rgt = right[q];
+    u64 row = alloc_off[q];
+    for (;;) {
+    i64 l_next = 0, rgt_next = 0;
+    u64 row_next = 0;
+    const i64 q_next = q + stride;
+    if (LOOP && q_next < npat) {
+        l_next = left[q_next];
+        rgt_next = right[q_next];
+        row_next = alloc_off[q_next];
+    }
     int nheads = 0;
     bool all_distinct = false;
     u64 d = 0;
-    const i64 l = left[q];
-    const i64 occ64 = right[q] - l;
+    const i64 occ64 = rgt - l;
     if (occ64 > kWarpCap) {
         d = dlarge[q];
     } else if (occ64 > 0) {
@@ -637,10 +653,16 @@ __global__ void __launch_bounds__(kTileWarps * 32, MAXR <= 4 ? 6 : MAXR == 8 ? 5
         }
     }
     // compact row: coalesced 4-byte doc stores (+ 2-byte counts for the rare rows with repeats)
-    const u64 row = alloc_off[q];
     for (int r = lane; r < nheads; r += 32) st_stream_u32(cdocs + row + r, s_doc[pad_idx(r)]);
     if (!all_distinct)
         for (int r = lane; r < nheads; r += 32) ccnt[row + r] = (u16)(s_pos[pad_idx(r + 1)] - s_pos[pad_idx(r)]);
+    if (!LOOP || q_next >= npat) break;
+    q = q_next;
+    l = l_next;
+    rgt = rgt_next;
+    row = row_next;
+    __syncwarp();  // s_doc / s_pos are reused by the next pattern
+    }
 }
 
 // Phase B.  pairs[i] = (ids[doc_i], count_i) for every compact entry i.  ids[] (8 bytes per document, 800 MB at the
@@ -828,7 +850,7 @@ static int bits_for_u64(u64 v) {
 }
 
 // resident CTAs per SM of a kernel (its persistent grids are exactly one wave), cached per kernel and device
-static int resident_ctas(const void* kernel, int threads) {
+static int resident_ctas(const void* kernel, int threads, size_t smem = 0) {
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, int> cache;
     int dev = 0;
@@ -837,7 +859,7 @@ static int resident_ctas(const void* kernel, int threads) {
     auto it = cache.find({kernel, dev});
     if (it != cache.end()) return it->second;
     int v = 0;
-    CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, 0));
+    CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem));
     v = v > 0 ? v : 1;
     cache[{kernel, dev}] = v;
     return v;
@@ -885,6 +907,23 @@ __global__ void rank_scatter_kernel(const u64* __restrict__ keys, const u32* __r
     }
 }
 
+template <typename SAT>
+__global__ void __launch_bounds__(256) sa_rank_kernel(const SAT* __restrict__ sa, u64 mask, const u32* __restrict__ rank_tab, i64 n,
+                                                      u32* __restrict__ out) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+        u32 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = i + u * stride < n ? (u32)((u64)ld_stream(sa + i + u * stride) & mask) : 0u;
+        u32 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(rank_tab + d[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n) out[i + u * stride] = v[u];
+    }
+}
+
 // Examines the ids once per built index.  Returns true when the rows have to be re-keyed (ids do not ascend with the
 // doc index): rank_tab / ids_by_rank are then filled.  Ids are assumed distinct, as the reference's are (object ids).
 static bool id_order_tables(const Index& ix, cudaStream_t st) {
@@ -910,10 +949,45 @@ static bool id_order_tables(const Index& ix, cudaStream_t st) {
             rank_scatter_kernel<<<grid, 256, 0, st>>>(cur ? k1.p : k0.p, cur ? v1.p : v0.p, nd, ix.d_rank_tab, ix.d_ids_by_rank);
             CDB_LAUNCH_CHECK();
             CDB_CUDA(cudaStreamSynchronize(st));
+            // Rank companion of the suffix array: sa_rank[i] = rank_tab[sa[i] & mask], 4 bytes per suffix.  With it an
+            // id-ordered gather reads a plain contiguous interval (half the bytes of the packed array's) instead of one
+            // random rank_tab lookup per occurrence (measured at the 10 GB configuration: 28 ms against 3.7 ms per 10^6
+            // keywords).  Only taken when it leaves a quarter of the device memory free for the query temporaries.
+            const char* ec = getenv("CDB_SA_RANK_COMPANION");
+            if (ix.n > 0 && (!ec || atoi(ec) != 0)) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, ix.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+                size_t free_b = 0, total_b = 0;
+                CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                const size_t need = (size_t)ix.n * 4;
+                if (free_b > need && free_b - need >= total_b / 4 && cudaMalloc((void**)&ix.d_sa_rank, need) == cudaSuccess) {
+                    const int g = num_sms() * 16;
+                    if (ix.width == 4)
+                        sa_rank_kernel<u32><<<g, 256, 0, st>>>(reinterpret_cast<const u32*>(ix.d_sa), ix.mask, ix.d_rank_tab, ix.n, ix.d_sa_rank);
+                    else
+                        sa_rank_kernel<u64><<<g, 256, 0, st>>>(reinterpret_cast<const u64*>(ix.d_sa), ix.mask, ix.d_rank_tab, ix.n, ix.d_sa_rank);
+                    CDB_LAUNCH_CHECK();
+                    CDB_CUDA(cudaStreamSynchronize(st));
+                } else {
+                    cudaGetLastError();
+                    ix.d_sa_rank = nullptr;
+                }
+            }
         }
         ix.ids_order = h ? 0 : 1;
     }
     return ix.ids_order == 0;
+}
+
+// per-pattern (row length, occurrences) as 32-bit integers, [2][npat]: what a sharded index exchanges per batch
+__global__ void stats32_kernel(const u64* __restrict__ row_off, const i64* __restrict__ left, const i64* __restrict__ right,
+                               i64 npat, int32_t* __restrict__ stats) {
+    const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    const u64 rl = row_off[q + 1] - row_off[q];
+    const i64 oc = right[q] - left[q];
+    stats[q] = rl > 0x7fffffffull ? 0x7fffffff : (int32_t)rl;
+    stats[npat + q] = oc > 0x7fffffffll ? 0x7fffffff : (int32_t)oc;
 }
 
 // ---- host driver ------------------------------------------------------------------------------------------------
@@ -924,10 +998,14 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     // id order: keys are id ranks (rank_tab) and the table translate reads is ids_by_rank; when the ids already ascend with
     // the doc index both orders coincide and nothing changes
     const u32* remap = nullptr;
+    const u32* sa_rank = nullptr;
     const i64* ids_tab = ix.d_ids;
     if (id_order && id_order_tables(ix, st)) {
-        remap = ix.d_rank_tab;
         ids_tab = ix.d_ids_by_rank;
+        if (ix.d_sa_rank)
+            sa_rank = ix.d_sa_rank;  // sa_rank[i] = rank of the id of the document suffix i belongs to
+        else
+            remap = ix.d_rank_tab;   // no room for the companion: the ranks are looked up per occurrence (slower)
     }
     const i64 ntiles = ceil_div(npat, kTileWarps);
     DevBuf<i64> left(npat, st), right(npat, st);
@@ -990,7 +1068,11 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
             CDB_CUDA(cudaMemcpyAsync(loff.p, h_loff.data(), (lc.nlc + 1) * 8, cudaMemcpyHostToDevice, st));
             DevBuf<u64> k0(lc.ltotal, st), k1(lc.ltotal, st);
             const int grid = (int)std::min<i64>(ceil_div((i64)lc.ltotal, 256), kNumSMs * 16);
-            large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal, k0.p, remap);
+            if (sa_rank)
+                large_expand_kernel<u32><<<grid, 256, 0, st>>>(sa_rank, 0xffffffffull, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal,
+                                                               k0.p, nullptr);
+            else
+                large_expand_kernel<SAT><<<grid, 256, 0, st>>>(sa, ix.mask, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal, k0.p, remap);
             CDB_LAUNCH_CHECK();
             int cbuf = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, lc.ltotal, 0,
                                                          32 + bits_for_u64(lc.nlc - 1), st);
@@ -1044,10 +1126,24 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     auto launch_gather = [&](auto maxr_tag) {
         constexpr int MAXR = decltype(maxr_tag)::value;
         const size_t smem = (size_t)kTileWarps * warp_smem_bytes<MAXR>();
+        if (sa_rank) {  // id order from the rank companion of the suffix array: a plain u32 array, nothing to look up
+            auto kernel = gather_kernel<u32, MAXR, false>;
+            if (smem > 48 * 1024) CDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            i64 grid = ntiles;
+            if (MAXR <= 8) grid = std::min<i64>(ntiles, (i64)num_sms() * resident_ctas((const void*)kernel, kTileWarps * 32, smem));
+            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa_rank, 0xffffffffull, bucket_mul, left.p, right.p, npat, dlarge.p,
+                                                                 alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, nullptr);
+            return;
+        }
         auto go = [&](auto kernel) {
             if (smem > 48 * 1024) CDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<(unsigned)ntiles, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p, alloc_off.p,
-                                                                   row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, remap);
+            i64 grid = ntiles;
+            if (MAXR <= 8) {  // persistent grid: one wave of resident CTAs
+                const int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32, smem);
+                grid = std::min<i64>(ntiles, (i64)num_sms() * per_sm);
+            }
+            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p, alloc_off.p,
+                                                                 row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, remap);
         };
         if (remap)
             go(gather_kernel<SAT, MAXR, true>);
@@ -1083,6 +1179,9 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
                                                 row_off.p, ids_tab, pairs.p);
         CDB_LAUNCH_CHECK();
     }
+    DevBuf<int32_t> stats((size_t)npat * 2, st);
+    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, stats.p);
+    CDB_LAUNCH_CHECK();
     u64 total_pairs = 0;
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(ev[6], st));
@@ -1107,6 +1206,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     out->pairs = pairs.detach();
     out->left = left.detach();
     out->right = right.detach();
+    out->stats32 = stats.detach();
     out->_owner = (void*)st;
 }
 

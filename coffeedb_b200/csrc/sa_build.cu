@@ -433,6 +433,78 @@ __global__ void apply_perm_kernel(const u32* __restrict__ perm2, const u64* __re
     chunk_vals[widx[j]] = v;
 }
 
+// ---- prefix doubling over the ties that survive the extension rounds -------------------------------------------------------
+// Key extension adds S symbols per round: two byte-identical 64 KB documents would need ~8 000 rounds.  After
+// kExtensionRounds of them a chunk hands its remaining ties over; once every chunk is in place the inverse suffix
+// array rank[text position] is built (own rank for settled suffixes, rank of the group's first member for tied ones)
+// and the groups are refined by rank doubling: suffixes that share their first h symbols are ordered by the rank of the
+// suffix h symbols further on (Manber-Myers / Larsson-Sadakane), h doubling per level — O(log maxlen) levels.  The sorts,
+// the scatter into the array and the tie detection are the extension rounds' own.
+constexpr int kExtensionRounds = 4;
+
+template <typename P>
+struct PendingTies {
+    DevBuf<u32> widx, gid;  // chunk-relative suffix-array slot and group number of every tied suffix, in array order
+    DevBuf<P> pay;          // its packed element
+    u64 wm = 0, ngroups = 0;
+    P* vals = nullptr;      // the chunk's range of the suffix array
+    i64 base = 0;           // rank of vals[0] in the whole array
+};
+
+template <typename P>
+__device__ __forceinline__ i64 text_pos(P packed, u64 mask, int bits1, const i64* __restrict__ doc_off, i64* rem) {
+    const u64 p = (u64)packed;
+    const i64 d = (i64)(p & mask), off = (i64)(p >> bits1);
+    const i64 ds = __ldg(doc_off + d), de = __ldg(doc_off + d + 1);
+    *rem = de - ds - off;
+    return ds + off;
+}
+
+template <typename P>
+__global__ void isa_init_kernel(const P* __restrict__ sa, i64 n, u64 mask, int bits1, const i64* __restrict__ doc_off,
+                                u64* __restrict__ rank) {
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
+        i64 rem;
+        rank[text_pos<P>(sa[j], mask, bits1, doc_off, &rem)] = (u64)j;
+    }
+}
+
+// head[j] = 1 when worklist slot j starts a group (same group number AND same key as its predecessor = same group)
+__global__ void group_heads_kernel(const u32* __restrict__ gid, const u64* __restrict__ keys, u64 m, u8* __restrict__ head) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    head[j] = (j == 0 || gid[j] != gid[j - 1] || (keys && keys[j] != keys[j - 1])) ? 1 : 0;
+}
+__global__ void group_first_kernel(const u8* __restrict__ head, const u64* __restrict__ ord, u64 m, u32* __restrict__ first) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m && head[j]) first[ord[j]] = (u32)j;
+}
+// rank of every worklist member = rank of its group's first member
+template <typename P>
+__global__ void group_rank_kernel(const u8* __restrict__ head, const u64* __restrict__ ord, const u32* __restrict__ first,
+                                  const u32* __restrict__ widx, const P* __restrict__ pay, u64 m, i64 base, u64 mask, int bits1,
+                                  const i64* __restrict__ doc_off, u64* __restrict__ rank) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const u64 g = ord[j] + head[j] - 1;
+    i64 rem;
+    rank[text_pos<P>(pay[j], mask, bits1, doc_off, &rem)] = (u64)base + widx[first[g]];
+}
+
+// doubling key of a tied suffix whose group shares `depth` symbols: ended before that -> its group is byte-identical and
+// the canonical order is the packed value (note N2); ended exactly there -> first (end-of-document is the smallest
+// symbol); otherwise 1 + rank of the suffix `depth` symbols further on (same document, so the rank exists)
+template <typename P>
+__global__ void rankkey_kernel(const P* __restrict__ pay, u64 m, const i64* __restrict__ doc_off, int bits1, u64 mask, i64 depth,
+                               const u64* __restrict__ rank, u64* __restrict__ keys, u32* __restrict__ iota) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    i64 rem;
+    const i64 pos = text_pos<P>(pay[j], mask, bits1, doc_off, &rem);
+    keys[j] = rem < depth ? (u64)pay[j] : (rem == depth ? 0ull : 1ull + rank[pos + depth]);
+    iota[j] = (u32)j;
+}
+
 // ---- host driver ------------------------------------------------------------------------------------------------
 static int bits_for(u64 v) {  // number of bits needed to represent values 0..v
     int b = 1;
@@ -487,7 +559,7 @@ struct ChunkSorter {
 
     // Sorts the m (key, packed) pairs in (k[0], v[0]) completely; returns where the finished suffix-array slice is:
     // `dest` when given (the last radix pass scatters straight into it), else one of v[0] / v[1].
-    P* run(u64* k[2], P* v[2], u64 m, P* dest = nullptr) {
+    P* run(u64* k[2], P* v[2], u64 m, P* dest = nullptr, std::vector<PendingTies<P>>* pending = nullptr, i64 base = 0) {
         const int keybits = b * S;
         timers.begin(st);
         bool used = false;
@@ -507,7 +579,21 @@ struct ChunkSorter {
         i64 depth = S0;
         const int tiebits = ix.bits1 + ix.bits2;
         const int sortbits = keybits > tiebits ? keybits : tiebits;
+        int ext_rounds = 0;
         while (wm > 0) {
+            if (pending && ext_rounds == kExtensionRounds) {  // long repeats: the rest is refined by rank doubling
+                pending->emplace_back();
+                PendingTies<P>& pt = pending->back();
+                pt.widx = std::move(widx);
+                pt.gid = std::move(gid);
+                pt.pay = std::move(pay);
+                pt.wm = wm;
+                pt.ngroups = ngroups;
+                pt.vals = vals;
+                pt.base = base;
+                break;
+            }
+            ++ext_rounds;
             ix.rounds++;
             const unsigned gb = (unsigned)ceil_div((i64)wm, 256);
             DevBuf<u64> nk(wm, st), nk2(wm, st);
@@ -573,6 +659,83 @@ struct ChunkSorter {
         ties_write_kernel<HasGid, P><<<(unsigned)nb, TC_THREADS, 0, st>>>(keys, gid_in, widx_in, pay_in, m, bsum.p,
                                                                         widx.p, pay.p, gid.p);
         CDB_LAUNCH_CHECK();
+    }
+
+    // ranks of all members of one worklist (slots in array order, groups = runs of equal (gid, key)) -> rank[]
+    void write_group_ranks(const PendingTies<P>& pt, const u32* widx, const u32* gid, const u64* keys, const P* pay, u64 wm,
+                           u64* rank) {
+        const unsigned gb = (unsigned)ceil_div((i64)wm, 256);
+        DevBuf<u8> head(wm, st);
+        DevBuf<u64> ord(wm + 1, st);
+        DevBuf<u32> first(wm, st);
+        group_heads_kernel<<<gb, 256, 0, st>>>(gid, keys, wm, head.p);
+        CDB_LAUNCH_CHECK();
+        prim::exclusive_scan<u8>(head.p, ord.p, wm, st);
+        group_first_kernel<<<gb, 256, 0, st>>>(head.p, ord.p, wm, first.p);
+        CDB_LAUNCH_CHECK();
+        group_rank_kernel<P><<<gb, 256, 0, st>>>(head.p, ord.p, first.p, widx, pay, wm, pt.base, ix.mask, ix.bits1, ix.d_off, rank);
+        CDB_LAUNCH_CHECK();
+    }
+
+    // Rank doubling over the ties every chunk handed over (all of them share `depth` symbols inside their groups).
+    // sa = the whole suffix array, complete up to the order inside those groups.
+    void finish_by_doubling(std::vector<PendingTies<P>>& pending, const P* sa, i64 depth) {
+        if (pending.empty()) return;
+        const i64 n = ix.n;
+        BigBuf<u64> rank((size_t)n + 1);
+        isa_init_kernel<P><<<kNumSMs * 16, 256, 0, st>>>(sa, n, ix.mask, ix.bits1, ix.d_off, rank.p);
+        CDB_LAUNCH_CHECK();
+        for (PendingTies<P>& pt : pending) write_group_ranks(pt, pt.widx.p, pt.gid.p, nullptr, pt.pay.p, pt.wm, rank.p);
+        const int tiebits = ix.bits1 + ix.bits2;
+        const int rankbits = bits_for((u64)n + 1);
+        const int sortbits = rankbits > tiebits ? rankbits : tiebits;
+        bool any = true;
+        while (any) {
+            any = false;
+            ix.rounds++;
+            for (PendingTies<P>& pt : pending) {
+                const u64 wm = pt.wm;
+                if (wm == 0) continue;
+                const unsigned gb = (unsigned)ceil_div((i64)wm, 256);
+                DevBuf<u64> nk(wm, st), nk2(wm, st);
+                DevBuf<u32> p0(wm, st), p1(wm, st);
+                rankkey_kernel<P><<<gb, 256, 0, st>>>(pt.pay.p, wm, ix.d_off, ix.bits1, ix.mask, depth, rank.p, nk.p, p0.p);
+                CDB_LAUNCH_CHECK();
+                timers.begin(st);
+                const int c1 = rs::radix_sort_pairs<u32>(nk.p, nk2.p, p0.p, p1.p, wm, 0, sortbits, st);
+                timers.end(st);
+                u64* ks = c1 ? nk2.p : nk.p;
+                u32* ps = c1 ? p1.p : p0.p;
+                u64* kfree = c1 ? nk.p : nk2.p;
+                u32* pfree = c1 ? p0.p : p1.p;
+                DevBuf<u64> gk(wm, st), gk2(wm, st);
+                DevBuf<u32> q1(wm, st);
+                gather_gid_kernel<<<gb, 256, 0, st>>>(pt.gid.p, ps, wm, gk.p, pfree);
+                CDB_LAUNCH_CHECK();
+                timers.begin(st);
+                const int c2 = rs::radix_sort_pairs<u32>(gk.p, gk2.p, pfree, q1.p, wm, 0, bits_for(pt.ngroups ? pt.ngroups - 1 : 0), st);
+                timers.end(st);
+                u32* perm2 = c2 ? q1.p : pfree;
+                DevBuf<P> pay2(wm, st);
+                apply_perm_kernel<P><<<gb, 256, 0, st>>>(perm2, ks, ps, pt.pay.p, pt.widx.p, wm, kfree, pay2.p, pt.vals);
+                CDB_LAUNCH_CHECK();
+                // every member's new rank (the groups just split), then the ties that are left
+                write_group_ranks(pt, pt.widx.p, pt.gid.p, kfree, pay2.p, wm, rank.p);
+                DevBuf<u32> widx2, gid2;
+                DevBuf<P> pay3;
+                u64 wm2 = 0, ng2 = 0;
+                compact<true>(kfree, pt.gid.p, pt.widx.p, pay2.p, wm, widx2, pay3, gid2, wm2, ng2);
+                pt.widx = std::move(widx2);
+                pt.gid = std::move(gid2);
+                pt.pay = std::move(pay3);
+                pt.wm = wm2;
+                pt.ngroups = ng2;
+                any = any || wm2 > 0;
+            }
+            depth *= 2;
+            if (depth > ((i64)1 << 62)) throw Error(CDB_ERR_STATE, "suffix-array build: rank doubling did not converge");
+        }
+        CDB_CUDA(cudaStreamSynchronize(st));
     }
 };
 
@@ -640,7 +803,15 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
         u64* k[2] = {k0.p, k1.p};
         P* v[2] = {v0.p, v1.p};
         ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
-        P* fin = cs.run(k, v, (u64)n);
+        std::vector<PendingTies<P>> pending;
+        P* fin = cs.run(k, v, (u64)n, nullptr, &pending, 0);
+        if (!pending.empty()) {
+            // the spare key / value buffers are not needed any more: their memory holds the inverse array
+            k0.release();
+            k1.release();
+            (fin == v1.p ? v0 : v1).release();
+            cs.finish_by_doubling(pending, fin, (i64)S0 + (i64)kExtensionRounds * S);
+        }
         CDB_CUDA(cudaStreamSynchronize(st));
         ix.d_sa = fin == v1.p ? (void*)v1.detach() : (void*)v0.detach();
         ix.sort_ms = timers.total_ms();
@@ -667,6 +838,7 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
                 cap * (16.0 + sizeof(P)) / 1e9,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
     unsigned long long* cursor = d_hist.p + nbuckets;
+    std::vector<PendingTies<P>> pending;
     i64 sa_base = 0;
     u32 blo = 0;
     while (blo < nbuckets) {
@@ -687,10 +859,18 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
             CDB_LAUNCH_CHECK();
             u64* k[2] = {k0.p, k1.p};
             ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
-            cs.run(k, v, (u64)cnt, slice);  // the chunk lands in its final suffix-array range
+            cs.run(k, v, (u64)cnt, slice, &pending, sa_base);  // the chunk lands in its final suffix-array range
             sa_base += cnt;
         }
         blo = bhi;
+    }
+    if (!pending.empty()) {
+        CDB_CUDA(cudaStreamSynchronize(st));
+        k0.release();
+        k1.release();
+        v0.release();
+        ChunkSorter<P> cs{ix, tab, b, S0, S, st, timers};
+        cs.finish_by_doubling(pending, sa.p, (i64)S0 + (i64)kExtensionRounds * S);
     }
     CDB_CUDA(cudaStreamSynchronize(st));
     ix.d_sa = (void*)sa.detach();

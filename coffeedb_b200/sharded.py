@@ -44,11 +44,32 @@ class ShardedResult:
     occurrences      int64 [npat]          total occurrences of every pattern over all shards
     """
 
-    def __init__(self, row_off, pairs, shard_rows, occurrences, rank, keep=None):
-        self.row_off, self.pairs, self.shard_rows, self.occurrences = row_off, pairs, shard_rows, occurrences
+    def __init__(self, row_off, pairs, shard_rows, occurrences, rank, keep=None, exchanged=None):
+        self.row_off, self.pairs = row_off, pairs
+        self._shard_rows, self._occ = shard_rows, occurrences
+        self._exchanged = exchanged  # [world, 2, npat] as it came out of the all_gather (widened on first use)
         self.rank = rank
         self._gro = None
         self._keep = keep  # owner of the device buffers row_off / pairs alias
+
+    @property
+    def shard_rows(self):
+        if self._shard_rows is None:
+            if self._exchanged is not None:
+                self._shard_rows = self._exchanged[:, 0, :].to(torch.int64)
+            else:  # one shard: nothing was exchanged
+                self._shard_rows = (self.row_off[1:] - self.row_off[:-1]).view(1, -1)
+        return self._shard_rows
+
+    @property
+    def occurrences(self):
+        """Total occurrences of every pattern over all shards = column sums of the exchanged counts."""
+        if self._occ is None:
+            if self._exchanged is not None:
+                self._occ = self._exchanged[:, 1, :].sum(dim=0, dtype=torch.int64)
+            else:
+                self._occ = self._local_occ()
+        return self._occ
 
     @property
     def global_row_off(self):
@@ -164,9 +185,9 @@ class ShardedStringIndex:
             tp = res.total_pairs
             pairs = (torch.as_tensor(_DevArray(res.pairs, 2 * tp), device=self.device).view(tp, 2) if tp
                      else torch.zeros((0, 2), dtype=torch.int64, device=self.device))
-            occ = (torch.as_tensor(_DevArray(res.right, npat), device=self.device)
-                   - torch.as_tensor(_DevArray(res.left, npat), device=self.device)) if npat else d_off[:0]
-            return row_off, pairs, occ, _ResultOwner(self.local, res)
+            # (row length, occurrences) of every pattern as 32-bit integers, written by the library: the exchange payload
+            stats = torch.as_tensor(_DevArray(res.stats32, 2 * npat, "<i4"), device=self.device) if npat and res.stats32 else None
+            return row_off, pairs, stats, _ResultOwner(self.local, res)
         # host engine (CPU tests inject one; the product StringIndex raises without a CUDA device)
         nbytes = int(d_off[-1]) if npat else 0
         ro, pr = self.local.locate_batch(d_pat[:nbytes].numpy(), d_off.numpy())
@@ -175,7 +196,8 @@ class ShardedStringIndex:
         occ = torch.zeros(npat, dtype=torch.int64)
         if len(pr):
             occ.index_add_(0, torch.repeat_interleave(torch.arange(npat), ro_t[1:] - ro_t[:-1]), torch.from_numpy(pr[:, 1].copy()))
-        return ro_t, torch.from_numpy(pr.copy()), occ, None
+        rows = ro_t[1:] - ro_t[:-1]
+        return ro_t, torch.from_numpy(pr.copy()), torch.stack([rows, occ]).reshape(-1), None
 
     def locate_batch(self, patterns=None, pat_off=None, src: int = 0, device_patterns=None) -> ShardedResult:
         """Collective.  `patterns` (list of bytes, or packed uint8 + offsets) is read on rank `src` only;
@@ -183,26 +205,55 @@ class ShardedStringIndex:
         if device_patterns is not None:
             d_pat, d_off = device_patterns
             if self.world > 1:
-                dist.broadcast(d_pat, self._global(src), group=self.group)
-                self._broadcast_offsets(d_off, d_pat.numel(), src)
+                d_pat, d_off = self._broadcast_device_patterns(d_pat, d_off, src)
         else:
             d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
         npat = d_off.numel() - 1
-        row_off, pairs, occ, keep = self.locate_local(d_pat, d_off)
-        rows = row_off[1:] - row_off[:-1]
-        if self.world > 1:
-            # ONE collective per batch: every shard's (row lengths, occurrences) per pattern.  The occurrence totals the
-            # reference's `count` needs are the column sums, so no separate all_reduce.
-            xdt = torch.int32 if self.narrow else torch.int64
-            mine = torch.stack([rows, occ]).reshape(-1).to(xdt)               # [2 * npat]
-            allst = torch.empty(self.world * 2 * npat, dtype=xdt, device=self.device)
-            dist.all_gather_into_tensor(allst, mine, group=self.group)
-            allst = allst.view(self.world, 2, npat)
-            shard_rows = allst[:, 0, :].to(torch.int64)
-            occ = allst[:, 1, :].sum(dim=0, dtype=torch.int64)
-        else:
-            shard_rows = rows.view(1, npat)
-        return ShardedResult(row_off, pairs, shard_rows, occ, self.rank, keep)
+        row_off, pairs, stats, keep = self.locate_local(d_pat, d_off)
+        if self.world == 1:  # nothing to exchange: per-pattern counts are derived from this shard's result on first use
+            res = ShardedResult(row_off, pairs, None, None, 0, keep)
+            dev, local_stats = self.device, stats
+            if keep is not None:
+                res._local_occ = lambda: (torch.as_tensor(_DevArray(keep.res.right, npat), device=dev)
+                                          - torch.as_tensor(_DevArray(keep.res.left, npat), device=dev)) if npat else d_off[:0]
+            else:
+                res._local_occ = lambda: local_stats[npat:].to(torch.int64)
+            return res
+        if stats is None:  # empty batch
+            stats = torch.zeros(2 * npat, dtype=torch.int32, device=self.device)
+        # ONE collective per batch: every shard's (row lengths, occurrences) per pattern, as the 32-bit integers the
+        # library wrote when every shard has < 2^31 suffixes (no element-wise work between the locate and the collective).
+        # The occurrence totals the reference's `count` needs are the column sums, so no separate all_reduce; shard_rows,
+        # occurrences and the global CSR offsets are derived from the gathered block on first use.
+        wide = not self.narrow
+        if wide and stats.dtype != torch.int64:  # a shard with >= 2^31 suffixes: counts may not fit 32 bits
+            rows = row_off[1:] - row_off[:-1]
+            occ = (torch.as_tensor(_DevArray(keep.res.right, npat), device=self.device)
+                   - torch.as_tensor(_DevArray(keep.res.left, npat), device=self.device)) if keep is not None else stats[npat:].to(torch.int64)
+            stats = torch.stack([rows, occ]).reshape(-1)
+        allst = torch.empty(self.world * 2 * npat, dtype=stats.dtype, device=self.device)
+        dist.all_gather_into_tensor(allst, stats.contiguous(), group=self.group)
+        allst = allst.view(self.world, 2, npat)
+        return ShardedResult(row_off, pairs, None, None, self.rank, keep, exchanged=allst)
+
+    def _broadcast_device_patterns(self, d_pat, d_off, src: int):
+        """One broadcast per batch: [pattern offsets as 4-byte integers | pattern bytes] in one buffer (batches of 2 GB
+        or more keep the two-broadcast path with 8-byte offsets)."""
+        nbytes, npat = d_pat.numel(), d_off.numel() - 1
+        if nbytes >= (1 << 31):
+            dist.broadcast(d_pat, self._global(src), group=self.group)
+            dist.broadcast(d_off, self._global(src), group=self.group)
+            return d_pat, d_off
+        head = 4 * (npat + 1)
+        buf = torch.empty(head + nbytes, dtype=torch.uint8, device=self.device)
+        if self.rank == src:
+            buf[:head].view(torch.int32).copy_(d_off)
+            buf[head:].copy_(d_pat)
+        dist.broadcast(buf, self._global(src), group=self.group)
+        if self.rank != src:
+            d_off.copy_(buf[:head].view(torch.int32))
+            d_pat = buf[head:]
+        return d_pat, d_off
 
     def gather_rows(self, res: ShardedResult, dst: int = 0):
         """Collective.  Assembles the flat answer on rank `dst`: (global_row_off, pairs) with row q = the shard rows of

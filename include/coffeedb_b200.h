@@ -70,6 +70,8 @@ typedef struct cdb_device_result {
     int64_t* pairs;   /* device [2*total_pairs] */
     int64_t* left;    /* device [npat]  SA interval [left,right) of every pattern (src/index.cpp:262-287) */
     int64_t* right;   /* device [npat] */
+    int32_t* stats32; /* device [2*npat]: row length, then occurrences, of every pattern as 32-bit integers (saturating) —
+                         what the shards of a split corpus exchange per batch */
     void* _owner;
 } cdb_device_result;
 
@@ -207,6 +209,27 @@ void cdb_spans_free(cdb_spans* s);
  * returns the rendered length (also when out is too small or NULL). */
 int64_t cdb_splice(const void* text, int64_t tlen, const int64_t* spans, int64_t nspans, const void* left, int64_t llen,
                    const void* right, int64_t rlen, void* out, int64_t out_cap);
+
+/* ---- one string_index over several GPUs of this process (SURVEY.md 8e behind the boundary) ----------------------------
+ * The reference is one process (src/database.cpp:170-282, 387-393); a sharded index therefore sits behind the same
+ * add / build / query calls.  Documents are cut into contiguous doc-index ranges of about equal bytes, one shard per entry
+ * of devices[] (an ordinal may repeat: several shards on one GPU), every shard is built by its own host thread, and a
+ * batch is located on all shards at once: the packed patterns are uploaded once and copied device-to-device, the shards
+ * exchange their per-pattern row offsets device-to-device and each writes its part of every row straight into the
+ * result — row q = the shard rows in shard order = ascending doc index = string_index::query on the whole corpus
+ * (src/index.cpp:316-322).  On corpora in the note-N1 layout (bytes on both sides of 0x80, SURVEY.md 8e "Exception") the
+ * answer is the per-shard reference answers concatenated, as with any sharded index. */
+typedef struct cdb_sharded cdb_sharded;
+cdb_status cdb_sharded_create(const int32_t* devices, int32_t ndev, const cdb_options* opts, cdb_sharded** out);
+void cdb_sharded_destroy(cdb_sharded* s);
+cdb_status cdb_sharded_add(cdb_sharded* s, int64_t id, const void* value, int64_t len);
+cdb_status cdb_sharded_add_many(cdb_sharded* s, const int64_t* ids, const void* text, const int64_t* doc_off, int64_t nd);
+cdb_status cdb_sharded_build(cdb_sharded* s);
+/* Batched string_index::query over all shards; the result is released with cdb_result_free. */
+cdb_status cdb_sharded_locate_batch(const cdb_sharded* s, const void* pat, const int64_t* pat_off, int64_t npat, cdb_result* out);
+/* Shard g (borrowed; valid until cdb_sharded_destroy) and the doc-index range [doc_begin, doc_end) it holds. */
+cdb_status cdb_sharded_shard(const cdb_sharded* s, int32_t g, cdb_index** shard, int64_t* doc_begin, int64_t* doc_end);
+int32_t cdb_sharded_count(const cdb_sharded* s);
 
 /* ---- filter(): set algebra over constraint results, on the device -----------------------------------
  * Replaces the body of filter() (src/interface.cpp:46-147) and what it calls: query(key, range) of string keys

@@ -99,12 +99,14 @@ def build_keys(objs, order):
     return keys
 
 
-@pytest.mark.parametrize("doc_order", ["id order", "shuffled"])
-def test_filter_equals_reference_server(reference_answers, doc_order):
+@pytest.mark.parametrize("doc_order", ["id order", "shuffled", "shuffled, ranks looked up"])
+def test_filter_equals_reference_server(reference_answers, doc_order, monkeypatch):
     objs, answers, counts = reference_answers
     order = list(range(N))
-    if doc_order == "shuffled":  # doc index != id order: the id-rank tables are used (locate.cu id_order_tables)
+    if doc_order != "id order":  # doc index != id order: the id-rank tables are used (locate.cu id_order_tables)
         random.Random(5).shuffle(order)
+    if doc_order == "shuffled, ranks looked up":  # without the rank companion of the suffix array (as when memory is short)
+        monkeypatch.setenv("CDB_SA_RANK_COMPANION", "0")
     keys = build_keys(objs, order)
     try:
         got = cdb.filter_batch(keys, REQUESTS)

@@ -748,3 +748,71 @@ def test_loader_staging_uploads_full_chunks_during_add():
     kw = bytes(text[off[41000] + 3: off[41000] + 7])
     assert np.array_equal(ix.query_array(kw), oracle.port.query(text, off, ids, sa, bits1, kw))
     ix.close()
+
+
+# ---- long repeats: rank doubling after the extension rounds (sa_build.cu finish_by_doubling) -----------------------------
+def _repetitive_corpora():
+    rng = np.random.default_rng(123)
+    x = rng.integers(ord("a"), ord("e"), size=12000, dtype=np.uint8)
+    yield "two identical documents", [x, x.copy()]
+    yield "three copies and a prefix", [x, x[:7000].copy(), x.copy(), x.copy()]
+    yield "periodic", [np.frombuffer(b"abcab" * 2500, np.uint8), np.frombuffer(b"abcab" * 1800 + b"x", np.uint8)]
+    yield "runs of one byte", [np.full(9000, ord("z"), np.uint8), np.full(5000, ord("z"), np.uint8), np.frombuffer(b"zzzy", np.uint8)]
+    y = rng.integers(0x20, 0xF0, size=9000, dtype=np.uint8)  # bytes on both sides of 0x80: note-N1 layout on top
+    yield "identical mixed-byte documents", [y, y.copy(), rng.integers(0x20, 0xF0, size=3000, dtype=np.uint8)]
+    shared = rng.integers(ord("a"), ord("c"), size=6000, dtype=np.uint8)
+    yield "long shared substrings", [np.concatenate([rng.integers(ord("a"), ord("c"), size=int(k), dtype=np.uint8), shared])
+                                     for k in rng.integers(1, 50, size=12)]
+
+
+@pytest.mark.parametrize("name,docs", list(_repetitive_corpora()), ids=[n for n, _ in _repetitive_corpora()])
+@pytest.mark.parametrize("chunked", [False, True])
+def test_long_repeats_take_rank_doubling(name, docs, chunked, monkeypatch):
+    """Corpora whose suffixes share thousands of leading bytes: key extension alone would need hundreds of rounds (S
+    symbols each); after 4 of them the remaining ties are refined by rank doubling.  Same array as the reference port,
+    few rounds, with one chunk and with a chunked build."""
+    if chunked:
+        monkeypatch.setenv("CDB_BUILD_WORKSPACE_MB", "1")
+    text = np.concatenate(docs)
+    off = np.zeros(len(docs) + 1, np.int64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    ids = np.arange(len(docs), dtype=np.int64) * 3 + 11
+    ix = build(text, off, ids)
+    st = ix.build_stats()
+    sa, bits1, _w = oracle.port.build_sa(text, off)
+    assert np.array_equal(ix.export_sa(), sa), name
+    assert ix.verify_sa()["ok"]
+    assert st["rounds"] <= 4 * max(st["chunks"], 1) + 20, st  # not hundreds
+    kw = bytes(text[off[1] + 5: off[1] + 5 + 40])
+    assert np.array_equal(ix.query_array(kw), oracle.port.query(text, off, ids, sa, bits1, kw))
+    ix.close()
+
+
+def test_two_identical_64k_documents_build_in_milliseconds():
+    """two byte-identical ~64 KB UTF-8 documents needed ~8 000 extension rounds (8 symbols each).
+    Timed, compared with the reference port and checked by the independent device verifier."""
+    import time
+    docs = []
+    for seed in (3, 4):  # two different long documents, each present twice, plus a short one
+        text, _off, _ids = corpora.utf8ish(1, 65536, seed=seed)
+        docs += [text, text.copy()]
+    docs.append(docs[0][:3000].copy())
+    t = np.concatenate(docs)
+    off = np.zeros(len(docs) + 1, np.int64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    ids = np.arange(len(docs), dtype=np.int64) + 5
+    ix = cdb.StringIndex()
+    ix.add_many(ids, t, off)
+    t0 = time.perf_counter()
+    ix.build()
+    dt = time.perf_counter() - t0
+    st = ix.build_stats()
+    v = ix.verify_sa()
+    assert v["ok"] and v["ties"] >= len(docs[0]), v  # every suffix of a copy ties with its twin
+    sa, bits1, _w = oracle.port.build_sa(t, off)
+    assert np.array_equal(ix.export_sa(), sa)
+    assert st["rounds"] <= 30 and dt < 5.0, (st, dt)
+    kw = bytes(docs[0][100:140])
+    assert np.array_equal(ix.query_array(kw), oracle.port.query(t, off, ids, sa, bits1, kw))
+    print(f"\nlong identical documents ({[len(d) for d in docs]} bytes): {st['rounds']} rounds, {dt * 1e3:.1f} ms")
+    ix.close()
