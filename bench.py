@@ -838,15 +838,18 @@ def filter_leg(ix, pat, poff, npat, steps):
         cdb.filter_result_free(res)
         return nbytes, tot, first
 
-    for _ in range(2):
+    for _ in range(3):  # the first call also builds the id-order tables of the index (once per index)
         one()
     launches0 = cdb.launch_count()
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(steps):
+        t1 = time.perf_counter()
         d2h, tot, _f = one()
+        per_step.append((time.perf_counter() - t1) * 1e3)
     dt = time.perf_counter() - t0
     lst = cdb.last_locate_stats()  # the id-ordered locate inside the last call
-    return {"value": npat * steps / dt, "ms_per_step": dt / steps * 1e3,
+    return {"value": npat * steps / dt, "ms_per_step": dt / steps * 1e3, "ms_each_step": [round(x, 3) for x in per_step],
             "locate_phases_ms": {k: lst[k] for k in ("search_ms", "gather_ms", "translate_ms", "total_ms")},
             "h2d_bytes_per_step": int(kw.nbytes + terms.nbytes + rto.nbytes + span.nbytes), "d2h_bytes_per_step": int(d2h),
             "pairs_returned_per_step": int(tot), "launches_per_step": (cdb.launch_count() - launches0) // steps,

@@ -31,6 +31,8 @@ EXPORTS = [
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
     "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
     "cdb_numeric_create", "cdb_numeric_destroy", "cdb_numeric_query", "cdb_filter", "cdb_filter_result_free",
+    "cdb_sharded_create", "cdb_sharded_destroy", "cdb_sharded_add", "cdb_sharded_add_many", "cdb_sharded_build",
+    "cdb_sharded_locate_batch", "cdb_sharded_shard", "cdb_sharded_count",
 ]
 
 CDB_OK = 0
@@ -49,7 +51,7 @@ class Result(C.Structure):
 class DeviceResult(C.Structure):
     _fields_ = [("npat", C.c_int64), ("total_pairs", C.c_int64), ("total_occurrences", C.c_int64),
                 ("row_off", C.c_void_p), ("pairs", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
-                ("stats32", C.c_void_p), ("_owner", C.c_void_p)]
+                ("stats32", C.c_void_p), ("row_flags", C.c_void_p), ("_owner", C.c_void_p)]
 
 
 class Spans(C.Structure):
@@ -151,6 +153,16 @@ def lib():
         L.cdb_filter.argtypes = [C.POINTER(FilterBatch), C.POINTER(FilterResult)]
         L.cdb_filter_result_free.argtypes = [C.POINTER(FilterResult)]
         L.cdb_filter_result_free.restype = None
+        L.cdb_sharded_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Options), C.POINTER(vp)]
+        L.cdb_sharded_destroy.argtypes = [vp]
+        L.cdb_sharded_destroy.restype = None
+        L.cdb_sharded_add.argtypes = [vp, C.c_int64, vp, C.c_int64]
+        L.cdb_sharded_add_many.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.cdb_sharded_build.argtypes = [vp]
+        L.cdb_sharded_locate_batch.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Result)]
+        L.cdb_sharded_shard.argtypes = [vp, C.c_int32, C.POINTER(vp), i64p, i64p]
+        L.cdb_sharded_count.argtypes = [vp]
+        L.cdb_sharded_count.restype = C.c_int32
         _lib = L
     return _lib
 
@@ -391,7 +403,8 @@ class StringIndex:
 
     def close(self):
         if self._h:
-            self._L.cdb_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._L.cdb_destroy(self._h)
             self._h = C.c_void_p()
             self._keep = []
 
@@ -574,3 +587,72 @@ def filter_batch(keys: dict, requests: list) -> list:
     finally:
         filter_result_free(res)
     return [(pr[ro[r]:ro[r + 1]], int(mt[r])) for r in range(n)]
+
+
+class MultiDeviceIndex:
+    """One string_index over several GPUs of this process (cdb_sharded_*): same add / build / query
+    surface as StringIndex; `devices` lists one CUDA ordinal per shard (an ordinal may repeat)."""
+
+    def __init__(self, devices, compat_signed: bool = True, keep_host_copy: bool = False):
+        self._L = lib()
+        self._h = C.c_void_p()
+        dv = (C.c_int32 * len(devices))(*devices)
+        opt = Options(-1, 1 if compat_signed else 0, 0, 1 if keep_host_copy else 0, 0)
+        _check(self._L.cdb_sharded_create(dv, len(devices), C.byref(opt), C.byref(self._h)))
+
+    def add(self, id_: int, value: bytes):
+        v = _u8(value)
+        _check(self._L.cdb_sharded_add(self._h, id_, v.ctypes.data if len(v) else None, len(v)))
+
+    def add_many(self, ids, text, doc_off):
+        ids = np.ascontiguousarray(ids, np.int64)
+        text = _u8(text)
+        doc_off = np.ascontiguousarray(doc_off, np.int64)
+        _check(self._L.cdb_sharded_add_many(self._h, ids.ctypes.data, text.ctypes.data if len(text) else None, doc_off.ctypes.data,
+                                            len(ids)))
+
+    def build(self):
+        _check(self._L.cdb_sharded_build(self._h))
+
+    def locate_batch(self, patterns, pat_off=None):
+        """-> (row_off int64 [npat+1], pairs int64 [total, 2]); row q = string_index::query(pattern q) on the whole corpus."""
+        if pat_off is None:
+            pat, pat_off = pack(list(patterns))
+        else:
+            pat, pat_off = _u8(patterns), np.ascontiguousarray(pat_off, np.int64)
+        res = Result()
+        _check(self._L.cdb_sharded_locate_batch(self._h, pat.ctypes.data if len(pat) else None, pat_off.ctypes.data, len(pat_off) - 1,
+                                                C.byref(res)))
+        try:
+            n = res.npat
+            ro = np.ctypeslib.as_array(res.row_off, shape=(n + 1,)).copy()
+            pr = np.ctypeslib.as_array(res.pairs, shape=(max(res.total_pairs, 1), 2))[: res.total_pairs].copy()
+        finally:
+            self._L.cdb_result_free(C.byref(res))
+        return ro, pr
+
+    def query(self, keyword: bytes):
+        ro, pr = self.locate_batch([keyword])
+        return [(int(a), int(b)) for a, b in pr]
+
+    def shards(self):
+        """[(borrowed StringIndex view, doc_begin, doc_end)] — for parity checks of the individual shards."""
+        out = []
+        for g in range(self._L.cdb_sharded_count(self._h)):
+            h, b, e = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+            _check(self._L.cdb_sharded_shard(self._h, g, C.byref(h), C.byref(b), C.byref(e)))
+            view = StringIndex.__new__(StringIndex)
+            view._L, view._h, view._keep, view._borrowed = self._L, h, [], True
+            out.append((view, b.value, e.value))
+        return out
+
+    def close(self):
+        if self._h:
+            self._L.cdb_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

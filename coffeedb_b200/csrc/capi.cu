@@ -787,6 +787,7 @@ void cdb_device_result_free(cdb_device_result* r) {
     if (r->left) cudaFreeAsync(r->left, st);
     if (r->right) cudaFreeAsync(r->right, st);
     if (r->stats32) cudaFreeAsync(r->stats32, st);
+    if (r->row_flags) cudaFreeAsync(r->row_flags, st);
     std::memset(r, 0, sizeof(*r));
 }
 

@@ -168,6 +168,7 @@ struct FKeyDev {
     int nkind; // numeric: 0 int64, 1 double
     const i64* row_off;  // string: this batch's id-ordered rows
     const i64* pairs;
+    const u8* row_flags; //         bit 0: the row's counts are not all 1
     const u64* vkey;     // numeric
     const i64* vid;
     const u64* ikey;
@@ -200,7 +201,8 @@ struct FArgs {
     const u16* pi;
 };
 
-enum { CLS_NONE = 0, CLS_WARP = 1, CLS_CTA = 2, CLS_NUM = 3 };
+// CLS_DIRECT: warp path whose single term is the whole request (no other key, no $correlation range): nothing to merge
+enum { CLS_NONE = 0, CLS_WARP = 1, CLS_CTA = 2, CLS_NUM = 3, CLS_DIRECT = 4 };
 
 __device__ __forceinline__ void request_span(const FArgs& A, i64 r, u64 n, u64* sb, u64* se) {
     u64 b = 0, e = n;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256) size_kernel(FArgs A) {
             const u64 nn = (u64)A.keys[firstnum].nn;
             alloc = numspan < nn ? numspan : nn;
         } else if (T <= (u64)kFCap) {
-            cls = CLS_WARP;
+            cls = (nstr == 1 && t1 - t0 == 1 && A.corr == nullptr) ? CLS_DIRECT : CLS_WARP;
             u64 sb, se;
             request_span(A, r, T, &sb, &se);
             alloc = se - sb;
@@ -571,6 +573,71 @@ __global__ void __launch_bounds__(kFWarps * 32) filter_warp_kernel(FArgs A) {
     filter_request<false, u32>(A, r, s.key, s.cnt, s.ks, s.perm, s.tm, nullptr);
 }
 
+// One keyword per request and nothing else (the usual request): the row is the id-ascending answer, so the warp only
+// needs the counts (to see whether they tie) and 6 KB of shared memory for the rare row whose counts differ — eight
+// requests per CTA and several CTAs per SM instead of the 12 warps per SM the merging kernel's 16 KB per request allow.
+struct DirectScratch {
+    u32 cnt[kFCap];
+    u16 perm[kFCap];
+};
+constexpr int kFDirectWarps = 8;
+
+__global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 r = (i64)blockIdx.x * kFDirectWarps + warp;
+    if (r >= A.nreq || A.cls[r] != CLS_DIRECT) return;
+    DirectScratch& s = reinterpret_cast<DirectScratch*>(smem_raw)[warp];
+    const cdb_filter_term t = A.terms[A.req_term_off[r]];
+    const FKeyDev& F = A.keys[t.key];
+    const i64 rowi = A.term_row[A.req_term_off[r]];
+    const i64 r0 = F.row_off[rowi];
+    const u64 n = (u64)(F.row_off[rowi + 1] - r0);
+    const i64* row = F.pairs + 2 * r0;
+    u64 sb, se;
+    request_span(A, r, n, &sb, &se);
+    if (lane == 0) {
+        A.matched[r] = n;
+        A.fin_len[r] = se - sb;
+        A.raw_len[r] = se - sb;
+    }
+    if (se <= sb) return;
+    // the locate already knows whether every count of the row is 1 (no document hit twice): then all $correlations tie
+    // and the row is not read at all beyond the span's elements
+    i64 mn = 1, mx = 1;
+    if (F.row_flags[rowi] & 1) {
+        mn = 0x7fffffffffffffffll;
+        mx = -0x7fffffffffffffffll - 1;
+        for (u64 i = lane; i < n; i += 32) {
+            const i64 c = __ldg(row + 2 * i + 1);
+            mn = c < mn ? c : mn;
+            mx = c > mx ? c : mx;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const i64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
+        }
+    }
+    i64* out = A.raw + 2 * A.raw_off[r];
+    const u16* src = A.pi + n * (n - 1) / 2;
+    if (mn != mx) {
+        for (u64 i = lane; i < n; i += 32) {
+            s.cnt[i] = (u32)__ldg(row + 2 * i + 1);
+            s.perm[i] = (u16)i;
+        }
+        __syncwarp();
+        const u32* cnt = s.cnt;
+        if (lane == 0)
+            coffeedb_b200::sort_order::std_sort_order(s.perm, (int)n, [cnt](u16 a, u16 b) { return cnt[a] > cnt[b]; });
+        __syncwarp();
+        src = s.perm;
+    }
+    for (u64 j = sb + lane; j < se; j += 32)
+        *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)src[j]);
+}
+
 __global__ void __launch_bounds__(256) filter_cta_kernel(FArgs A, const i64* __restrict__ list, const u64* __restrict__ scr_off,
                                                          i64* scr_key, i64* scr_cnt, u8* scr_ks) {
     __shared__ TermMeta tm;
@@ -672,7 +739,7 @@ __global__ void key_pack_kernel(const cdb_filter_term* __restrict__ terms, i64 n
 __global__ void __launch_bounds__(256) compact_kernel(FArgs A, const u64* __restrict__ fin_off, i64* __restrict__ fin) {
     const int lane = threadIdx.x & 31;
     const i64 r = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= A.nreq || A.cls[r] != CLS_WARP) return;
+    if (r >= A.nreq || (A.cls[r] != CLS_WARP && A.cls[r] != CLS_DIRECT)) return;
     const u64 n = fin_off[r + 1] - fin_off[r];
     const longlong2* src = reinterpret_cast<const longlong2*>(A.raw + 2 * A.raw_off[r]);
     longlong2* dst = reinterpret_cast<longlong2*>(fin + 2 * fin_off[r]);
@@ -787,6 +854,7 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
                 locate_device(*ix, pat.p, poff.p, nkw, st, &results[k], /*id_order=*/true);  // throws on an empty keyword
                 F.row_off = results[k].row_off;
                 F.pairs = results[k].pairs;
+                F.row_flags = results[k].row_flags;
                 lap("locate in id order");
             }
         }
@@ -829,9 +897,13 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         if (herr == 1) throw Error(CDB_ERR_ARG, "cdb_filter: a request has more than 64 terms");
         if (herr) throw Error(CDB_ERR_ARG, "cdb_filter: a term names a key, range or keyword outside the batch");
         std::vector<i64> big, num;
+        i64 ndirect = 0, nwarp = 0;
         for (i64 r = 0; r < nreq; ++r) {
-            if (hcls[r] == CLS_CTA) big.push_back(r);
-            if (hcls[r] == CLS_NUM) num.push_back(r);
+            const u8 c = hcls[r];
+            if (c == CLS_CTA) big.push_back(r);
+            if (c == CLS_NUM) num.push_back(r);
+            ndirect += c == CLS_DIRECT;
+            nwarp += c == CLS_WARP || c == CLS_NONE;
         }
         o.raw.alloc((size_t)tot[0] * 2, st);
         A.raw_off = o.raw_off.p;
@@ -841,7 +913,13 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         A.matched = o.matched.p;
         A.pi = sort_table(filter_device_of(b), st);
         // ---- the merges
-        {
+        if (ndirect) {
+            const size_t smem = sizeof(DirectScratch) * kFDirectWarps;
+            CDB_CUDA(cudaFuncSetAttribute(filter_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            filter_direct_kernel<<<(unsigned)ceil_div(nreq, kFDirectWarps), kFDirectWarps * 32, smem, st>>>(A);
+            CDB_LAUNCH_CHECK();
+        }
+        if (nwarp) {
             const size_t smem = sizeof(WarpScratch) * kFWarps;
             CDB_CUDA(cudaFuncSetAttribute(filter_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             filter_warp_kernel<<<(unsigned)ceil_div(nreq, kFWarps), kFWarps * 32, smem, st>>>(A);

@@ -955,12 +955,26 @@ static bool id_order_tables(const Index& ix, cudaStream_t st) {
             // keywords).  Only taken when it leaves a quarter of the device memory free for the query temporaries.
             const char* ec = getenv("CDB_SA_RANK_COMPANION");
             if (ix.n > 0 && (!ec || atoi(ec) != 0)) {
-                cudaMemPool_t pool;
-                if (cudaDeviceGetDefaultMemPool(&pool, ix.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+                // memory held by the stream-ordered pool for query temporaries counts as available (it is re-used, not
+                // lost), but is only handed back to the driver when the allocation does not fit otherwise
+                const size_t need = (size_t)ix.n * 4;
                 size_t free_b = 0, total_b = 0;
                 CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-                const size_t need = (size_t)ix.n * 4;
-                if (free_b > need && free_b - need >= total_b / 4 && cudaMalloc((void**)&ix.d_sa_rank, need) == cudaSuccess) {
+                cudaMemPool_t pool;
+                const bool have_pool = cudaDeviceGetDefaultMemPool(&pool, ix.device) == cudaSuccess;
+                unsigned long long reserved = 0, used = 0;
+                if (have_pool) {
+                    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                }
+                const size_t avail = free_b + (size_t)(reserved > used ? reserved - used : 0);
+                bool ok = avail > need && avail - need >= total_b / 4;
+                if (ok && cudaMalloc((void**)&ix.d_sa_rank, need) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (have_pool) cudaMemPoolTrimTo(pool, 0);
+                    ok = cudaMalloc((void**)&ix.d_sa_rank, need) == cudaSuccess;
+                }
+                if (ok) {
                     const int g = num_sms() * 16;
                     if (ix.width == 4)
                         sa_rank_kernel<u32><<<g, 256, 0, st>>>(reinterpret_cast<const u32*>(ix.d_sa), ix.mask, ix.d_rank_tab, ix.n, ix.d_sa_rank);
@@ -980,12 +994,17 @@ static bool id_order_tables(const Index& ix, cudaStream_t st) {
 }
 
 // per-pattern (row length, occurrences) as 32-bit integers, [2][npat]: what a sharded index exchanges per batch
+// + row_flags: bit 0 = the row's counts are not all 1 (gather_kernel left that in bit 15 of the row's seg entries;
+// rows of the large path: not known, flagged)
 __global__ void stats32_kernel(const u64* __restrict__ row_off, const i64* __restrict__ left, const i64* __restrict__ right,
-                               i64 npat, int32_t* __restrict__ stats) {
+                               i64 npat, const u16* __restrict__ seg, int nranges, int32_t* __restrict__ stats,
+                               u8* __restrict__ row_flags) {
     const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= npat) return;
     const u64 rl = row_off[q + 1] - row_off[q];
     const i64 oc = right[q] - left[q];
+    const u16 s0 = seg[(size_t)(q / kTileWarps) * (nranges + 1) * kTileWarps + (q % kTileWarps)];
+    row_flags[q] = (oc > kWarpCap || (s0 >> 15)) ? 1 : 0;
     stats[q] = rl > 0x7fffffffull ? 0x7fffffff : (int32_t)rl;
     stats[npat + q] = oc > 0x7fffffffll ? 0x7fffffff : (int32_t)oc;
 }
@@ -1112,6 +1131,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u16> ccnt((size_t)cap_pairs, st);  // only touched for rows with repeated documents
     DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
+    DevBuf<u8> rowflag((size_t)npat, st);
     // distribution-sort scale: bucket = doc * 1024 / nd (0 switches the sorting network on for every interval)
     const char* env_buckets = getenv("CDB_GATHER_BUCKETS");
     const bool use_buckets = !env_buckets || atoi(env_buckets) != 0;
@@ -1180,7 +1200,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
     }
     DevBuf<int32_t> stats((size_t)npat * 2, st);
-    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, stats.p);
+    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, stats.p, rowflag.p);
     CDB_LAUNCH_CHECK();
     u64 total_pairs = 0;
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
@@ -1207,6 +1227,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     out->left = left.detach();
     out->right = right.detach();
     out->stats32 = stats.detach();
+    out->row_flags = rowflag.detach();
     out->_owner = (void*)st;
 }
 

@@ -143,6 +143,65 @@ private:
 
 using string_index = basic_string_index<index_base>;
 
+// The same surface over several GPUs of this process (cdb_sharded_*, include/coffeedb_b200.h): documents are split into
+// contiguous doc-index ranges, one shard per entry of `devices`; query() rows are the whole-corpus rows (ascending doc
+// index).  `using string_index = coffeedb_b200::basic_sharded_string_index<index>;` in src/index.h, constructed with the
+// device list, shards every string key of the database over the box's GPUs without touching database.cpp.
+template <class Base>
+class basic_sharded_string_index : public Base {
+public:
+    using value_type = std::string;
+    static constexpr int8_t number = 3;
+    using result_type = std::vector<std::pair<int64_t, int64_t>>;
+
+    explicit basic_sharded_string_index(const std::vector<int32_t>& devices = default_devices(), bool compat_signed = true) {
+        cdb_options o{};
+        o.device = -1;
+        o.compat_signed = compat_signed ? 1 : 0;
+        check(cdb_sharded_create(devices.data(), (int32_t)devices.size(), &o, &h_));
+    }
+    ~basic_sharded_string_index() override { cdb_sharded_destroy(h_); }
+
+    void add(int64_t id, std::string_view value) { check(cdb_sharded_add(h_, id, value.data(), (int64_t)value.size())); }
+    void build() override { check(cdb_sharded_build(h_)); }
+
+    result_type query(const std::string& keyword) const override { return query_batch({keyword})[0]; }
+
+    std::vector<result_type> query_batch(const std::vector<std::string>& keywords) const {
+        std::string bytes;
+        std::vector<int64_t> off(keywords.size() + 1, 0);
+        for (size_t q = 0; q < keywords.size(); ++q) {
+            bytes += keywords[q];
+            off[q + 1] = (int64_t)bytes.size();
+        }
+        cdb_result r{};
+        check(cdb_sharded_locate_batch(h_, bytes.data(), off.data(), (int64_t)keywords.size(), &r));
+        std::vector<result_type> out(keywords.size());
+        for (size_t q = 0; q < keywords.size(); ++q) {
+            out[q].reserve((size_t)(r.row_off[q + 1] - r.row_off[q]));
+            for (int64_t i = r.row_off[q]; i < r.row_off[q + 1]; ++i) out[q].emplace_back(r.pairs[2 * i], r.pairs[2 * i + 1]);
+        }
+        cdb_result_free(&r);
+        return out;
+    }
+
+    // every CUDA device of the box, one shard each
+    static std::vector<int32_t> default_devices() {
+        std::vector<int32_t> d;
+        for (int g = 0; g < cdb_device_count(); ++g) d.push_back(g);
+        if (d.empty()) d.push_back(0);
+        return d;
+    }
+
+private:
+    static void check(cdb_status s) {
+        if (s != CDB_OK) throw std::runtime_error(cdb_last_error());
+    }
+    cdb_sharded* h_ = nullptr;
+};
+
+using sharded_string_index = basic_sharded_string_index<index_base>;
+
 // $correlation composition over (id, count) lists, as filter() does it on the host (src/interface.cpp:79-146).  The
 // device delivers exact per-(keyword, document) counts; these helpers are the reference-shaped integer adds on top.
 namespace correlation {

@@ -72,6 +72,7 @@ typedef struct cdb_device_result {
     int64_t* right;   /* device [npat] */
     int32_t* stats32; /* device [2*npat]: row length, then occurrences, of every pattern as 32-bit integers (saturating) —
                          what the shards of a split corpus exchange per batch */
+    uint8_t* row_flags; /* device [npat]: bit 0 = some document occurs more than once in the row (otherwise every count is 1) */
     void* _owner;
 } cdb_device_result;
 

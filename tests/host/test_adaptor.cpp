@@ -156,6 +156,24 @@ int main(int argc, char** argv) {
             REQUIRE(i == 0 || got[i - 1].second >= got[i].second);
         }
     }
+    {  // the same surface over several shards (cdb_sharded_*): three shards on the devices of this box
+        std::vector<int32_t> devs;
+        for (int g = 0; g < 3; ++g) devs.push_back(g % cdb_device_count());
+        coffeedb_b200::sharded_string_index sh(devs);
+        sindex one;
+        std::mt19937_64 rng(99);
+        std::vector<std::string> docs(500);
+        for (size_t i = 0; i < docs.size(); ++i) {
+            docs[i].resize(20 + rng() % 200);
+            for (auto& c : docs[i]) c = (char)('a' + rng() % 4);
+            sh.add(9000 - (int64_t)i, docs[i]);
+            one.add(9000 - (int64_t)i, docs[i]);
+        }
+        sh.build();
+        one.build();
+        for (const char* kw : {"a", "ab", "abcd", "dddd", "zz"}) REQUIRE(sh.query(kw) == one.query(kw));
+        REQUIRE(sh.query_batch({"ab", "ca"}) == one.query_batch({"ab", "ca"}));
+    }
     std::puts("adaptor gpu ok");
     return 0;
 }
