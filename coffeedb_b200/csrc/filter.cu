@@ -199,6 +199,9 @@ struct FArgs {
     u64* fin_len;
     u64* matched;
     const u16* pi;
+    // one-keyword requests whose counts do not all tie: handed from filter_direct_kernel to filter_direct_sort_kernel
+    u32* slow_list;
+    unsigned long long* slow_count;
 };
 
 // CLS_DIRECT: warp path whose single term is the whole request (no other key, no $correlation range): nothing to merge
@@ -583,11 +586,9 @@ struct DirectScratch {
 constexpr int kFDirectWarps = 8;
 
 __global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 r = (i64)blockIdx.x * kFDirectWarps + warp;
     if (r >= A.nreq || A.cls[r] != CLS_DIRECT) return;
-    DirectScratch& s = reinterpret_cast<DirectScratch*>(smem_raw)[warp];
     const cdb_filter_term t = A.terms[A.req_term_off[r]];
     const FKeyDev& F = A.keys[t.key];
     const i64 rowi = A.term_row[A.req_term_off[r]];
@@ -620,22 +621,68 @@ __global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs
             mx = b > mx ? b : mx;
         }
     }
+    if (mn != mx) {
+        // The sums differ (0.65 % of the rows at cfg3): the order needs the sequential sort.  It runs in a kernel of its
+        // own, one 32-thread CTA per such row — left here, one slow lane kept its whole 8-request CTA resident for
+        // ~150 us and the kernel ran at 17 % occupancy (3.1 ms instead of well under 1).
+        if (lane == 0) A.slow_list[atomicAdd(A.slow_count, 1ull)] = (u32)r;
+        return;
+    }
     i64* out = A.raw + 2 * A.raw_off[r];
     const u16* src = A.pi + n * (n - 1) / 2;
-    if (mn != mx) {
-        for (u64 i = lane; i < n; i += 32) {
-            s.cnt[i] = (u32)__ldg(row + 2 * i + 1);
-            s.perm[i] = (u16)i;
-        }
-        __syncwarp();
-        const u32* cnt = s.cnt;
-        if (lane == 0)
-            coffeedb_b200::sort_order::std_sort_order(s.perm, (int)n, [cnt](u16 a, u16 b) { return cnt[a] > cnt[b]; });
-        __syncwarp();
-        src = s.perm;
-    }
     for (u64 j = sb + lane; j < se; j += 32)
         *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)src[j]);
+}
+
+// The rows filter_direct_kernel handed over: one 32-thread CTA per row (persistent grid over the list), lane 0 runs the
+// restated introsort.  Elements are (count << 16 | index) in one word when every count fits 16 bits — one shared-memory
+// load per comparison instead of two dependent ones — and (count array, 16-bit handles) otherwise.
+__global__ void __launch_bounds__(32) filter_direct_sort_kernel(FArgs A) {
+    __shared__ DirectScratch s;
+    const int lane = threadIdx.x;
+    const unsigned long long count = *A.slow_count;
+    for (unsigned long long k = blockIdx.x; k < count; k += gridDim.x) {
+        const i64 r = (i64)A.slow_list[k];
+        const cdb_filter_term t = A.terms[A.req_term_off[r]];
+        const FKeyDev& F = A.keys[t.key];
+        const i64 rowi = A.term_row[A.req_term_off[r]];
+        const i64 r0 = F.row_off[rowi];
+        const u64 n = (u64)(F.row_off[rowi + 1] - r0);
+        const i64* row = F.pairs + 2 * r0;
+        u64 sb, se;
+        request_span(A, r, n, &sb, &se);
+        i64 mx = 0;
+        for (u64 i = lane; i < n; i += 32) {
+            const i64 c = __ldg(row + 2 * i + 1);
+            s.cnt[i] = (u32)c;
+            mx = c > mx ? c : mx;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const i64 b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = b > mx ? b : mx;
+        }
+        i64* out = A.raw + 2 * A.raw_off[r];
+        if (mx < 65536) {
+            for (u64 i = lane; i < n; i += 32) s.cnt[i] = (s.cnt[i] << 16) | (u32)i;
+            __syncwarp();
+            if (lane == 0)
+                coffeedb_b200::sort_order::std_sort_order(s.cnt, (int)n, [](u32 a, u32 b) { return (a >> 16) > (b >> 16); });
+            __syncwarp();
+            for (u64 j = sb + lane; j < se; j += 32)
+                *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)(s.cnt[j] & 0xffffu));
+        } else {
+            for (u64 i = lane; i < n; i += 32) s.perm[i] = (u16)i;
+            __syncwarp();
+            const u32* cnt = s.cnt;
+            if (lane == 0)
+                coffeedb_b200::sort_order::std_sort_order(s.perm, (int)n, [cnt](u16 a, u16 b) { return cnt[a] > cnt[b]; });
+            __syncwarp();
+            for (u64 j = sb + lane; j < se; j += 32)
+                *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)s.perm[j]);
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(256) filter_cta_kernel(FArgs A, const i64* __restrict__ list, const u64* __restrict__ scr_off,
@@ -913,10 +960,17 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         A.matched = o.matched.p;
         A.pi = sort_table(filter_device_of(b), st);
         // ---- the merges
+        DevBuf<u32> slow_list;
+        DevBuf<unsigned long long> slow_count;
         if (ndirect) {
-            const size_t smem = sizeof(DirectScratch) * kFDirectWarps;
-            CDB_CUDA(cudaFuncSetAttribute(filter_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            filter_direct_kernel<<<(unsigned)ceil_div(nreq, kFDirectWarps), kFDirectWarps * 32, smem, st>>>(A);
+            slow_list.alloc((size_t)nreq, st);
+            slow_count.alloc(1, st);
+            CDB_CUDA(cudaMemsetAsync(slow_count.p, 0, 8, st));
+            A.slow_list = slow_list.p;
+            A.slow_count = slow_count.p;
+            filter_direct_kernel<<<(unsigned)ceil_div(nreq, kFDirectWarps), kFDirectWarps * 32, 0, st>>>(A);
+            CDB_LAUNCH_CHECK();
+            filter_direct_sort_kernel<<<(unsigned)std::min<i64>(nreq, (i64)num_sms() * 32), 32, 0, st>>>(A);
             CDB_LAUNCH_CHECK();
         }
         if (nwarp) {

@@ -67,6 +67,15 @@ public:
 
     void build() override { check(cdb_build(h_)); }
 
+    // build() that reads the suffix array back from `path` when the file was saved for this very corpus (SURVEY.md 8f-4;
+    // the reference rebuilds at every start, src/server.cpp:43-44).  Returns true when the array came from the file.
+    bool build_or_load(const std::string& path) {
+        int32_t loaded = 0;
+        check(cdb_build_or_load(h_, path.c_str(), &loaded));
+        return loaded != 0;
+    }
+    void save(const std::string& path) const { check(cdb_save(h_, path.c_str())); }
+
     // One keyword, as the server calls it (src/database.cpp:387-393).  Concurrent calls on the same index — the
     // reference runs query() from up to max(8, hw-1) httplib threads — are coalesced into one device batch by
     // cdb_query (micro_batcher.hpp); a lone call is served at once.
