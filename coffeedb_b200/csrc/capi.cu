@@ -683,6 +683,12 @@ struct FilterOwner {
     }
 };
 
+// fin_off of one part of a pipelined batch -> offsets inside the whole batch's result
+__global__ void shift_offsets_kernel(u64* off, i64 n, u64 base) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] += base;
+}
+
 cdb_status cdb_filter(const cdb_filter_batch* b, cdb_filter_result* out) {
     CDB_TRY
     if (!b || !out || b->nreq < 0 || (b->nreq > 0 && !b->req_term_off) || (b->nkeys > 0 && !b->keys))
@@ -692,54 +698,120 @@ cdb_status cdb_filter(const cdb_filter_batch* b, cdb_filter_result* out) {
     int dev = filter_device_of(*b);
     if (dev < 0) CDB_CUDA(cudaGetDevice(&dev));
     DeviceSetter ds(dev);
-    cudaStream_t st = thread_ctx(dev).stream;
+    ThreadCtx& tc = thread_ctx(dev);
+    cudaStream_t st = tc.stream;
     const i64 nreq = b->nreq;
+    const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
+    // Batches whose result size is bounded by their spans CAN be cut into parts that go through the device one after the
+    // other, the copy of part k's slices to the host (its own stream) running under the kernels of part k+1
+    // (CDB_FILTER_PARTS > 1).  Measured at cfg3 (10^6 requests, 0.5 GB of slices = 9.3 ms over PCIe): 4 parts take 27.3 ms
+    // against 23.3 ms in one piece — every part pays its own upload, keyword packing, scans and synchronisations
+    // (about 3 ms), more than the copy it hides — so one part is the default.
+    int nparts = 1;
+    u64 bound = 0;
+    i64 part_min = (i64)1 << 17;
+    if (const char* e = getenv("CDB_FILTER_PART_MIN")) part_min = std::max<i64>(2, atoll(e));  // tests: small batches in parts
+    if (b->span && nreq >= part_min) {
+        bool ok = true;
+        for (i64 r = 0; r < nreq && ok; ++r) {
+            const i64 s0 = b->span[2 * r] < 0 ? 0 : b->span[2 * r], s1 = b->span[2 * r + 1];
+            if (s1 > s0) bound += (u64)(s1 - s0);
+            ok = bound <= ((u64)1 << 28);  // 4 GB of pairs
+        }
+        if (const char* e = getenv("CDB_FILTER_PARTS")) nparts = ok ? std::max(1, std::min(16, atoi(e))) : 1;
+        if ((i64)nparts > nreq) nparts = 1;
+    }
     FilterOwner* own = new FilterOwner();
+    std::vector<std::unique_ptr<FilterOut>> parts;
+    std::vector<std::vector<i64>> rto((size_t)nparts);
     try {
-        FilterOut fo;
-        const bool dbg = getenv("CDB_DEBUG_TIMING") != nullptr;
-        auto t0 = std::chrono::steady_clock::now();
-        filter_batch_device(*b, st, fo);
-        auto t1 = std::chrono::steady_clock::now();
+        const auto t0 = std::chrono::steady_clock::now();
         own->p[0] = g_pinned.get((size_t)(nreq + 1) * 8, &own->cap[0]);
-        own->p[1] = g_pinned.get((size_t)(fo.total_fin ? fo.total_fin : 1) * 16, &own->cap[1]);
         own->p[2] = g_pinned.get((size_t)(nreq ? nreq : 1) * 8, &own->cap[2]);
         i64* ro = (i64*)own->p[0];
-        i64* pr = (i64*)own->p[1];
-        CDB_CUDA(cudaMemcpyAsync(ro, fo.fin_off.p, (size_t)(nreq + 1) * 8, cudaMemcpyDeviceToHost, st));
-        if (fo.total_fin) CDB_CUDA(cudaMemcpyAsync(pr, fo.fin.p, (size_t)fo.total_fin * 16, cudaMemcpyDeviceToHost, st));
-        if (nreq) CDB_CUDA(cudaMemcpyAsync(own->p[2], fo.matched.p, (size_t)nreq * 8, cudaMemcpyDeviceToHost, st));
+        i64* pr = nullptr;
+        if (nparts > 1) {
+            own->p[1] = g_pinned.get((size_t)(bound ? bound : 1) * 16, &own->cap[1]);
+            pr = (i64*)own->p[1];
+        }
+        u64 total = 0;
+        std::vector<i64> part_begin((size_t)nparts + 1, nreq);
+        for (int k = 0; k < nparts; ++k) part_begin[k] = nreq / nparts * k;
+        for (int k = 0; k < nparts; ++k) {
+            const i64 r0 = part_begin[k], n = part_begin[k + 1] - r0;
+            cdb_filter_batch sub = *b;
+            if (nparts > 1) {  // requests [r0, r0 + n): their terms, rebased offsets, their rows of corr_range / span
+                const i64 t0k = b->req_term_off[r0];
+                rto[k].resize((size_t)n + 1);
+                for (i64 r = 0; r <= n; ++r) rto[k][r] = b->req_term_off[r0 + r] - t0k;
+                sub.terms = b->terms + t0k;
+                sub.req_term_off = rto[k].data();
+                sub.nreq = n;
+                sub.corr_range = b->corr_range ? b->corr_range + 2 * r0 : nullptr;
+                sub.span = b->span + 2 * r0;
+            }
+            parts.emplace_back(new FilterOut());
+            FilterOut& fo = *parts.back();
+            filter_batch_device(sub, st, fo);
+            if (nparts == 1) {
+                own->p[1] = g_pinned.get((size_t)(fo.total_fin ? fo.total_fin : 1) * 16, &own->cap[1]);
+                pr = (i64*)own->p[1];
+            }
+            if (total && n) {
+                shift_offsets_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, st>>>(fo.fin_off.p, n + 1, total);
+                CDB_LAUNCH_CHECK();
+            }
+            cudaStream_t cs = st;
+            if (nparts > 1) {
+                if (!tc.copy_stream) CDB_CUDA(cudaStreamCreateWithFlags(&tc.copy_stream, cudaStreamNonBlocking));
+                cs = tc.copy_stream;
+                CDB_CUDA(cudaEventRecord(tc.ev[ThreadCtx::kEvents - 1], st));
+                CDB_CUDA(cudaStreamWaitEvent(cs, tc.ev[ThreadCtx::kEvents - 1], 0));
+            }
+            if (n) CDB_CUDA(cudaMemcpyAsync(ro + r0, fo.fin_off.p, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+            if (fo.total_fin) CDB_CUDA(cudaMemcpyAsync(pr + 2 * total, fo.fin.p, (size_t)fo.total_fin * 16, cudaMemcpyDeviceToHost, cs));
+            if (n) CDB_CUDA(cudaMemcpyAsync((i64*)own->p[2] + r0, fo.matched.p, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+            total += fo.total_fin;
+        }
+        const auto t1 = std::chrono::steady_clock::now();
         CDB_CUDA(cudaStreamSynchronize(st));
+        if (nparts > 1) CDB_CUDA(cudaStreamSynchronize(tc.copy_stream));
+        ro[nreq] = (i64)total;
         if (dbg)
-            fprintf(stderr, "[cdb_filter] device %.3f ms, result buffers + copy to the host %.3f ms (%lld pairs)\n",
+            fprintf(stderr, "[cdb_filter] %d part(s): device %.3f ms, rest of the copy to the host %.3f ms (%lld pairs)\n", nparts,
                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), (long long)fo.total_fin);
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), (long long)total);
         // Requests that did not fit the warp path: their id-ascending survivors come back whole and get the reference's own
         // final step here — the std::sort of src/interface.cpp:143-146 and the span of :196-209.
         std::vector<std::pair<int64_t, int64_t>> v;
-        for (i64 r : fo.pending) {
-            u64 off = 0, len = 0;
-            CDB_CUDA(cudaMemcpyAsync(&off, fo.raw_off.p + r, 8, cudaMemcpyDeviceToHost, st));
-            CDB_CUDA(cudaMemcpyAsync(&len, fo.raw_len.p + r, 8, cudaMemcpyDeviceToHost, st));
-            CDB_CUDA(cudaStreamSynchronize(st));
-            v.resize((size_t)len);
-            static_assert(sizeof(std::pair<int64_t, int64_t>) == 16, "pair layout");
-            if (len) CDB_CUDA(cudaMemcpyAsync((void*)v.data(), fo.raw.p + 2 * off, (size_t)len * 16, cudaMemcpyDeviceToHost, st));
-            CDB_CUDA(cudaStreamSynchronize(st));
-            std::sort(v.begin(), v.end(), [](auto x, auto y) { return x.second > y.second; });
-            const i64 take = ro[r + 1] - ro[r];
-            i64 first = 0;
-            if (b->span) first = b->span[2 * r] < 0 ? 0 : b->span[2 * r];
-            if (take > 0) std::memcpy(pr + 2 * ro[r], (const void*)(v.data() + first), (size_t)take * 16);
+        for (int k = 0; k < nparts; ++k) {
+            FilterOut& fo = *parts[k];
+            for (i64 rl : fo.pending) {
+                const i64 r = part_begin[k] + rl;
+                u64 off = 0, len = 0;
+                CDB_CUDA(cudaMemcpyAsync(&off, fo.raw_off.p + rl, 8, cudaMemcpyDeviceToHost, st));
+                CDB_CUDA(cudaMemcpyAsync(&len, fo.raw_len.p + rl, 8, cudaMemcpyDeviceToHost, st));
+                CDB_CUDA(cudaStreamSynchronize(st));
+                v.resize((size_t)len);
+                static_assert(sizeof(std::pair<int64_t, int64_t>) == 16, "pair layout");
+                if (len) CDB_CUDA(cudaMemcpyAsync((void*)v.data(), fo.raw.p + 2 * off, (size_t)len * 16, cudaMemcpyDeviceToHost, st));
+                CDB_CUDA(cudaStreamSynchronize(st));
+                std::sort(v.begin(), v.end(), [](auto x, auto y) { return x.second > y.second; });
+                const i64 take = ro[r + 1] - ro[r];
+                i64 first = 0;
+                if (b->span) first = b->span[2 * r] < 0 ? 0 : b->span[2 * r];
+                if (take > 0) std::memcpy(pr + 2 * ro[r], (const void*)(v.data() + first), (size_t)take * 16);
+            }
         }
         out->nreq = nreq;
-        out->total_pairs = (i64)fo.total_fin;
+        out->total_pairs = (i64)total;
         out->row_off = ro;
         out->pairs = pr;
         out->matched = (const i64*)own->p[2];
         out->_owner = own;
     } catch (...) {
         cudaStreamSynchronize(st);
+        if (tc.copy_stream) cudaStreamSynchronize(tc.copy_stream);
         own->release();
         delete own;
         throw;

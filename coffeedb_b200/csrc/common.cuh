@@ -136,6 +136,7 @@ struct ThreadCtx {
     static constexpr int kEvents = 8;
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device-to-host copies that run under the next part's kernels (cdb_filter)
     cudaEvent_t ev[kEvents] = {};
     ~ThreadCtx() {
         if (!stream) return;
@@ -144,6 +145,7 @@ struct ThreadCtx {
         cudaSetDevice(device);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         cudaStreamDestroy(stream);
         if (prev >= 0) cudaSetDevice(prev);
     }

@@ -124,6 +124,31 @@ def test_filter_equals_reference_server(reference_answers, doc_order, monkeypatc
             k.close()
 
 
+def test_filter_in_parts_equals_reference_server(reference_answers, monkeypatch):
+    """Large span-bounded batches go through the device in parts whose copies to the host overlap the next part's
+    kernels (capi.cu: cdb_filter).  Forced here on the 28 requests (3 parts): same answers, including the requests that are
+    finished on the host (CTA path, numeric-only) and land in the middle of a part."""
+    objs, answers, counts = reference_answers
+    order = list(range(N))
+    random.Random(6).shuffle(order)
+    keys = build_keys(objs, order)
+    monkeypatch.setenv("CDB_FILTER_PART_MIN", "4")
+    monkeypatch.setenv("CDB_FILTER_PARTS", "3")
+    reqs = [dict(r, span=r.get("span", "[0,100000)")) for r in REQUESTS]  # every request bounded: the parts path is taken
+    try:
+        got = cdb.filter_batch(keys, reqs)
+        for req, (pairs, matched), want, cnt in zip(reqs, got, answers, counts):
+            assert [(int(a), int(b)) for a, b in pairs] == want, (req, pairs[:8], want[:8])
+            assert matched == cnt
+        monkeypatch.setenv("CDB_FILTER_PARTS", "16")
+        got = cdb.filter_batch(keys, reqs)
+        for req, (pairs, _m), want in zip(reqs, got, answers):
+            assert [(int(a), int(b)) for a, b in pairs] == want, req
+    finally:
+        for k in keys.values():
+            k.close()
+
+
 def test_numeric_query_is_the_reference_numeric_query():
     """cdb_numeric_query == numeric_query (src/index.cpp:63-74): sort by (value, id), two lower bounds with the pairs
     parse_range builds (src/utility.h:69-86)."""
