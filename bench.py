@@ -261,7 +261,7 @@ def spans_leg(ix, last, text, ids, d_pat, d_poff, npat, w, dev, hbm_peak, pat, p
 
 
 
-def cfg5_shard_leg(dev, nbytes):
+def cfg5_shard_leg(dev, nbytes, seed=55, rank=0, world=1):
     """One shard of BASELINE configs[4] on one GPU: `nbytes` of valid UTF-8 in documents of up to 64 KB (64-bit elements,
     note-N1 layout: the search runs the reference's own recurrences), two numeric columns, and 10^5 requests
     `substring (4..12 bytes, half sampled / half random) AND year in a 10 % range` through cdb_filter with span [0,32).
@@ -270,22 +270,29 @@ def cfg5_shard_leg(dev, nbytes):
     import torch
     import coffeedb_b200 as cdb
     from tests import corpora
-    t5, o5, i5, nd5, n5 = corpora.utf8_corpus_on_device(nbytes, seed=55, device_index=dev.index or 0)
+    if world > 1:
+        import torch.distributed as dist
+    t5, o5, i5, nd5, n5 = corpora.utf8_corpus_on_device(nbytes, seed=seed, device_index=dev.index or 0)
+    i5 += rank * (1 << 40)  # ids are unique over the shards
     ix5 = cdb.StringIndex(device=dev.index or 0)
     t0 = time.perf_counter()
     ix5.build_device(t5.data_ptr(), o5.data_ptr(), i5.data_ptr(), nd5, torch.cuda.current_stream().cuda_stream, keep=(t5, o5, i5))
     wall = time.perf_counter() - t0
     b5, inf5, v5 = ix5.build_stats(), ix5.info(), ix5.verify_sa()
-    rng = np.random.default_rng(501)
+    rng = np.random.default_rng(501)  # the same requests on every rank (a broadcast batch); columns differ per shard
+    crng = np.random.default_rng(900 + rank)
     h_ids = i5.cpu().numpy()
-    year = rng.integers(1900, 2100, size=nd5).astype(np.int64)
-    score = rng.random(nd5)
+    year = crng.integers(1900, 2100, size=nd5).astype(np.int64)
+    score = crng.random(nd5)
     ycol = cdb.NumericIndex(0, h_ids, year, device=dev.index or 0)
     scol = cdb.NumericIndex(1, h_ids, score, device=dev.index or 0)
     nreq = 100_000
     m = rng.integers(4, 13, size=nreq)
-    starts = torch.from_numpy(rng.integers(0, n5 - 16, size=nreq)).to(dev)
-    win = t5[(starts.unsqueeze(1) + torch.arange(12, device=dev).unsqueeze(0)).reshape(-1)].cpu().numpy().reshape(nreq, 12)
+    starts = torch.from_numpy(np.random.default_rng(777).integers(0, n5 - 16, size=nreq)).to(dev)  # own generator: the shared one must advance identically on every rank
+    win_t = t5[(starts.unsqueeze(1) + torch.arange(12, device=dev).unsqueeze(0)).reshape(-1)].contiguous()
+    if world > 1:
+        dist.broadcast(win_t, 0)  # the sampled keywords come from rank 0's shard and go to every rank
+    win = win_t.cpu().numpy().reshape(nreq, 12)
     rnd = rng.integers(0x20, 0x7F, size=(nreq, 12), dtype=np.uint8)
     use_rnd = rng.random(nreq) < 0.5
     win[use_rnd] = rnd[use_rnd]
@@ -305,15 +312,35 @@ def cfg5_shard_leg(dev, nbytes):
     def call(sp):
         return cdb.filter_raw([ix5, ycol, scol], args[0], args[1], args[2], args[3], None, sp)
 
+    def step():
+        """one batch: every shard answers the requests on its documents; the per-request match counts (what `count`
+        reports, src/interface.cpp:289-300) are summed over the shards with NCCL"""
+        res = call(span)
+        m_host = np.ctypeslib.as_array(res.matched, shape=(nreq,))
+        ret = res.total_pairs
+        if world > 1:
+            m_dev = torch.from_numpy(m_host).to(dev, non_blocking=False)
+            dist.all_reduce(m_dev)
+            tot = int(m_dev.sum())
+        else:
+            tot = int(m_host.sum())
+        cdb.filter_result_free(res)
+        return ret, tot
+
     for _ in range(2):
-        cdb.filter_result_free(call(span))
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     steps = 3
     for _ in range(steps):
-        res = call(span)
-        returned, matched_total = res.total_pairs, int(np.ctypeslib.as_array(res.matched, shape=(nreq,)).sum())
-        cdb.filter_result_free(res)
-    dt = (time.perf_counter() - t0) / steps
+        returned, matched_total = step()
+    torch.cuda.synchronize()
+    dt_t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt = float(dt_t.item())
     # parity on a sample: full answers (no span) against locate rows ∩ numeric predicate
     res = call(None)
     ro = np.ctypeslib.as_array(res.row_off, shape=(nreq + 1,))
@@ -341,6 +368,27 @@ def cfg5_shard_leg(dev, nbytes):
     ycol.close()
     scol.close()
     ix5.close()
+    return out
+
+
+def query_pool_leg():
+    """The reference server's calling pattern in C++ (tools/query_pool_bench.cpp): T worker threads, each calling
+    string_index::query(keyword) — ONE keyword per call (src/database.cpp:387-393) — on a 1 GB index of the cfg2 shape
+    (10^7 docs x 100 B, five-byte keywords, ~84 pairs per answer).  Calls are coalesced into device batches by cdb_query;
+    lone calls take the small-batch path."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "_build", "query_pool_bench")
+    if not os.path.exists(exe):
+        return {"error": "tools/_build/query_pool_bench has not been built (__graft_entry__.build())"}
+    r = subprocess.run([exe, "10000000", "100", "5", "400"], capture_output=True, text=True, timeout=300)
+    out = {"threads": {}, "what": "C++ worker threads calling string_index::query, one 5-byte keyword per call, 10^7 docs x 100 B"}
+    for line in r.stdout.splitlines():
+        m = re.match(r"\s*(\d+) threads:\s+(\d+) queries/s\s+\((\d+) queries in (\d+) device batches", line)
+        if m:
+            out["threads"][m.group(1)] = {"queries_per_sec": int(m.group(2)), "device_batches": int(m.group(4))}
+    if not out["threads"]:
+        out["error"] = (r.stdout + r.stderr)[-300:]
     return out
 
 
@@ -486,6 +534,46 @@ def reference_self_built(w, nd_cap=1_000_000):
     t0 = time.perf_counter()
     r.build()
     return r, {"n": int(off[-1]), "nd": nd, "build_s": time.perf_counter() - t0}
+
+
+def run_cfg5(args):
+    """BASELINE configs[4]: 40 GB of UTF-8 documents (<= 64 KB each) sharded over the ranks (5 GB per GPU at N = 8), mixed
+    numeric-range + substring constraints through cdb_filter on every shard, per-request match counts merged with NCCL.
+    `python -m torch.distributed.run ... bench.py --cfg5 --gpus N`; prints one JSON line on rank 0."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    r = cfg5_shard_leg(dev, args.cfg5_bytes, seed=55 + rank, rank=rank, world=world)
+    summary = torch.tensor([r["corpus_bytes"], r["docs"], r["build_ms"], 1.0 if r["parity_sample"] == "ok" and r["verified"] else 0.0],
+                           dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(summary) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, summary)
+    else:
+        allr = [summary]
+    if rank == 0:
+        tot_bytes = sum(float(a[0]) for a in allr)
+        out = {"metric": "cfg5_requests_per_sec", "value": r["requests_per_sec"], "unit": "requests/s", "n_gpus": world,
+               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "dtype": "int64", "data": "synthetic",
+               "config": {"workload": "cfg5", "corpus_bytes_total": tot_bytes, "shards": world,
+                          "docs_total": int(sum(float(a[1]) for a in allr)), "requests_per_step": r["requests_per_step"],
+                          "parallelism": f"doc-range shards x{world}: the same request batch on every shard (cdb_filter: substring AND "
+                                         "year range), per-request match counts summed with one NCCL all_reduce"},
+               "objects_matched_per_step_all_shards": r["objects_matched_per_step"],
+               "build_ms_slowest_shard": max(float(a[2]) for a in allr),
+               "build_corpus_GB_per_s": tot_bytes / 1e9 / (max(float(a[2]) for a in allr) / 1e3),
+               "all_shards_verified_and_parity_ok": all(float(a[3]) == 1.0 for a in allr),
+               "rank0": r}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_reference(args):
@@ -864,6 +952,7 @@ def run_ours(args):
                 if out["extras"] is None:
                     out["extras"] = {}
                 out["extras"]["cfg5_shard"] = cfg5_shard_leg(dev, 5_000_000_000)
+                out["extras"]["query_pool_cpp"] = query_pool_leg()
             except Exception as e:  # noqa: BLE001
                 if isinstance(out.get("extras"), dict):
                     out["extras"]["cfg5_shard"] = {"error": repr(e)[:300]}
@@ -1029,10 +1118,14 @@ def main():
     ap.add_argument("--no-spans", dest="spans", action="store_false", help="skip the highlight-span leg")
     ap.add_argument("--no-filter", dest="filter", action="store_false", help="e2e through cdb_locate_batch (full rows) only")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the secondary workloads (W8s, cfg2)")
+    ap.add_argument("--cfg5", action="store_true", help="BASELINE configs[4] instead of the headline workload (see run_cfg5)")
+    ap.add_argument("--cfg5-bytes", type=int, default=5_000_000_000, help="bytes of UTF-8 text per shard for --cfg5")
     ap.add_argument("--sigma", type=int, default=26, help="alphabet size (profiling aid; the named workloads use 26)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.cfg5:
+        run_cfg5(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
