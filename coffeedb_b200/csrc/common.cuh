@@ -18,7 +18,7 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
 
-constexpr int kNumSMs = 148;  // B200 (grid-size heuristics of the build kernels)
+constexpr int kNumSMs = 148;  // B200: only the fallback of num_sms() when the device cannot be asked
 
 // SM count of the current device (persistent grids are sized from it)
 inline int num_sms() {

@@ -7,21 +7,28 @@
 //                          recurrences verbatim (same midpoints, same predicates), so the interval is identical on
 //                          that not-quite-sorted array.  A probe = SA element -> doc_off pair -> 16 bytes of text,
 //                          compared as big-endian integers (== unsigned memcmp).
-//   K5-K7 gather_kernel    phase A, one launch per batch.  A CTA takes a tile of 8 consecutive patterns, one warp each
-//                          (occ <= kWarpCap): coalesced read of the SA interval, doc = element & mask, bitonic
-//                          sorting network in registers, run-length encoding.  Warps never wait for each other: the
-//                          compact row (u32 docs, + u16 counts when a document is hit more than once) goes to the scan
-//                          of the occurrence counts (an upper bound), the exact CSR offsets come from a scan of the
-//                          row lengths afterwards.
+//   K5-K7 gather_kernel    phase A, one launch per batch, one warp per pattern (occ <= kWarpCap): coalesced read of the SA
+//                          interval, doc = element & mask, sort of the <= 1024 doc indices in registers and the warp's
+//                          shared memory — a DISTRIBUTION SORT when the interval's documents are spread over the corpus
+//                          (the usual case: counting + scatter with shared-memory atomics, then a few odd-even
+//                          transposition phases), an all-ascending bitonic network when a bucket overflows (clustered
+//                          or repeated documents) and for intervals <= 128 — then run-length encoding from the
+//                          registers.  Warps never wait for each other: the compact row (u32 docs, + u16 counts when a
+//                          document is hit more than once) goes to the scan of the occurrence counts (an upper bound),
+//                          the exact CSR offsets come from a scan of the row lengths afterwards.  Variants for batches
+//                          of short intervals (<= 128 / 256 / 512) use fewer registers; the two shortest run as a
+//                          persistent grid.  In id order (for cdb_filter) the keys are id ranks instead of doc indices.
 //         translate_kernel phase B: pairs = (ids[doc], count), ordered by doc range so that the slice of ids[] in use
 //                          stays in L2 (a fused gather spent 99 GB of DRAM reads on 25.8 GB of algorithmic bytes).
+//                          Bound by the per-SM L1 -> crossbar request port, not by HBM.
+//   small batches          <= 256 keywords: one upload, search_kernel + ONE fused kernel (small_gather_kernel) writing
+//                          into mapped pinned memory, one synchronisation (a query() per request: 34 us instead of 150).
 //   K5-K7 large path       patterns with longer intervals are expanded into (entry << 32 | doc) keys, sorted by
 //                          the device radix sort (the same engine as the build) and run-length encoded, in
 //                          sub-batches of bounded size; their row lengths are known before gather_kernel runs and
 //                          enter the same scan, the rows themselves are emitted straight into the CSR result.
 //   K8  highlight spans    live in spans.cu (batched over (request, document) texts).
-// All integer work; bounded by HBM traffic and, in gather_kernel, by the ALU pipe (64*S + w*occ + 24*d
-// algorithmic bytes per pattern).
+// All integer work (64*S + w*occ + 24*d algorithmic bytes per pattern).
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -1086,7 +1093,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
             DevBuf<u64> loff(lc.nlc + 1, st);
             CDB_CUDA(cudaMemcpyAsync(loff.p, h_loff.data(), (lc.nlc + 1) * 8, cudaMemcpyHostToDevice, st));
             DevBuf<u64> k0(lc.ltotal, st), k1(lc.ltotal, st);
-            const int grid = (int)std::min<i64>(ceil_div((i64)lc.ltotal, 256), kNumSMs * 16);
+            const int grid = (int)std::min<i64>(ceil_div((i64)lc.ltotal, 256), num_sms() * 16);
             if (sa_rank)
                 large_expand_kernel<u32><<<grid, 256, 0, st>>>(sa_rank, 0xffffffffull, large_list.p + j0, lc.nlc, left.p, loff.p, lc.ltotal,
                                                                k0.p, nullptr);
@@ -1194,7 +1201,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaEventRecord(ev[5], st));
     for (LargeChunk& lc : lchunks) {
         if (lc.nu == 0) continue;
-        const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), kNumSMs * 16);
+        const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), num_sms() * 16);
         large_emit_kernel<<<grid, 256, 0, st>>>(lc.ukey.p, lc.ustart.p, lc.nu, lc.ltotal, large_list.p + lc.j0, lc.entry_first.p,
                                                 row_off.p, ids_tab, pairs.p);
         CDB_LAUNCH_CHECK();

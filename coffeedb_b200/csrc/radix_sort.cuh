@@ -254,7 +254,7 @@ int radix_sort_pairs(u64* k0, u64* k1, V* v0, V* v1, u64 n, int begin_bit, int e
     CDB_CUDA(cudaMemsetAsync(counter.p, 0, counter.bytes(), st));
     {
         u64 want = (n / 2 + 511) / 512;
-        int grid = (int)(want < (u64)(kNumSMs * 4) ? (want ? want : 1) : (u64)(kNumSMs * 4));
+        int grid = (int)(want < (u64)(num_sms() * 4) ? (want ? want : 1) : (u64)(num_sms() * 4));
         hist_kernel<<<grid, 512, 0, st>>>(k0, n, pd, ghist.p);
         CDB_LAUNCH_CHECK();
     }

@@ -683,7 +683,7 @@ struct ChunkSorter {
         if (pending.empty()) return;
         const i64 n = ix.n;
         BigBuf<u64> rank((size_t)n + 1);
-        isa_init_kernel<P><<<kNumSMs * 16, 256, 0, st>>>(sa, n, ix.mask, ix.bits1, ix.d_off, rank.p);
+        isa_init_kernel<P><<<num_sms() * 16, 256, 0, st>>>(sa, n, ix.mask, ix.bits1, ix.d_off, rank.p);
         CDB_LAUNCH_CHECK();
         for (PendingTies<P>& pt : pending) write_group_ranks(pt, pt.widx.p, pt.gid.p, nullptr, pt.pay.p, pt.wm, rank.p);
         const int tiebits = ix.bits1 + ix.bits2;
@@ -788,7 +788,7 @@ static void build_typed(Index& ix, const SymTab& tab, int b, int S, cudaStream_t
             throw Error(CDB_ERR_NOMEM, "not enough device memory for the suffix-array build workspace");
     }
     const i64 ex_tiles = ceil_div(n, EX_TILE);
-    const unsigned ex_grid = (unsigned)std::min<i64>(ex_tiles, (i64)kNumSMs * 8);
+    const unsigned ex_grid = (unsigned)std::min<i64>(ex_tiles, (i64)num_sms() * 8);
     DevBuf<i64> tile_doc((size_t)ex_tiles + 1, st);
     tile_doc_kernel<<<(unsigned)ceil_div(ex_tiles + 1, 256), 256, 0, st>>>(ix.d_off, ix.nd, n, ex_tiles, tile_doc.p);
     CDB_LAUNCH_CHECK();
@@ -934,7 +934,7 @@ __global__ void reverse_kernel(P* __restrict__ a, u64 len) {
 template <typename P>
 static void reverse_range(P* a, u64 len, cudaStream_t st) {
     if (len < 2) return;
-    const int grid = (int)std::min<i64>(ceil_div((i64)(len / 2), 256), kNumSMs * 16);
+    const int grid = (int)std::min<i64>(ceil_div((i64)(len / 2), 256), num_sms() * 16);
     reverse_kernel<P><<<grid, 256, 0, st>>>(a, len);
     CDB_LAUNCH_CHECK();
 }
@@ -1021,7 +1021,7 @@ u64 corpus_hash(const Index& ix, i64 n, cudaStream_t st) {
     CDB_CUDA(cudaMemsetAsync(acc.p, 0, 8, st));
     auto words = [&](const void* p, u64 nwords, u64 salt) {
         if (!nwords) return;
-        const int g = (int)std::min<i64>(ceil_div((i64)nwords, 256), kNumSMs * 8);
+        const int g = (int)std::min<i64>(ceil_div((i64)nwords, 256), num_sms() * 8);
         hash_words_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const u64*>(p), nwords, salt, acc.p);
         CDB_LAUNCH_CHECK();
     };
@@ -1055,7 +1055,7 @@ void build_index(Index& ix, cudaStream_t st, const SavedArraySource* saved) {
     CDB_CUDA(cudaMemsetAsync(d_max.p, 0, 8, st));
     CDB_CUDA(cudaMemsetAsync(d_present.p, 0, 1024, st));
     if (ix.nd > 0) {
-        int g = (int)std::min<i64>(ceil_div(ix.nd, 256), kNumSMs * 8);
+        int g = (int)std::min<i64>(ceil_div(ix.nd, 256), num_sms() * 8);
         doc_stats_kernel<<<g, 256, 0, st>>>(ix.d_off, ix.nd, d_max.p);
         CDB_LAUNCH_CHECK();
     }
@@ -1075,7 +1075,7 @@ void build_index(Index& ix, cudaStream_t st, const SavedArraySource* saved) {
     ix.chuck_size = std::max<i64>(4096, ix.n / 256);
     ix.mixed = false;
     if (ix.n > 0) {
-        int g = (int)std::min<i64>(ceil_div(ix.n / 16 + 1, 256), kNumSMs * 8);
+        int g = (int)std::min<i64>(ceil_div(ix.n / 16 + 1, 256), num_sms() * 8);
         byte_presence_kernel<<<g, 256, 0, st>>>(ix.d_text, ix.n, d_present.p);
         CDB_LAUNCH_CHECK();
         u32 present[256];
