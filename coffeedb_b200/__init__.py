@@ -20,7 +20,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcoffeedb_b200.so")
+LIB_PATH = os.environ.get("CDB_LIB") or os.path.join(HERE, "libcoffeedb_b200.so")  # CDB_LIB: A/B runs of a variant build
 CSRC = os.path.join(HERE, "csrc")
 
 # every symbol include/coffeedb_b200.h declares

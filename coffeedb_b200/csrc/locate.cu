@@ -416,6 +416,12 @@ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
 // lane holds ranks lane*R .. lane*R + R-1, like warp_bitonic_regs.
 //   s_out: 33*R words (pad_idx layout), s_cnt: 33*R words, 16-byte aligned.  bucket_mul = floor(2^32 * 1024 / nd), saturated.
 constexpr u32 kBucketMax = 24;
+#ifndef CDB_BUCKET_MIN_R
+#define CDB_BUCKET_MIN_R 4
+#endif
+// intervals of up to 32 * R keys with R below this always take the sorting network.  4 (intervals of 65..128 keys sort by
+// distribution too) took the shard-sized gather from 0.82 to 0.71 ms per 10^6 rows of ~84 entries; it was 8 in round 1.
+constexpr int kBucketMinR = CDB_BUCKET_MIN_R;
 
 template <int R>
 __device__ __forceinline__ bool warp_bucket_sort(u32 (&x)[R], int occ, u32 bucket_mul, u32* s_out, u32* s_cnt, int lane) {
@@ -525,7 +531,7 @@ __device__ __forceinline__ int load_sort_rle(const SAT* __restrict__ sa, i64 l, 
     }
     // s_doc / s_pos double as the sorts' scratch (33*R words each) before they are filled
     bool sorted = false;
-    if constexpr (R >= 8) {
+    if constexpr (R >= kBucketMinR) {
         if (bucket_mul) sorted = warp_bucket_sort<R>(x, occ, bucket_mul, s_doc, s_pos, lane);
     }
     if (!sorted) warp_bitonic_regs<R>(x, lane, s_doc);
