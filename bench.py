@@ -756,6 +756,9 @@ def run_ours(args):
     barrier()
     launches = cdb.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if getattr(sh, "_trace", None):
+        tr = np.array(sh._trace[-args.steps:])
+        print(f"[rank {rank}] broadcast / locate / all_gather ms per batch: {tr.mean(axis=0).round(3).tolist()}", file=sys.stderr)
     st_last = cdb.last_locate_stats()
     occs = st_last["occurrences"]  # this shard's occurrences per step
     _p, _o, last = step()  # one more (untimed) step whose result is kept for the whole-job totals

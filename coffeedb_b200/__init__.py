@@ -27,7 +27,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many", "cdb_staging_stats",
     "cdb_build", "cdb_build_device", "cdb_save", "cdb_build_or_load", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
-    "cdb_result_free", "cdb_locate_batch_device", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
+    "cdb_result_free", "cdb_locate_batch_device", "cdb_locate_batch_device_ex", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
     "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
     "cdb_numeric_create", "cdb_numeric_destroy", "cdb_numeric_query", "cdb_filter", "cdb_filter_result_free",
@@ -79,6 +79,9 @@ class FilterResult(C.Structure):
                 ("pairs", C.POINTER(C.c_int64)), ("matched", C.POINTER(C.c_int64)), ("_owner", C.c_void_p)]
 
 
+# cdb_rows_ready_fn: (user, stats32 device pointer, npat, stream)
+ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
 # cdb_filter_term (include/coffeedb_b200.h)
 TERM_DTYPE = np.dtype([("key", "<i4"), ("range", "<i4"), ("kw_begin", "<i8"), ("kw_end", "<i8")])
 
@@ -127,6 +130,7 @@ def lib():
         L.cdb_query_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cdb_result_free.restype = None
         L.cdb_locate_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp, C.POINTER(DeviceResult)]
+        L.cdb_locate_batch_device_ex.argtypes = [vp, vp, vp, C.c_int64, vp, ROWS_READY_FN, vp, C.POINTER(DeviceResult)]
         L.cdb_device_result_free.argtypes = [C.POINTER(DeviceResult)]
         L.cdb_device_result_free.restype = None
         L.cdb_locate_spans.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(Spans)]
@@ -303,6 +307,14 @@ class StringIndex:
     def locate_batch_device(self, d_pat_ptr: int, d_pat_off_ptr: int, npat: int, stream: int = 0) -> DeviceResult:
         res = DeviceResult()
         _check(self._L.cdb_locate_batch_device(self._h, d_pat_ptr, d_pat_off_ptr, npat, stream, C.byref(res)))
+        return res
+
+    def locate_batch_device_ex(self, d_pat_ptr: int, d_pat_off_ptr: int, npat: int, stream: int, rows_ready) -> DeviceResult:
+        """locate_batch_device with the sharded caller's hook: rows_ready(stats32_ptr, npat) runs once the per-pattern
+        (row length, occurrences) are enqueued, before the pairs are filled."""
+        res = DeviceResult()
+        cb = ROWS_READY_FN(lambda _user, stats, n, _st: rows_ready(stats, n))
+        _check(self._L.cdb_locate_batch_device_ex(self._h, d_pat_ptr, d_pat_off_ptr, npat, stream, cb, None, C.byref(res)))
         return res
 
     def device_result_free(self, res: DeviceResult):

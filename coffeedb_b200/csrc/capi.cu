@@ -851,6 +851,19 @@ cdb_status cdb_locate_batch_device(const cdb_index* h, const void* d_pat, const 
     CDB_CATCH
 }
 
+cdb_status cdb_locate_batch_device_ex(const cdb_index* h, const void* d_pat, const int64_t* d_pat_off, int64_t npat,
+                                      void* stream, cdb_rows_ready_fn rows_ready, void* user, cdb_device_result* out) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !out || npat < 1) throw Error(CDB_ERR_ARG, "cdb_locate_batch_device_ex: bad argument");
+    if (!ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    std::memset(out, 0, sizeof(*out));
+    DeviceSetter ds(ix->device);
+    locate_device(*ix, (const u8*)d_pat, d_pat_off, npat, (cudaStream_t)stream, out, false, rows_ready, user);
+    return CDB_OK;
+    CDB_CATCH
+}
+
 void cdb_device_result_free(cdb_device_result* r) {
     if (!r) return;
     cudaStream_t st = (cudaStream_t)r->_owner;

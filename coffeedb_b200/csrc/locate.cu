@@ -1025,7 +1025,7 @@ __global__ void stats32_kernel(const u64* __restrict__ row_off, const i64* __res
 // ---- host driver ------------------------------------------------------------------------------------------------
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                         cdb_device_result* out, bool id_order) {
+                         cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user) {
     const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
     // id order: keys are id ranks (rank_tab) and the table translate reads is ids_by_rank; when the ids already ascend with
     // the doc index both orders coincide and nothing changes
@@ -1193,6 +1193,11 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         launch_gather(std::integral_constant<int, 32>{});
     CDB_LAUNCH_CHECK();
     scan_in_place(row_off.p, (u64)npat, st);
+    // per-pattern (row length, occurrences) are final here: a sharded caller starts its exchange now, under translate
+    DevBuf<int32_t> stats((size_t)npat * 2, st);
+    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, stats.p, rowflag.p);
+    CDB_LAUNCH_CHECK();
+    if (rows_ready) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     {
@@ -1212,9 +1217,6 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
                                                 row_off.p, ids_tab, pairs.p);
         CDB_LAUNCH_CHECK();
     }
-    DevBuf<int32_t> stats((size_t)npat * 2, st);
-    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, stats.p, rowflag.p);
-    CDB_LAUNCH_CHECK();
     u64 total_pairs = 0;
     CDB_CUDA(cudaMemcpyAsync(&total_pairs, row_off.p + npat, 8, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(ev[6], st));
@@ -1384,11 +1386,11 @@ bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, 
 }
 
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                   cdb_device_result* out, bool id_order) {
+                   cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user) {
     if (ix.width == 4)
-        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out, id_order);
+        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user);
     else
-        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out, id_order);
+        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user);
 }
 
 }  // namespace cdb

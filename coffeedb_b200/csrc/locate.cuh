@@ -5,8 +5,11 @@ namespace cdb {
 // Batched locate with patterns and results in device memory (see locate.cu).
 // id_order: rows in ascending id instead of ascending doc index (what filter() merges, src/interface.cpp:79-135): the
 // interval's doc indices are mapped to id ranks before they are sorted, and translated through ids_by_rank.
+// rows_ready: called on the host once the kernels that produce stats32 (per-pattern row length and occurrences) have been
+// enqueued, before translate is — a sharded caller launches its exchange on another stream from there (cdb_locate_batch_device_ex).
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                   cdb_device_result* out, bool id_order = false);
+                   cdb_device_result* out, bool id_order = false, cdb_rows_ready_fn rows_ready = nullptr,
+                   void* rows_ready_user = nullptr);
 // Small-batch fast path (locate.cu, experimental): one upload, two launches, one synchronisation.  On success the
 // rows are in mapped pinned memory of the calling thread — valid until its next call: row q has rowlen[q] pairs at
 // pairs + 2 * (rowocc[0] + ... + rowocc[q-1]).  Returns false when the batch has to take the general path.

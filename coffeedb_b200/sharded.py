@@ -108,6 +108,10 @@ class ShardedStringIndex:
         self.nd_global = None
         self.doc_base = None
         self.narrow = False
+        # CDB_SHARD_TRACE=1: (broadcast, local locate, all_gather) milliseconds of every batch, CUDA events (profiling aid)
+        import os
+        self._trace = [] if os.environ.get("CDB_SHARD_TRACE") else None
+        self._side = None  # stream of the per-batch exchange
 
     # -- corpus --------------------------------------------------------------------------------------------------
     def add_many(self, ids, text, doc_off):
@@ -175,12 +179,19 @@ class ShardedStringIndex:
         if self.rank != src:
             d_off.copy_(off32)
 
-    def locate_local(self, d_pat, d_off):
-        """This shard's rows for the batch -> (row_off, pairs[total,2], occ[npat], keep)."""
+    def locate_local(self, d_pat, d_off, rows_ready=None):
+        """This shard's rows for the batch -> (row_off, pairs[total,2], stats32[2*npat], keep).  rows_ready(stats32 tensor)
+        is called as soon as the per-pattern counts are enqueued, before the pairs are filled (the exchange starts there)."""
         npat = d_off.numel() - 1
         if self.device.type == "cuda":
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            res = self.local.locate_batch_device(d_pat.data_ptr(), d_off.data_ptr(), npat, stream)
+            if rows_ready is not None and npat:
+                dev = self.device
+                res = self.local.locate_batch_device_ex(
+                    d_pat.data_ptr(), d_off.data_ptr(), npat, stream,
+                    lambda ptr, n: rows_ready(torch.as_tensor(_DevArray(ptr, 2 * n, "<i4"), device=dev)))
+            else:
+                res = self.local.locate_batch_device(d_pat.data_ptr(), d_off.data_ptr(), npat, stream)
             row_off = torch.as_tensor(_DevArray(res.row_off, npat + 1), device=self.device)
             tp = res.total_pairs
             pairs = (torch.as_tensor(_DevArray(res.pairs, 2 * tp), device=self.device).view(tp, 2) if tp
@@ -202,6 +213,10 @@ class ShardedStringIndex:
     def locate_batch(self, patterns=None, pat_off=None, src: int = 0, device_patterns=None) -> ShardedResult:
         """Collective.  `patterns` (list of bytes, or packed uint8 + offsets) is read on rank `src` only;
         `device_patterns=(d_pat, d_off)` skips the packing when the batch is already on the device of rank `src`."""
+        trace = self._trace
+        if trace is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         if device_patterns is not None:
             d_pat, d_off = device_patterns
             if self.world > 1:
@@ -209,7 +224,27 @@ class ShardedStringIndex:
         else:
             d_pat, d_off = self.broadcast_patterns(patterns, pat_off, src)
         npat = d_off.numel() - 1
-        row_off, pairs, stats, keep = self.locate_local(d_pat, d_off)
+        if trace is not None:
+            ev[1].record()
+        # Narrow exchange on GPUs: the all_gather of the 32-bit counts starts on a side stream from inside the locate, as
+        # soon as the counts are enqueued, and runs under the kernel that fills the pairs.
+        early = {}
+        hook = None
+        if self.world > 1 and self.narrow and self.device.type == "cuda" and npat:
+            def hook(stats_t):
+                main = torch.cuda.current_stream(self.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                self._side.wait_event(ready)
+                with torch.cuda.stream(self._side):
+                    out_t = torch.empty(self.world * 2 * npat, dtype=torch.int32, device=self.device)
+                    dist.all_gather_into_tensor(out_t, stats_t, group=self.group)
+                early["allst"] = out_t
+        row_off, pairs, stats, keep = self.locate_local(d_pat, d_off, hook)
+        if trace is not None:
+            ev[2].record()
         if self.world == 1:  # nothing to exchange: per-pattern counts are derived from this shard's result on first use
             res = ShardedResult(row_off, pairs, None, None, 0, keep)
             dev, local_stats = self.device, stats
@@ -231,9 +266,18 @@ class ShardedStringIndex:
             occ = (torch.as_tensor(_DevArray(keep.res.right, npat), device=self.device)
                    - torch.as_tensor(_DevArray(keep.res.left, npat), device=self.device)) if keep is not None else stats[npat:].to(torch.int64)
             stats = torch.stack([rows, occ]).reshape(-1)
-        allst = torch.empty(self.world * 2 * npat, dtype=stats.dtype, device=self.device)
-        dist.all_gather_into_tensor(allst, stats.contiguous(), group=self.group)
+        if "allst" in early:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            allst = early["allst"]
+            allst.record_stream(torch.cuda.current_stream(self.device))
+        else:
+            allst = torch.empty(self.world * 2 * npat, dtype=stats.dtype, device=self.device)
+            dist.all_gather_into_tensor(allst, stats.contiguous(), group=self.group)
         allst = allst.view(self.world, 2, npat)
+        if trace is not None:
+            ev[3].record()
+            ev[3].synchronize()
+            trace.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
         return ShardedResult(row_off, pairs, None, None, self.rank, keep, exchanged=allst)
 
     def _broadcast_device_patterns(self, d_pat, d_off, src: int):
