@@ -405,7 +405,7 @@ def secondary_workloads(sh, ix, text, snd, w, dev, hbm_peak):
             sh_.locate_batch(device_patterns=(d_pat, d_poff), src=0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ph = {k: 0.0 for k in ("search_ms", "gather_ms", "translate_ms", "total_ms")}
+        ph = {k: 0.0 for k in ("search_ms", "gather_ms", "translate_ms", "listing_ms", "total_ms")}
         e0.record()
         for _ in range(steps):
             res = sh_.locate_batch(device_patterns=(d_pat, d_poff), src=0)
@@ -739,7 +739,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
-    phase = {k: 0.0 for k in ("search_ms", "gather_ms", "large_ms", "tail_ms", "translate_ms", "total_ms")}
+    phase = {k: 0.0 for k in ("search_ms", "gather_ms", "large_ms", "tail_ms", "translate_ms", "listing_ms", "total_ms")}
     barrier()
     if rank == 0:
         sampler.start()
@@ -778,6 +778,48 @@ def run_ours(args):
     value = npat * args.steps / (ms_total / 1e3)
     for k in phase:
         phase[k] /= args.steps
+    listed_rows, listed_pairs = st_last["nlisted"], st_last["listed_pairs"]
+    linfo = ix.listing_info(0)
+
+    # ---- the same batches on the suffix-array path alone (CDB_LISTING_USE=0: search -> gather -> translate), so that the
+    # line also carries what keywords NOT of the directory's length cost, and stays comparable with round 1
+    sa_path = None
+    if listed_rows:
+        os.environ["CDB_LISTING_USE"] = "0"
+        try:
+            for _ in range(args.warmup):
+                step()
+            ph2 = {k: 0.0 for k in phase}
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                p2, _occ2, res2 = step()
+                st2 = cdb.last_locate_stats()
+                for k in ph2:
+                    ph2[k] += st2[k]
+                del res2
+            f1.record()
+            barrier()
+            ms2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            for k in ph2:
+                ph2[k] /= args.steps
+            sa_ms = float(ms2.item()) / args.steps
+            sa_bytes = (algorithmic_bytes_per_pattern(n_shard, width, st2["occurrences"] / npat, p2 / npat, w["m"],
+                                                      ix.prefix_directory()["symbols"]))
+            sa_path_bytes = (sa_bytes["search"] + sa_bytes["gather"]) * npat
+            sa_path = {"value": npat / (sa_ms / 1e3), "unit": UNIT, "ms_per_step": sa_ms, "phases_ms": ph2,
+                       "pairs_equal": bool(p2 == pairs),
+                       "algorithmic_bytes_per_step": sa_path_bytes,
+                       "frac_of_hbm_peak": sa_path_bytes / (ph2["total_ms"] / 1e3) / 1e9 / hbm_peak,
+                       "translate_frac": 24.0 * (p2 / npat) * npat / (ph2["translate_ms"] / 1e3) / 1e9 / hbm_peak if ph2["translate_ms"] > 0 else None,
+                       "gather_frac": width * (st2["occurrences"] / npat) * npat / (ph2["gather_ms"] / 1e3) / 1e9 / hbm_peak if ph2["gather_ms"] > 0 else None,
+                       "what": "the same batches with the document listing bypassed (CDB_LISTING_USE=0): search_kernel -> gather_kernel "
+                               "-> translate_kernel, w*occ + 24*d algorithmic bytes per keyword (SURVEY.md 8d)"}
+        finally:
+            del os.environ["CDB_LISTING_USE"]
 
     # ---- e2e: host buffers through cdb_locate_batch, H2D + D2H inside the timed region
     def e2e_step():
@@ -845,21 +887,30 @@ def run_ours(args):
     # pattern; gather_kernel (phase A) reads the SA interval (w*occ); translate_kernel (phase B) reads ids[] and
     # writes the (id, count) pairs (24*d).  The compact intermediate rows between A and B (8*d written, 8*d read)
     # are this design's own overhead and are NOT counted as algorithmic bytes.
+    # Rows answered from the document listing (keywords of exactly the directory's length): listing_emit_kernel reads
+    # 4 + hi_bytes per occurrence and writes the 16-byte pair — no ids[] lookup, no intermediate; those are the bytes it
+    # is charged with (fewer than the survey's w*occ + 24*d, which assumes the suffix-array interval is read).
+    lw = 4 + (linfo["hi_bytes"] if linfo["present"] else 0)
+    frac_listed = listed_pairs / pairs if pairs else 0.0  # share of the step's result that came from the listing
+    occ_listed = occ_pp * frac_listed if listed_rows else 0.0  # (all rows or none in the bench's batches)
+    d_listed = d_pp * frac_listed if listed_rows else 0.0
     kernels = {
         "search_kernel": (phase["search_ms"], alg["search"] * npat),
-        "gather_kernel": (phase["gather_ms"], width * occ_pp * npat),
-        "translate_kernel": (phase["translate_ms"], 24.0 * d_pp * npat),
+        "gather_kernel": (phase["gather_ms"], width * (occ_pp - occ_listed) * npat),
+        "translate_kernel": (phase["translate_ms"], 24.0 * (d_pp - d_listed) * npat),
+        "listing_emit_kernel": (phase["listing_ms"], (lw * occ_listed + 16.0 * d_listed) * npat),
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    path_bytes = (alg["search"] + alg["gather"]) * npat
+    path_bytes = alg["search"] * npat + sum(v[1] for k, v in kernels.items() if k != "search_kernel")
+    survey_bytes = (alg["search"] + alg["gather"]) * npat
     # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of the same configuration
     traffic, traffic_src = None, None
     import glob
     tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_cfg3.json")))  # the newest capture (by round tag)
     tpath = tfiles[-1] if tfiles else ""
-    if world == 1 and wname == "cfg3" and tpath:
+    if world == 1 and wname == "cfg3" and tpath and os.path.exists(tpath):
         tj = json.load(open(tpath))
         if dom in tj.get("kernels", {}):
             traffic, traffic_src = tj["kernels"][dom]["traffic"], tj["source"]
@@ -873,9 +924,14 @@ def run_ours(args):
                         "frac": (v[1] / (v[0] / 1e3) / 1e9 / hbm_peak if v[0] > 0 else 0.0)} for k, v in kernels.items()},
         "path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (phase["total_ms"] / 1e3) / 1e9,
                  "frac": path_bytes / (phase["total_ms"] / 1e3) / 1e9 / hbm_peak,
-                 "note": "w*occ + 24*d per pattern (SURVEY.md 8d) plus the search's bytes: 64*S probes, or 45 B when the "
-                         "prefix directory resolves the keyword without probing",
+                 "note": "bytes the path has to move per step: the search's (64*S probes, or 45 B when the prefix directory "
+                         "resolves the keyword without probing) + per keyword (4 + hi_bytes)*occ + 16*d when its row is "
+                         "streamed from the document listing, w*occ + 24*d (SURVEY.md 8d) when it is gathered from the suffix array",
+                 "survey_formula_bytes_per_step": survey_bytes,
+                 "survey_formula_frac": survey_bytes / (phase["total_ms"] / 1e3) / 1e9 / hbm_peak,
                  "probes_per_pattern": alg["S"]},
+        "listing": {"present": linfo["present"], "bytes_per_suffix": lw if linfo["present"] else 0, "bytes": linfo["bytes"],
+                    "build_ms": linfo["build_ms"], "rows_per_step": listed_rows, "pairs_per_step": listed_pairs},
     }
 
     # ---- CPU baseline: the reference's query() on this box's host cores, same index, bounded sample
@@ -919,6 +975,7 @@ def run_ours(args):
                        "parallelism": "replica" if world == 1 else f"doc-range shards x{world}, NCCL pattern bcast + count merge"},
             "e2e": e2e_main,
             "e2e_full_rows": e2e_full,
+            "sa_path": sa_path,
             "filter": filt,
             "gpu_launches": int(launches),
             "single_query_latency_us": single_us,
@@ -1042,7 +1099,7 @@ def filter_leg(ix, pat, poff, npat, steps):
     dt = time.perf_counter() - t0
     lst = cdb.last_locate_stats()  # the id-ordered locate inside the last call
     return {"value": npat * steps / dt, "ms_per_step": dt / steps * 1e3, "ms_each_step": [round(x, 3) for x in per_step],
-            "locate_phases_ms": {k: lst[k] for k in ("search_ms", "gather_ms", "translate_ms", "total_ms")},
+            "locate_phases_ms": {k: lst[k] for k in ("search_ms", "gather_ms", "translate_ms", "listing_ms", "total_ms")},
             "h2d_bytes_per_step": int(kw.nbytes + terms.nbytes + rto.nbytes + span.nbytes), "d2h_bytes_per_step": int(d2h),
             "pairs_returned_per_step": int(tot), "launches_per_step": (cdb.launch_count() - launches0) // steps,
             "call": f"cdb_filter: {npat} requests {{key: keyword, span: [{FILTER_SPAN[0]},{FILTER_SPAN[1]})}} -> (id, $correlation) in "

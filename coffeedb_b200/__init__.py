@@ -26,10 +26,10 @@ CSRC = os.path.join(HERE, "csrc")
 # every symbol include/coffeedb_b200.h declares
 EXPORTS = [
     "cdb_last_error", "cdb_version", "cdb_device_count", "cdb_create", "cdb_destroy", "cdb_add", "cdb_add_many", "cdb_staging_stats",
-    "cdb_build", "cdb_build_device", "cdb_save", "cdb_build_or_load", "cdb_info", "cdb_prefix_directory", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
+    "cdb_build", "cdb_build_device", "cdb_save", "cdb_build_or_load", "cdb_info", "cdb_prefix_directory", "cdb_listing_info", "cdb_export_sa", "cdb_sa_device_ptr", "cdb_locate_batch",
     "cdb_result_free", "cdb_locate_batch_device", "cdb_locate_batch_device_ex", "cdb_device_result_free", "cdb_locate_spans", "cdb_locate_spans_batch",
     "cdb_locate_spans_batch_device", "cdb_device_spans_free", "cdb_spans_free",
-    "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
+    "cdb_splice", "cdb_verify_sa", "cdb_compare_sa", "cdb_build_stats", "cdb_last_locate_stats", "cdb_last_locate_stats_ex", "cdb_launch_count", "cdb_query", "cdb_query_stats", "cdb_trim",
     "cdb_numeric_create", "cdb_numeric_destroy", "cdb_numeric_query", "cdb_filter", "cdb_filter_result_free",
     "cdb_sharded_create", "cdb_sharded_destroy", "cdb_sharded_add", "cdb_sharded_add_many", "cdb_sharded_build",
     "cdb_sharded_locate_batch", "cdb_sharded_shard", "cdb_sharded_count",
@@ -122,6 +122,7 @@ def lib():
         L.cdb_build_device.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.cdb_info.argtypes = [vp, i64p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.cdb_prefix_directory.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i64p]
+        L.cdb_listing_info.argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i64p, C.POINTER(C.c_double)]
         L.cdb_export_sa.argtypes = [vp, vp, C.c_int64]
         L.cdb_sa_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.cdb_locate_batch.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(Result)]
@@ -176,11 +177,12 @@ def launch_count() -> int:
 
 
 def last_locate_stats() -> dict:
-    ms = (C.c_double * 6)()
-    cn = (C.c_int64 * 4)()
-    lib().cdb_last_locate_stats(ms, cn)
+    ms = (C.c_double * 8)()
+    cn = (C.c_int64 * 8)()
+    lib().cdb_last_locate_stats_ex(ms, cn)
     return {"search_ms": ms[0], "gather_ms": ms[1], "large_ms": ms[2], "tail_ms": ms[3], "translate_ms": ms[4],
-            "total_ms": ms[5], "npat": cn[0], "pairs": cn[1], "occurrences": cn[2], "nlarge": cn[3]}
+            "total_ms": ms[5], "listing_ms": ms[6], "npat": cn[0], "pairs": cn[1], "occurrences": cn[2], "nlarge": cn[3],
+            "nlisted": cn[4], "listed_pairs": cn[5]}
 
 
 def _check(rc: int):
@@ -329,6 +331,12 @@ class StringIndex:
         k, b, e = C.c_int32(), C.c_int32(), C.c_int64()
         _check(self._L.cdb_prefix_directory(self._h, C.byref(k), C.byref(b), C.byref(e)))
         return {"symbols": k.value, "bits_per_symbol": b.value, "entries": e.value}
+
+    def listing_info(self, order: int = 0) -> dict:
+        """The document listing of the directory's buckets (order 0: doc order, 1: id order), see cdb_listing_info."""
+        p, hw, b, ms = C.c_int32(), C.c_int32(), C.c_int64(), C.c_double()
+        _check(self._L.cdb_listing_info(self._h, order, C.byref(p), C.byref(hw), C.byref(b), C.byref(ms)))
+        return {"present": bool(p.value), "hi_bytes": hw.value, "bytes": b.value, "build_ms": ms.value}
 
     def build_stats(self) -> dict:
         t, s, r, c = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()

@@ -37,6 +37,9 @@ void Index::free_device() {
     if (d_ids_by_rank) cudaFree(d_ids_by_rank);
     if (d_sa_rank) cudaFree(d_sa_rank);
     d_sa_rank = nullptr;
+    listing[0].reset();
+    listing[1].reset();
+    listing_state[0] = listing_state[1] = 0;
     d_ptab = nullptr;
     d_rank_tab = nullptr;
     d_ids_by_rank = nullptr;
@@ -244,6 +247,19 @@ void cdb_last_locate_stats(double* ms6, int64_t* counts4) {
     }
     if (counts4) {
         counts4[0] = s.npat; counts4[1] = s.total_pairs; counts4[2] = s.total_occ; counts4[3] = s.nlarge;
+    }
+}
+
+void cdb_last_locate_stats_ex(double* ms8, int64_t* counts8) {
+    const LocateStats& s = g_locate_stats;
+    if (ms8) {
+        cdb_last_locate_stats(ms8, nullptr);
+        ms8[6] = s.listing_ms;
+        ms8[7] = 0;
+    }
+    if (counts8) {
+        cdb_last_locate_stats(nullptr, counts8);
+        counts8[4] = s.nlisted; counts8[5] = s.listed_pairs; counts8[6] = counts8[7] = 0;
     }
 }
 
@@ -463,6 +479,26 @@ cdb_status cdb_prefix_directory(const cdb_index* h, int32_t* symbols, int32_t* b
     if (symbols) *symbols = on ? ix->pt_k : 0;
     if (bits_per_symbol) *bits_per_symbol = on ? ix->pt_b : 0;
     if (entries) *entries = on ? ((i64)1 << (ix->pt_b * ix->pt_k)) : 0;
+    return CDB_OK;
+    CDB_CATCH
+}
+
+cdb_status cdb_listing_info(const cdb_index* h, int32_t order, int32_t* present, int32_t* hi_bytes, int64_t* bytes, double* build_ms) {
+    CDB_TRY
+    const Index* ix = reinterpret_cast<const Index*>(h);
+    if (!ix || !ix->built) throw Error(CDB_ERR_STATE, "index has not been built");
+    if (order != 0 && order != 1) throw Error(CDB_ERR_ARG, "cdb_listing_info: order must be 0 or 1");
+    std::shared_ptr<Listing> L;
+    {
+        std::lock_guard<std::mutex> lk(ix->listing_mu);
+        L = ix->listing[order];
+        // ids that ascend with the doc index: the doc-order listing serves both orders
+        if (!L && order == 1 && ix->ids_order == 1) L = ix->listing[0];
+    }
+    if (present) *present = L ? 1 : 0;
+    if (hi_bytes) *hi_bytes = L ? L->hw : 0;
+    if (bytes) *bytes = L ? (i64)L->bytes : 0;
+    if (build_ms) *build_ms = L ? L->build_ms : 0.0;
     return CDB_OK;
     CDB_CATCH
 }

@@ -58,8 +58,8 @@ extern std::atomic<unsigned long long> g_launches;
 
 // per-thread timing of the last locate call (CUDA events on the launching stream), milliseconds
 struct LocateStats {
-    float search_ms = 0, gather_ms = 0, large_ms = 0, tail_ms = 0, translate_ms = 0, total_ms = 0;
-    long long npat = 0, total_pairs = 0, total_occ = 0, nlarge = 0;
+    float search_ms = 0, gather_ms = 0, large_ms = 0, tail_ms = 0, translate_ms = 0, total_ms = 0, listing_ms = 0;
+    long long npat = 0, total_pairs = 0, total_occ = 0, nlarge = 0, nlisted = 0, listed_pairs = 0;
 };
 extern thread_local LocateStats g_locate_stats;
 

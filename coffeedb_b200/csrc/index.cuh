@@ -23,6 +23,30 @@ struct SymTab {
     u16 sym[256];
 };
 
+// Document listing of the prefix directory's buckets (locate.cu: build_listing).  The suffixes of bucket c — those whose
+// first pt_k symbols code to c, SA ranks [ptab[c], ptab[c+1]) — have their documents' ids stored at the same ranks,
+// sorted by doc index (order 0, what string_index::query reports) or by id (order 1, what filter() merges), as
+// (id - base) split into a 32-bit plane and an hw-byte plane.  A keyword of exactly pt_k symbols is then answered by
+// streaming its bucket: no sort, no ids[] lookup.  dcount[c] = distinct documents of the bucket, bit 31 = some document
+// occurs more than once, kNoListing = bucket not listed (more than 1024 suffixes: such keywords take the general path).
+constexpr u32 kNoListing = 0xffffffffu;
+struct Listing {
+    u32* lo = nullptr;      // [n]
+    void* hi = nullptr;     // [n] u8 / u16 / u32 (hw = 1 / 2 / 4), nullptr when hw == 0
+    u32* dcount = nullptr;  // [2^(pt_b * pt_k)]
+    int* d_flag = nullptr;  // build-time: set when two documents share an id (the listing is then dropped)
+    int hw = 0;
+    i64 base = 0;
+    size_t bytes = 0;
+    double build_ms = 0;
+    ~Listing() {
+        if (lo) cudaFree(lo);
+        if (hi) cudaFree(hi);
+        if (dcount) cudaFree(dcount);
+        if (d_flag) cudaFree(d_flag);
+    }
+};
+
 struct Index {
     cdb_options opt{};
     int device = 0;
@@ -67,6 +91,12 @@ struct Index {
     mutable u32* d_rank_tab = nullptr;
     mutable i64* d_ids_by_rank = nullptr;
     mutable u32* d_sa_rank = nullptr;  // rank companion of the suffix array (locate.cu: id_order_tables), when memory allows
+    // document listings, [0] doc order, [1] id order (the same object when the ids ascend with the doc index); a locate
+    // holds a reference for its duration, so one can be dropped (to make room for the other order) while calls are in flight.
+    // listing_state: 0 not tried yet, 1 present, -1 not available (no directory, ids too wide, no memory, CDB_LISTING=0)
+    mutable std::mutex listing_mu;
+    mutable std::shared_ptr<Listing> listing[2];
+    mutable int listing_state[2] = {0, 0};
     // cdb_query's coalescing queue (capi.cu), created on first use
     mutable std::mutex batcher_mu;
     mutable std::shared_ptr<void> batcher;
@@ -86,5 +116,7 @@ void build_index(Index& ix, cudaStream_t st, const SavedArraySource* saved = nul
 u64 corpus_hash(const Index& ix, i64 n, cudaStream_t st);
 // locate.cu: fills ix.d_ptab (after the suffix array is complete)
 void build_prefix_table(Index& ix, cudaStream_t st);
+// locate.cu: the listing of the given order (built on first use when memory allows), or an empty pointer
+std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st);
 
 }  // namespace cdb

@@ -57,11 +57,18 @@ struct SearchCtx {
     const u8* text;
     const u64* ptab;  // prefix directory (Index::d_ptab) or nullptr
     int pt_b, pt_k;
+    const u32* dcount;  // document listing of the directory's buckets (Listing::dcount) or nullptr
 };
 
 static SearchCtx make_ctx(const Index& ix) {
-    return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k};
+    return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k, nullptr};
 }
+
+// per-pattern word of a row that is answered from the document listing: bit 63 set, bit 62 = some document repeats,
+// low bits = distinct documents (the exact row length); 0 = the row takes the general path
+constexpr u64 kPreListed = 1ull << 63;
+constexpr u64 kPreRepeat = 1ull << 62;
+constexpr u64 kPreCount = kPreRepeat - 1;
 
 // three-way comparison of keyword vs the suffix stored at SA rank M:
 //   -1: keyword <  suffix            0: keyword is a prefix of suffix (keyword <= suffix, starts_with)
@@ -99,7 +106,8 @@ __device__ __forceinline__ int compare_at(const SearchCtx& c, i64 M, const u8* _
 template <typename SAT>
 __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restrict__ pat, const i64* __restrict__ pat_off,
                                           i64 q, i64* __restrict__ left_out, i64* __restrict__ right_out,
-                                          int* __restrict__ err, const u16* s_tab) {
+                                          int* __restrict__ err, const u16* s_tab, u64& pre) {
+    pre = 0;
     const i64 ps = pat_off[q];
     const i64 m = pat_off[q + 1] - ps;
     if (m <= 0) {  // src/index.cpp:239-241
@@ -157,6 +165,11 @@ __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restri
                 }
                 hi = L;
             }
+            // a keyword of exactly k symbols is one bucket of the directory: its row is listed (unless the bucket is too long)
+            if (c.dcount && m == (i64)k && lo < hi) {
+                const u32 dc = __ldg(c.dcount + code);
+                if (dc != kNoListing) pre = kPreListed | ((dc >> 31) ? kPreRepeat : 0ull) | (u64)(dc & 0x7fffffffu);
+            }
         }
         left_out[q] = lo;
         right_out[q] = hi;
@@ -193,20 +206,35 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, co
                                                      const i64* __restrict__ pat_off, i64 npat,
                                                      i64* __restrict__ left_out, i64* __restrict__ right_out,
                                                      int* __restrict__ err, u32* __restrict__ large_list,
-                                                     unsigned long long* __restrict__ counters, u64* __restrict__ wocc) {
+                                                     unsigned long long* __restrict__ counters, u64* __restrict__ wocc,
+                                                     u64* __restrict__ pre_out, i64* __restrict__ gright) {
     __shared__ u16 s_tab[256];
     s_tab[threadIdx.x] = tab.sym[threadIdx.x];
     __syncthreads();
     const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 occ = 0;
-    if (q < npat) occ = search_one<SAT>(c, pat, pat_off, q, left_out, right_out, err, s_tab);
+    u64 pre = 0;
+    if (q < npat) occ = search_one<SAT>(c, pat, pat_off, q, left_out, right_out, err, s_tab, pre);
     if (counters == nullptr) return;
-    // classification: long intervals go to the large path; the rest is summed (capacity of the result buffer)
+    // classification: long intervals go to the large path, listed rows are streamed from the document listing; the rest
+    // is summed (capacity of the result buffer)
     if (occ > kWarpCap) {
         large_list[atomicAdd(counters + 0, 1ull)] = (u32)q;
         occ = 0;
     }
-    if (q < npat) wocc[q] = (u64)occ;  // occurrences the warp path will read for this pattern (0: large path or no hit)
+    unsigned long long locc = 0, ld = 0;
+    if (pre_out) {
+        if (pre) {  // phase A sees an empty interval for this row
+            locc = (unsigned long long)occ;
+            ld = (unsigned long long)(pre & kPreCount);
+            occ = 0;
+        }
+        if (q < npat) {
+            pre_out[q] = pre;
+            gright[q] = pre ? left_out[q] : right_out[q];
+        }
+    }
+    if (q < npat) wocc[q] = (u64)occ;  // occurrences the warp path will read for this pattern (0: large path, listed or no hit)
     unsigned long long s = (unsigned long long)occ, mx = s;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -217,6 +245,20 @@ __global__ void __launch_bounds__(256) search_kernel(SearchCtx c, SymTab tab, co
     if ((threadIdx.x & 31) == 0 && s) {
         atomicAdd(counters + 1, s);
         atomicMax(counters + 5, mx);  // longest interval on the warp path: picks the gather_kernel variant
+    }
+    if (pre_out && __any_sync(0xffffffffu, pre != 0)) {
+        unsigned long long nrow = pre ? 1ull : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            locc += __shfl_xor_sync(0xffffffffu, locc, o);
+            ld += __shfl_xor_sync(0xffffffffu, ld, o);
+            nrow += __shfl_xor_sync(0xffffffffu, nrow, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters + 3, ld);    // result pairs of the listed rows (exact)
+            atomicAdd(counters + 6, nrow);  // listed rows
+            atomicAdd(counters + 7, locc);  // their occurrences
+        }
     }
 }
 
@@ -1010,16 +1052,368 @@ static bool id_order_tables(const Index& ix, cudaStream_t st) {
 // + row_flags: bit 0 = the row's counts are not all 1 (gather_kernel left that in bit 15 of the row's seg entries;
 // rows of the large path: not known, flagged)
 __global__ void stats32_kernel(const u64* __restrict__ row_off, const i64* __restrict__ left, const i64* __restrict__ right,
-                               i64 npat, const u16* __restrict__ seg, int nranges, int32_t* __restrict__ stats,
-                               u8* __restrict__ row_flags) {
+                               i64 npat, const u16* __restrict__ seg, int nranges, const u64* __restrict__ pre,
+                               int32_t* __restrict__ stats, u8* __restrict__ row_flags) {
     const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= npat) return;
     const u64 rl = row_off[q + 1] - row_off[q];
     const i64 oc = right[q] - left[q];
-    const u16 s0 = seg[(size_t)(q / kTileWarps) * (nranges + 1) * kTileWarps + (q % kTileWarps)];
-    row_flags[q] = (oc > kWarpCap || (s0 >> 15)) ? 1 : 0;
+    const u64 p = pre ? pre[q] : 0;
+    bool rep;
+    if (p & kPreListed)
+        rep = (p & kPreRepeat) != 0;
+    else if (oc > kWarpCap)
+        rep = true;
+    else
+        rep = seg ? (seg[(size_t)(q / kTileWarps) * (nranges + 1) * kTileWarps + (q % kTileWarps)] >> 15) != 0 : false;
+    row_flags[q] = rep ? 1 : 0;
     stats[q] = rl > 0x7fffffffull ? 0x7fffffff : (int32_t)rl;
     stats[npat + q] = oc > 0x7fffffffll ? 0x7fffffff : (int32_t)oc;
+}
+
+// ---- document listing (Listing, index.cuh) ------------------------------------------------------------------------
+// Built once per index and order from the finished suffix array: one warp per directory bucket of <= kWarpCap suffixes
+// reads the bucket, maps the elements to their sort keys (doc index; id rank for the id order), sorts them with the
+// gather's own sorts and stores (id - base) of every suffix's document at the suffix's rank, in key order.  A keyword of
+// exactly pt_k symbols is one bucket: listing_emit_kernel streams its row — 4 + hw bytes read per occurrence, 16 bytes
+// written per (id, count) pair, no sort and no random lookup at query time.
+__global__ void ids_minmax_kernel(const i64* __restrict__ ids, i64 nd, long long* __restrict__ mm) {
+    long long lo = 0x7fffffffffffffffll, hi = -0x7fffffffffffffffll - 1;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += (i64)gridDim.x * blockDim.x) {
+        const long long v = ids[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 0, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+
+template <typename SAT, int R>
+__device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32 bucket_mul, u32* s_a, u32* s_b,
+                                              int lane, const u32* __restrict__ remap, const i64* __restrict__ table, i64 base,
+                                              int hw, u32* __restrict__ out_lo, void* __restrict__ out_hi, int* __restrict__ dup_flag) {
+    u32 x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        x[r] = i < occ ? (u32)((u64)ld_stream(sa + l + i) & mask) : 0xffffffffu;
+    }
+    if (remap) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r * 32 + lane < occ) x[r] = __ldg(remap + x[r]);
+    }
+    bool sorted = false;
+    if constexpr (R >= kBucketMinR) {
+        if (bucket_mul) sorted = warp_bucket_sort<R>(x, occ, bucket_mul, s_a, s_b, lane);
+    }
+    if (!sorted) warp_bitonic_regs<R>(x, lane, s_a);
+    // blocked layout: lane holds ranks lane*R .. lane*R + R-1; a rank is a run head when its key differs from the previous one's
+    const u32 prev_x = __shfl_up_sync(0xffffffffu, x[R - 1], 1);
+    int nh = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int idx = lane * R + r;
+        const u32 px = r ? x[r > 0 ? r - 1 : 0] : prev_x;
+        nh += (idx < occ && (idx == 0 || x[r] != px)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
+    // through shared memory into the striped layout (rank r*32 + lane): coalesced stores, and the keys leave the registers
+    // before the values arrive
+    __syncwarp();
+    {
+        u32* da = s_a + lane * R + ((lane * R) >> 5);
+#pragma unroll
+        for (int r = 0; r < R; ++r) da[r] = x[r];
+    }
+    __syncwarp();
+    u64 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        x[r] = s_a[pad_idx(i)];
+        v[r] = i < occ ? (u64)(__ldg(table + x[r]) - base) : 0ull;
+    }
+    bool dup = false;
+    u32 carry_x = 0;
+    u64 carry_v = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        u32 px = __shfl_up_sync(0xffffffffu, x[r], 1);
+        u64 pv = __shfl_up_sync(0xffffffffu, v[r], 1);
+        if (lane == 0) {
+            px = carry_x;
+            pv = carry_v;
+        }
+        dup |= i > 0 && i < occ && x[r] != px && v[r] == pv;  // two documents, one id: a listed row could not tell them apart
+        carry_x = __shfl_sync(0xffffffffu, x[r], 31);
+        carry_v = __shfl_sync(0xffffffffu, v[r], 31);
+        if (i < occ) {
+            out_lo[l + i] = (u32)v[r];
+            const u32 h = (u32)(v[r] >> 32);
+            if (hw == 1) reinterpret_cast<u8*>(out_hi)[l + i] = (u8)h;
+            else if (hw == 2) reinterpret_cast<u16*>(out_hi)[l + i] = (u16)h;
+            else if (hw == 4) reinterpret_cast<u32*>(out_hi)[l + i] = h;
+        }
+    }
+    if (dup) *dup_flag = 1;
+    __syncwarp();
+    return (u32)nh;
+}
+
+template <typename SAT>
+__global__ void __launch_bounds__(kTileWarps * 32, 2) listing_build_kernel(const SAT* __restrict__ sa, u64 mask, u32 bucket_mul,
+                                                                          const u64* __restrict__ ptab, u64 nentries,
+                                                                          const u32* __restrict__ remap, const i64* __restrict__ table,
+                                                                          i64 base, int hw, u32* __restrict__ out_lo,
+                                                                          void* __restrict__ out_hi, u32* __restrict__ dcount,
+                                                                          int* __restrict__ dup_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 c = (u64)blockIdx.x * kTileWarps + warp;
+    if (c >= nentries) return;
+    const i64 l = (i64)ptab[c];
+    const i64 occ64 = (i64)ptab[c + 1] - l;
+    if (occ64 <= 0 || occ64 > kWarpCap) {
+        if (lane == 0) dcount[c] = occ64 <= 0 ? 0u : kNoListing;
+        return;
+    }
+    u32* s_a = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<32>());
+    u32* s_b = s_a + 32 * 32 + 32;
+    const int occ = (int)occ64;
+    u32 d;
+#define CDB_LB(RR) listing_bucket<SAT, RR>(sa, l, occ, mask, bucket_mul, s_a, s_b, lane, remap, table, base, hw, out_lo, out_hi, dup_flag)
+    if (occ <= 32) d = CDB_LB(1);
+    else if (occ <= 64) d = CDB_LB(2);
+    else if (occ <= 128) d = CDB_LB(4);
+    else if (occ <= 256) d = CDB_LB(8);
+    else if (occ <= 512) d = CDB_LB(16);
+    else d = CDB_LB(32);
+#undef CDB_LB
+    if (lane == 0) dcount[c] = d | (d != (u32)occ ? 0x80000000u : 0u);
+}
+
+template <int HW>
+__device__ __forceinline__ u64 listing_value(const u32* __restrict__ lo, const void* __restrict__ hi, i64 i) {
+    u64 v = (u64)ld_stream_u32(lo + i);
+    if (HW == 1) v |= (u64)__ldg(reinterpret_cast<const u8*>(hi) + i) << 32;
+    if (HW == 2) v |= (u64)__ldg(reinterpret_cast<const u16*>(hi) + i) << 32;
+    if (HW == 4) v |= (u64)ld_stream_u32(reinterpret_cast<const u32*>(hi) + i) << 32;
+    return v;
+}
+
+__global__ void listing_rowlen_kernel(const u64* __restrict__ pre, i64 npat, u64* __restrict__ rowlen, int write_zero) {
+    const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    const u64 p = pre[q];
+    if (p & kPreListed)
+        rowlen[q] = p & kPreCount;
+    else if (write_zero)
+        rowlen[q] = 0;
+}
+
+// The listed rows of a batch: pairs[row_off[q] + j] = (base + listing[left[q] + j], 1) — a streaming copy — or, for the
+// rows in which a document repeats, the run-length encoding of the listed values (equal values are adjacent, ids are
+// distinct).  Persistent grid, one warp per row, the next row's descriptors in flight while the current one streams.
+constexpr int kEmU = 4;
+template <int HW>
+__global__ void __launch_bounds__(kTileWarps * 32) listing_emit_kernel(const u32* __restrict__ lo, const void* __restrict__ hi, i64 base,
+                                                                     const u64* __restrict__ pre, const i64* __restrict__ left,
+                                                                     const i64* __restrict__ right, const u64* __restrict__ row_off,
+                                                                     i64 npat, i64* __restrict__ pairs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 stride = (i64)gridDim.x * kTileWarps;
+    const u64 pol = l2_policy_evict_first();
+    i64 q = (i64)blockIdx.x * kTileWarps + warp;
+    u64 p = 0, out = 0;
+    i64 l = 0, rg = 0;
+    if (q < npat) {
+        p = pre[q];
+        l = left[q];
+        rg = right[q];
+        out = row_off[q];
+    }
+    while (q < npat) {
+        const i64 qn = q + stride;
+        u64 pn = 0, outn = 0;
+        i64 ln = 0, rn = 0;
+        if (qn < npat) {
+            pn = pre[qn];
+            ln = left[qn];
+            rn = right[qn];
+            outn = row_off[qn];
+        }
+        if (p & kPreListed) {
+            const int occ = (int)(rg - l);
+            if (!(p & kPreRepeat)) {
+                for (int j0 = 0; j0 < occ; j0 += 32 * kEmU) {
+                    u64 v[kEmU];
+#pragma unroll
+                    for (int u = 0; u < kEmU; ++u) {
+                        const int j = j0 + u * 32 + lane;
+                        if (j < occ) v[u] = listing_value<HW>(lo, hi, l + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kEmU; ++u) {
+                        const int j = j0 + u * 32 + lane;
+                        if (j < occ) st_hint_v2(pairs + 2 * (out + (u64)j), make_longlong2(base + (i64)v[u], 1), pol);
+                    }
+                }
+            } else {
+                int carry_head = 0;     // rank of the last run head before this chunk
+                u32 heads_before = 0;   // run heads before this chunk
+                u64 last_v = 0;
+                for (int j0 = 0; j0 < occ; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < occ;
+                    const u64 v = valid ? listing_value<HW>(lo, hi, l + j) : 0ull;
+                    u64 prev = __shfl_up_sync(0xffffffffu, v, 1);
+                    if (lane == 0) prev = last_v;
+                    u64 next = __shfl_down_sync(0xffffffffu, v, 1);
+                    const bool nvalid = j + 1 < occ;
+                    if (lane == 31 && nvalid) next = listing_value<HW>(lo, hi, l + j + 1);
+                    const bool head = valid && (j == 0 || v != prev);
+                    const bool tail = valid && (!nvalid || next != v);
+                    const u32 hm = __ballot_sync(0xffffffffu, head);
+                    const u32 le = hm & (0xffffffffu >> (31 - lane));  // run heads at lanes <= lane
+                    const int headpos = le ? j0 + (31 - __clz(le)) : carry_head;
+                    const u32 idx = heads_before + __popc(le) - 1;
+                    if (tail) st_hint_v2(pairs + 2 * (out + (u64)idx), make_longlong2(base + (i64)v, (i64)(j - headpos + 1)), pol);
+                    if (hm) carry_head = j0 + (31 - __clz(hm));
+                    heads_before += __popc(hm);
+                    last_v = __shfl_sync(0xffffffffu, v, 31);
+                }
+            }
+        }
+        q = qn;
+        p = pn;
+        l = ln;
+        rg = rn;
+        out = outn;
+    }
+}
+
+static size_t device_memory_available(int device, size_t* total_out) {
+    // memory held by the stream-ordered pool for query temporaries counts as available (it is re-used, not lost)
+    size_t free_b = 0, total_b = 0;
+    CDB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    cudaMemPool_t pool;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    if (total_out) *total_out = total_b;
+    return free_b + (size_t)(reserved > used ? reserved - used : 0);
+}
+
+static bool big_malloc(void** p, size_t bytes, int device) {
+    if (cudaMalloc(p, bytes) == cudaSuccess) return true;
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    if (cudaMalloc(p, bytes) == cudaSuccess) return true;
+    cudaGetLastError();
+    *p = nullptr;
+    return false;
+}
+
+template <typename SAT>
+static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, cudaStream_t st) {
+    // order 1 is only asked for when the ids do not ascend with the doc index: rank_tab / ids_by_rank exist then
+    const u32* remap = order ? ix.d_rank_tab : nullptr;
+    const i64* table = order ? ix.d_ids_by_rank : ix.d_ids;
+    const u64 nentries = 1ull << (ix.pt_b * ix.pt_k);
+    cudaEvent_t e0, e1;
+    CDB_CUDA(cudaEventCreate(&e0));
+    CDB_CUDA(cudaEventCreate(&e1));
+    CDB_CUDA(cudaEventRecord(e0, st));
+    // width of (id - smallest id)
+    long long h_mm[2] = {0x7fffffffffffffffll, -0x7fffffffffffffffll - 1};
+    {
+        DevBuf<long long> mm(2, st);
+        CDB_CUDA(cudaMemcpyAsync(mm.p, h_mm, 16, cudaMemcpyHostToDevice, st));
+        ids_minmax_kernel<<<num_sms() * 4, 256, 0, st>>>(ix.d_ids, ix.nd, mm.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaMemcpyAsync(h_mm, mm.p, 16, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaStreamSynchronize(st));
+    }
+    const u64 span = (u64)h_mm[1] - (u64)h_mm[0];  // exact in unsigned arithmetic
+    if (h_mm[1] < h_mm[0] || span >> 63) return {};
+    const int hw = span < (1ull << 32) ? 0 : span < (1ull << 40) ? 1 : span < (1ull << 48) ? 2 : 4;
+    if (const char* e = getenv("CDB_LISTING_MAX_HW"))
+        if (hw > atoi(e)) return {};
+    const size_t need = (size_t)ix.n * (4 + hw) + (size_t)nentries * 4 + 256;
+    size_t total_b = 0;
+    size_t avail = device_memory_available(ix.device, &total_b);
+    const size_t keep_free = total_b / 8;  // query temporaries and results
+    size_t budget = ~(size_t)0;            // CDB_LISTING_BUDGET_MB: cap on the listings of one index (tests: forces the swap)
+    if (const char* e = getenv("CDB_LISTING_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
+    const int other = 1 - order;
+    auto other_bytes = [&]() { return ix.listing[other] && ix.listing[other] != ix.listing[order] ? ix.listing[other]->bytes : (size_t)0; };
+    if (avail < need + keep_free || need + other_bytes() > budget) {
+        // make room: the listing of the other order goes (it is rebuilt when that order is asked for again; calls that are
+        // using it keep it alive until they return)
+        if (other_bytes()) {
+            ix.listing[other].reset();
+            ix.listing_state[other] = 0;
+            avail = device_memory_available(ix.device, &total_b);
+        }
+        if (avail < need + keep_free || need > budget) return {};
+    }
+    auto L = std::make_shared<Listing>();
+    L->hw = hw;
+    L->base = (i64)h_mm[0];
+    L->bytes = need;
+    if (!big_malloc((void**)&L->lo, (size_t)ix.n * 4, ix.device)) return {};
+    if (hw && !big_malloc(&L->hi, (size_t)ix.n * hw, ix.device)) return {};
+    if (!big_malloc((void**)&L->dcount, (size_t)nentries * 4, ix.device)) return {};
+    if (!big_malloc((void**)&L->d_flag, 4, ix.device)) return {};
+    CDB_CUDA(cudaMemsetAsync(L->d_flag, 0, 4, st));
+    const char* env_buckets = getenv("CDB_GATHER_BUCKETS");
+    const bool use_buckets = !env_buckets || atoi(env_buckets) != 0;
+    const u32 bucket_mul = use_buckets && ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
+    const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
+    CDB_CUDA(cudaFuncSetAttribute(listing_build_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    listing_build_kernel<SAT><<<(unsigned)ceil_div((i64)nentries, kTileWarps), kTileWarps * 32, smem, st>>>(
+        reinterpret_cast<const SAT*>(ix.d_sa), ix.mask, bucket_mul, ix.d_ptab, nentries, remap, table, L->base, hw, L->lo, L->hi,
+        L->dcount, L->d_flag);
+    CDB_LAUNCH_CHECK();
+    int h_flag = 0;
+    CDB_CUDA(cudaMemcpyAsync(&h_flag, L->d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaEventRecord(e1, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    L->build_ms = ms;
+    if (getenv("CDB_DEBUG_TIMING")) fprintf(stderr, "[cdb] document listing (order %d, %d + 4 bytes per suffix): %.1f ms%s\n", order, hw, ms, h_flag ? " — dropped: two documents share an id" : "");
+    if (h_flag) return {};
+    return L;
+}
+
+std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st) {
+    if (!ix.d_ptab || ix.pt_k <= 0 || ix.n <= 0 || ix.nd <= 0) return {};
+    std::lock_guard<std::mutex> lk(ix.listing_mu);
+    if (ix.listing_state[order] > 0) return ix.listing[order];
+    if (ix.listing_state[order] < 0) return {};
+    const char* e = getenv("CDB_LISTING");
+    std::shared_ptr<Listing> L;
+    if (!e || atoi(e) != 0) L = ix.width == 4 ? build_listing_typed<u32>(ix, order, st) : build_listing_typed<u64>(ix, order, st);
+    ix.listing[order] = L;
+    ix.listing_state[order] = L ? 1 : -1;
+    return L;
 }
 
 // ---- host driver ------------------------------------------------------------------------------------------------
@@ -1032,38 +1426,55 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     const u32* remap = nullptr;
     const u32* sa_rank = nullptr;
     const i64* ids_tab = ix.d_ids;
+    int order = 0;
     if (id_order && id_order_tables(ix, st)) {
+        order = 1;
         ids_tab = ix.d_ids_by_rank;
         if (ix.d_sa_rank)
             sa_rank = ix.d_sa_rank;  // sa_rank[i] = rank of the id of the document suffix i belongs to
         else
             remap = ix.d_rank_tab;   // no room for the companion: the ranks are looked up per occurrence (slower)
     }
+    // document listing of this order (held for the duration of the call): keywords of exactly pt_k symbols are streamed from it
+    // (CDB_LISTING_USE=0, read per call: this call takes the suffix-array path whatever the index has — A/B measurements)
+    const char* env_use = getenv("CDB_LISTING_USE");
+    const std::shared_ptr<Listing> lst = (env_use && atoi(env_use) == 0) ? std::shared_ptr<Listing>() : get_listing(ix, order, st);
     const i64 ntiles = ceil_div(npat, kTileWarps);
     DevBuf<i64> left(npat, st), right(npat, st);
     DevBuf<u64> row_off(npat + 1, st);
     DevBuf<u64> dlarge;                          // row counts of large-path patterns (only allocated when needed)
-    DevBuf<unsigned long long> counters(6, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] unused, [4] translate ticket, [5] longest warp-path interval
+    DevBuf<unsigned long long> counters(8, st);  // [0] large patterns, [1] occurrences on the warp path, [2] err, [3] pairs of the listed rows, [4] translate ticket, [5] longest warp-path interval, [6] listed rows, [7] their occurrences
     DevBuf<u32> large_list(npat, st);
     CDB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
     cudaEvent_t* ev = thread_ctx(ix.device).ev;  // 7 of the thread's cached timing events
     CDB_CUDA(cudaEventRecord(ev[0], st));
     SearchCtx c = make_ctx(ix);
     DevBuf<u64> alloc_off(npat + 1, st);
+    DevBuf<u64> pre;      // per pattern: answered from the listing (and its exact row length) or not
+    DevBuf<i64> gright;   // right end of the interval as phase A sees it (== left for listed rows)
+    if (lst) {
+        c.dcount = lst->dcount;
+        pre.alloc(npat, st);
+        gright.alloc(npat, st);
+    }
     int* err = reinterpret_cast<int*>(counters.p + 2);
     search_kernel<SAT><<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(c, ix.symtab, d_pat, d_pat_off, npat, left.p, right.p, err,
-                                                                      large_list.p, counters.p, alloc_off.p);
+                                                                      large_list.p, counters.p, alloc_off.p, pre.p, gright.p);
     CDB_LAUNCH_CHECK();
+    const i64* right_a = lst ? gright.p : right.p;
     // where every pattern's compact row goes: exclusive scan (in place) of the warp-path occurrence counts, which are
     // upper bounds of the row lengths
     scan_in_place(alloc_off.p, (u64)npat, st);
     CDB_CUDA(cudaEventRecord(ev[1], st));
-    unsigned long long hc[6];
+    unsigned long long hc[8];
     CDB_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaStreamSynchronize(st));
     if ((int)(hc[2] & 0xffffffffu)) throw Error(CDB_ERR_EMPTY_KEYWORD, "Empty keywords are not allowed");
     const u64 nl = hc[0];
-    u64 total_occ = hc[1];
+    const u64 nlisted = hc[6], listed_pairs = hc[3];
+    u64 total_occ = hc[1] + hc[7];
+    // a batch answered from the listing alone (no warp-path occurrence, no long interval) skips phases A and B
+    const bool general = hc[1] > 0 || nl > 0 || nlisted == 0;
     CDB_CUDA(cudaEventRecord(ev[2], st));
     // large path, phase 1: exact row counts of the long intervals.  The occurrences of the large patterns are
     // expanded, sorted and run-length encoded in sub-batches of bounded size (25 bytes of temporaries per occurrence);
@@ -1131,18 +1542,24 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     }
     CDB_CUDA(cudaEventRecord(ev[3], st));
     // phase A: rows <= occurrences on the warp path + exact rows of the large path
-    const u64 cap_pairs = hc[1] + nu;
+    const u64 cap_warp = hc[1] + nu;           // compact rows of phase A
+    const u64 cap_pairs = cap_warp + listed_pairs;
     int nranges, rshift;
     ids_ranges(ix.nd, &nranges, &rshift);
     // Few lookups compared with the size of ids[] (short rows, e.g. long keywords): one pass over all rows costs less
     // than nranges sparse ones, and there is nothing for L2 to keep.
-    if (nranges > 1 && cap_pairs * 8 < (u64)ix.nd && !getenv("CDB_RANGE_BITS")) {
+    if (nranges > 1 && cap_warp * 8 < (u64)ix.nd && !getenv("CDB_RANGE_BITS")) {
         nranges = 1;
         rshift = 40;
     }
-    DevBuf<u32> cdocs((size_t)cap_pairs, st);
-    DevBuf<u16> ccnt((size_t)cap_pairs, st);  // only touched for rows with repeated documents
-    DevBuf<u16> seg((size_t)ntiles * (nranges + 1) * kTileWarps, st);
+    DevBuf<u32> cdocs;
+    DevBuf<u16> ccnt;  // only touched for rows with repeated documents
+    DevBuf<u16> seg;
+    if (general) {
+        cdocs.alloc((size_t)cap_warp, st);
+        ccnt.alloc((size_t)cap_warp, st);
+        seg.alloc((size_t)ntiles * (nranges + 1) * kTileWarps, st);
+    }
     DevBuf<i64> pairs((size_t)cap_pairs * 2, st);
     DevBuf<u8> rowflag((size_t)npat, st);
     // distribution-sort scale: bucket = doc * 1024 / nd (0 switches the sorting network on for every interval)
@@ -1164,7 +1581,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
             if (smem > 48 * 1024) CDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             i64 grid = ntiles;
             if (MAXR <= 8) grid = std::min<i64>(ntiles, (i64)num_sms() * resident_ctas((const void*)kernel, kTileWarps * 32, smem));
-            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa_rank, 0xffffffffull, bucket_mul, left.p, right.p, npat, dlarge.p,
+            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa_rank, 0xffffffffull, bucket_mul, left.p, right_a, npat, dlarge.p,
                                                                  alloc_off.p, row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, nullptr);
             return;
         }
@@ -1175,7 +1592,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
                 const int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32, smem);
                 grid = std::min<i64>(ntiles, (i64)num_sms() * per_sm);
             }
-            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right.p, npat, dlarge.p, alloc_off.p,
+            kernel<<<(unsigned)grid, kTileWarps * 32, smem, st>>>(sa, ix.mask, bucket_mul, left.p, right_a, npat, dlarge.p, alloc_off.p,
                                                                  row_off.p, cdocs.p, ccnt.p, seg.p, nranges, rshift, remap);
         };
         if (remap)
@@ -1183,24 +1600,30 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         else
             go(gather_kernel<SAT, MAXR, false>);
     };
-    if (hc[5] <= 128)
-        launch_gather(std::integral_constant<int, 4>{});
-    else if (mid_variants && hc[5] <= 256)
-        launch_gather(std::integral_constant<int, 8>{});
-    else if (mid_variants && hc[5] <= 512)
-        launch_gather(std::integral_constant<int, 16>{});
-    else
-        launch_gather(std::integral_constant<int, 32>{});
-    CDB_LAUNCH_CHECK();
+    if (general) {
+        if (hc[5] <= 128)
+            launch_gather(std::integral_constant<int, 4>{});
+        else if (mid_variants && hc[5] <= 256)
+            launch_gather(std::integral_constant<int, 8>{});
+        else if (mid_variants && hc[5] <= 512)
+            launch_gather(std::integral_constant<int, 16>{});
+        else
+            launch_gather(std::integral_constant<int, 32>{});
+        CDB_LAUNCH_CHECK();
+    }
+    if (nlisted) {  // the listed rows' lengths are known from the directory (phase A left 0 for them)
+        listing_rowlen_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(pre.p, npat, row_off.p, general ? 0 : 1);
+        CDB_LAUNCH_CHECK();
+    }
     scan_in_place(row_off.p, (u64)npat, st);
     // per-pattern (row length, occurrences) are final here: a sharded caller starts its exchange now, under translate
     DevBuf<int32_t> stats((size_t)npat * 2, st);
-    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, stats.p, rowflag.p);
+    stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, pre.p, stats.p, rowflag.p);
     CDB_LAUNCH_CHECK();
     if (rows_ready) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
-    {
+    if (general) {
         const i64 nitems = ceil_div(npat, 32) * nranges;
         const int per_sm = resident_ctas((const void*)translate_kernel, kTrWarps * 32);
         const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)num_sms() * per_sm);
@@ -1210,6 +1633,22 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[5], st));
+    // the listed rows: streamed from the document listing into their CSR rows
+    if (nlisted) {
+        auto emit = [&](auto kernel) {
+            const int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
+            const i64 grid = std::min<i64>(ntiles, (i64)num_sms() * per_sm);
+            kernel<<<(unsigned)grid, kTileWarps * 32, 0, st>>>(lst->lo, lst->hi, lst->base, pre.p, left.p, right.p, row_off.p, npat, pairs.p);
+        };
+        switch (lst->hw) {
+            case 0: emit(listing_emit_kernel<0>); break;
+            case 1: emit(listing_emit_kernel<1>); break;
+            case 2: emit(listing_emit_kernel<2>); break;
+            default: emit(listing_emit_kernel<4>); break;
+        }
+        CDB_LAUNCH_CHECK();
+    }
+    CDB_CUDA(cudaEventRecord(ev[7], st));
     for (LargeChunk& lc : lchunks) {
         if (lc.nu == 0) continue;
         const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), num_sms() * 16);
@@ -1227,12 +1666,15 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         cudaEventElapsedTime(&ls.large_ms, ev[2], ev[3]);
         cudaEventElapsedTime(&ls.gather_ms, ev[3], ev[4]);  // gather_kernel (phase A)
         cudaEventElapsedTime(&ls.translate_ms, ev[4], ev[5]);   // translate_kernel (phase B)
-        cudaEventElapsedTime(&ls.tail_ms, ev[5], ev[6]);   // large-path emit + final read-back
+        cudaEventElapsedTime(&ls.listing_ms, ev[5], ev[7]);  // listing_emit_kernel (rows answered from the document listing)
+        cudaEventElapsedTime(&ls.tail_ms, ev[7], ev[6]);   // large-path emit + final read-back
         cudaEventElapsedTime(&ls.total_ms, ev[0], ev[6]);
         ls.npat = npat;
         ls.total_pairs = (long long)total_pairs;
         ls.total_occ = (long long)total_occ;
         ls.nlarge = (long long)nl;
+        ls.nlisted = (long long)nlisted;
+        ls.listed_pairs = (long long)listed_pairs;
     }
     out->npat = npat;
     out->total_pairs = (i64)total_pairs;
@@ -1353,7 +1795,7 @@ static bool locate_small_typed(const Index& ix, const u8* pat, const i64* pat_of
     u32* large_list = reinterpret_cast<u32*>(wocc + kSmallMaxPat);
     SearchCtx c = make_ctx(ix);
     search_kernel<SAT><<<1, 256, 0, st>>>(c, ix.symtab, d_pat, d_off, (i64)npat, left, right, reinterpret_cast<int*>(counters + 2),
-                                         large_list, counters, wocc);
+                                         large_list, counters, wocc, nullptr, nullptr);
     CDB_LAUNCH_CHECK();
     const u32 bucket_mul = ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
     const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();

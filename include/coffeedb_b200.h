@@ -144,6 +144,14 @@ cdb_status cdb_info(const cdb_index* idx, int64_t* n, int64_t* nd, int32_t* widt
  * `bits_per_symbol` bits each index `entries` + 1 interval boundaries; symbols = 0 when the index has none (tiny
  * corpora, or the note-N1 layout where the reference's exact binary search must run). */
 cdb_status cdb_prefix_directory(const cdb_index* idx, int32_t* symbols, int32_t* bits_per_symbol, int64_t* entries);
+/* The document listing built beside the prefix directory (no reference counterpart): for every directory
+ * bucket of at most 1024 suffixes, the ids of the suffixes' documents in the order query() reports them (order 0: ascending
+ * doc index, src/index.cpp:288-322) or filter() merges them (order 1: ascending id, src/interface.cpp:82,88), 4 + hi_bytes
+ * bytes per suffix.  A keyword of exactly `symbols` (cdb_prefix_directory) symbols is answered by streaming its bucket.
+ * Order 0 is built by cdb_build when device memory allows, order 1 on the first id-ordered call (cdb_filter); when there
+ * is no room for both, the one not in use is dropped.  present = 0: none (no directory, ids spanning more than 2^63,
+ * two documents with one id, no memory, or CDB_LISTING=0) — every keyword then takes the suffix-array path. */
+cdb_status cdb_listing_info(const cdb_index* idx, int32_t order, int32_t* present, int32_t* hi_bytes, int64_t* bytes, double* build_ms);
 /* Copies the packed suffix array to host memory (n*width bytes), for parity checks. */
 cdb_status cdb_export_sa(const cdb_index* idx, void* buf, int64_t buf_bytes);
 /* Device pointer of the packed suffix array (borrowed). */
@@ -308,6 +316,9 @@ cdb_status cdb_build_stats(const cdb_index* idx, double* total_ms, double* sort_
  * tail (large-path emit + total read-back), translate (phase B), total}; counts4 = {npat, pairs, occurrences,
  * patterns that took the large-interval path}. */
 void cdb_last_locate_stats(double* ms6, int64_t* counts4);
+/* Same with the listing phase: ms8 = {the six above, listing (rows streamed from the document listing), 0};
+ * counts8 = {the four above, rows answered from the listing, their result pairs, 0, 0}. */
+void cdb_last_locate_stats_ex(double* ms8, int64_t* counts8);
 /* Number of CUDA kernels this library has launched in this process. */
 uint64_t cdb_launch_count(void);
 /* Returns the idle pinned host buffers the library keeps for result re-use to the driver (the pool is also capped:
