@@ -27,13 +27,11 @@ struct SymTab {
 // first pt_k symbols code to c, SA ranks [ptab[c], ptab[c+1]) — have their documents' ids stored at the same ranks,
 // sorted by doc index (order 0, what string_index::query reports) or by id (order 1, what filter() merges), as
 // (id - base) split into a 32-bit plane and an hw-byte plane.  A keyword of exactly pt_k symbols is then answered by
-// streaming its bucket: no sort, no ids[] lookup.  dcount[c] = distinct documents of the bucket, bit 31 = some document
-// occurs more than once, kNoListing = bucket not listed (more than 1024 suffixes: such keywords take the general path).
-constexpr u32 kNoListing = 0xffffffffu;
+// streaming its bucket: no sort, no ids[] lookup.  Which buckets are listed (1 .. 1024 suffixes; longer ones take the
+// general path), their number of distinct documents and whether one repeats sit in the high bits of ptab[c] (locate.cu).
 struct Listing {
     u32* lo = nullptr;      // [n]
     void* hi = nullptr;     // [n] u8 / u16 / u32 (hw = 1 / 2 / 4), nullptr when hw == 0
-    u32* dcount = nullptr;  // [2^(pt_b * pt_k)]
     int* d_flag = nullptr;  // build-time: set when two documents share an id (the listing is then dropped)
     int hw = 0;
     i64 base = 0;
@@ -42,7 +40,6 @@ struct Listing {
     ~Listing() {
         if (lo) cudaFree(lo);
         if (hi) cudaFree(hi);
-        if (dcount) cudaFree(dcount);
         if (d_flag) cudaFree(d_flag);
     }
 };

@@ -57,11 +57,11 @@ struct SearchCtx {
     const u8* text;
     const u64* ptab;  // prefix directory (Index::d_ptab) or nullptr
     int pt_b, pt_k;
-    const u32* dcount;  // document listing of the directory's buckets (Listing::dcount) or nullptr
+    bool listed;  // a document listing of the directory's buckets is in use: the high bits of ptab[] say which rows it answers
 };
 
 static SearchCtx make_ctx(const Index& ix) {
-    return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k, nullptr};
+    return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k, false};
 }
 
 // per-pattern word of a row that is answered from the document listing: bit 63 set, bit 62 = some document repeats,
@@ -69,6 +69,12 @@ static SearchCtx make_ctx(const Index& ix) {
 constexpr u64 kPreListed = 1ull << 63;
 constexpr u64 kPreRepeat = 1ull << 62;
 constexpr u64 kPreCount = kPreRepeat - 1;
+// A directory entry holds an SA rank in its low 48 bits.  Once a listing has been built, the high bits of ptab[c] describe
+// bucket c (ranks [ptab[c], ptab[c+1])): bit 63 = listed (1 .. kWarpCap suffixes), bit 62 = some document occurs more than
+// once, bits 48..58 = distinct documents.  The search finds them in the entry it reads anyway.
+constexpr u64 kPtRank = (1ull << 48) - 1;
+constexpr int kPtCountShift = 48;
+constexpr u64 kPtCountMask = 0x7ffull;
 
 // three-way comparison of keyword vs the suffix stored at SA rank M:
 //   -1: keyword <  suffix            0: keyword is a prefix of suffix (keyword <= suffix, starts_with)
@@ -143,8 +149,9 @@ __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restri
         i64 lo = 0, hi = 0;
         if (!absent) {
             const int sh = b * (k - kk);
-            lo = (i64)__ldg(c.ptab + (code << sh));
-            hi = (i64)__ldg(c.ptab + ((code + 1) << sh));
+            const u64 e_lo = __ldg(c.ptab + (code << sh));
+            lo = (i64)(e_lo & kPtRank);
+            hi = (i64)(__ldg(c.ptab + ((code + 1) << sh)) & kPtRank);
             if (m > (i64)k && lo < hi) {
                 i64 L = lo, R = hi;
                 while (L < R) {
@@ -166,10 +173,8 @@ __device__ __forceinline__ i64 search_one(const SearchCtx& c, const u8* __restri
                 hi = L;
             }
             // a keyword of exactly k symbols is one bucket of the directory: its row is listed (unless the bucket is too long)
-            if (c.dcount && m == (i64)k && lo < hi) {
-                const u32 dc = __ldg(c.dcount + code);
-                if (dc != kNoListing) pre = kPreListed | ((dc >> 31) ? kPreRepeat : 0ull) | (u64)(dc & 0x7fffffffu);
-            }
+            if (c.listed && m == (i64)k && lo < hi && (e_lo >> 63))
+                pre = kPreListed | (((e_lo >> 62) & 1) ? kPreRepeat : 0ull) | ((e_lo >> kPtCountShift) & kPtCountMask);
         }
         left_out[q] = lo;
         right_out[q] = hi;
@@ -1173,19 +1178,20 @@ __device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l,
 
 template <typename SAT>
 __global__ void __launch_bounds__(kTileWarps * 32, 2) listing_build_kernel(const SAT* __restrict__ sa, u64 mask, u32 bucket_mul,
-                                                                          const u64* __restrict__ ptab, u64 nentries,
+                                                                          u64* ptab, u64 nentries,
                                                                           const u32* __restrict__ remap, const i64* __restrict__ table,
                                                                           i64 base, int hw, u32* __restrict__ out_lo,
-                                                                          void* __restrict__ out_hi, u32* __restrict__ dcount,
-                                                                          int* __restrict__ dup_flag) {
+                                                                          void* __restrict__ out_hi, int* __restrict__ dup_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 c = (u64)blockIdx.x * kTileWarps + warp;
     if (c >= nentries) return;
-    const i64 l = (i64)ptab[c];
-    const i64 occ64 = (i64)ptab[c + 1] - l;
+    // other warps tag their own entries while this one reads: 8-byte accesses, the rank bits never change
+    const u64 e_lo = *reinterpret_cast<const volatile u64*>(ptab + c);
+    const i64 l = (i64)(e_lo & kPtRank);
+    const i64 occ64 = (i64)(*reinterpret_cast<const volatile u64*>(ptab + c + 1) & kPtRank) - l;
     if (occ64 <= 0 || occ64 > kWarpCap) {
-        if (lane == 0) dcount[c] = occ64 <= 0 ? 0u : kNoListing;
+        if (lane == 0 && (e_lo >> kPtCountShift)) ptab[c] = e_lo & kPtRank;
         return;
     }
     u32* s_a = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<32>());
@@ -1200,7 +1206,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) listing_build_kernel(const
     else if (occ <= 512) d = CDB_LB(16);
     else d = CDB_LB(32);
 #undef CDB_LB
-    if (lane == 0) dcount[c] = d | (d != (u32)occ ? 0x80000000u : 0u);
+    if (lane == 0) ptab[c] = (u64)l | (1ull << 63) | (d != (u32)occ ? (1ull << 62) : 0ull) | ((u64)d << kPtCountShift);
 }
 
 template <int HW>
@@ -1225,9 +1231,27 @@ __global__ void listing_rowlen_kernel(const u64* __restrict__ pre, i64 npat, u64
 // The listed rows of a batch: pairs[row_off[q] + j] = (base + listing[left[q] + j], 1) — a streaming copy — or, for the
 // rows in which a document repeats, the run-length encoding of the listed values (equal values are adjacent, ids are
 // distinct).  Persistent grid, one warp per row, the next row's descriptors in flight while the current one streams.
-constexpr int kEmU = 4;
+#ifndef CDB_EMIT_U
+#define CDB_EMIT_U 4
+#endif
+#ifndef CDB_EMIT_MINB
+#define CDB_EMIT_MINB 1
+#endif
+#ifndef CDB_EMIT_ST
+#define CDB_EMIT_ST 0
+#endif
+constexpr int kEmU = CDB_EMIT_U;
+__device__ __forceinline__ void emit_store(i64* p, longlong2 v, u64 pol) {
+#if CDB_EMIT_ST == 0
+    st_hint_v2(p, v, pol);
+#elif CDB_EMIT_ST == 1
+    *reinterpret_cast<longlong2*>(p) = v;
+#else
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+#endif
+}
 template <int HW>
-__global__ void __launch_bounds__(kTileWarps * 32) listing_emit_kernel(const u32* __restrict__ lo, const void* __restrict__ hi, i64 base,
+__global__ void __launch_bounds__(kTileWarps * 32, CDB_EMIT_MINB) listing_emit_kernel(const u32* __restrict__ lo, const void* __restrict__ hi, i64 base,
                                                                      const u64* __restrict__ pre, const i64* __restrict__ left,
                                                                      const i64* __restrict__ right, const u64* __restrict__ row_off,
                                                                      i64 npat, i64* __restrict__ pairs) {
@@ -1266,7 +1290,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) listing_emit_kernel(const u32
 #pragma unroll
                     for (int u = 0; u < kEmU; ++u) {
                         const int j = j0 + u * 32 + lane;
-                        if (j < occ) st_hint_v2(pairs + 2 * (out + (u64)j), make_longlong2(base + (i64)v[u], 1), pol);
+                        if (j < occ) emit_store(pairs + 2 * (out + (u64)j), make_longlong2(base + (i64)v[u], 1), pol);
                     }
                 }
             } else {
@@ -1353,7 +1377,7 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     const int hw = span < (1ull << 32) ? 0 : span < (1ull << 40) ? 1 : span < (1ull << 48) ? 2 : 4;
     if (const char* e = getenv("CDB_LISTING_MAX_HW"))
         if (hw > atoi(e)) return {};
-    const size_t need = (size_t)ix.n * (4 + hw) + (size_t)nentries * 4 + 256;
+    const size_t need = (size_t)ix.n * (4 + hw) + 256;
     size_t total_b = 0;
     size_t avail = device_memory_available(ix.device, &total_b);
     const size_t keep_free = total_b / 8;  // query temporaries and results
@@ -1377,7 +1401,6 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     L->bytes = need;
     if (!big_malloc((void**)&L->lo, (size_t)ix.n * 4, ix.device)) return {};
     if (hw && !big_malloc(&L->hi, (size_t)ix.n * hw, ix.device)) return {};
-    if (!big_malloc((void**)&L->dcount, (size_t)nentries * 4, ix.device)) return {};
     if (!big_malloc((void**)&L->d_flag, 4, ix.device)) return {};
     CDB_CUDA(cudaMemsetAsync(L->d_flag, 0, 4, st));
     const char* env_buckets = getenv("CDB_GATHER_BUCKETS");
@@ -1387,7 +1410,7 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     CDB_CUDA(cudaFuncSetAttribute(listing_build_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     listing_build_kernel<SAT><<<(unsigned)ceil_div((i64)nentries, kTileWarps), kTileWarps * 32, smem, st>>>(
         reinterpret_cast<const SAT*>(ix.d_sa), ix.mask, bucket_mul, ix.d_ptab, nentries, remap, table, L->base, hw, L->lo, L->hi,
-        L->dcount, L->d_flag);
+        L->d_flag);
     CDB_LAUNCH_CHECK();
     int h_flag = 0;
     CDB_CUDA(cudaMemcpyAsync(&h_flag, L->d_flag, 4, cudaMemcpyDeviceToHost, st));
@@ -1453,7 +1476,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<u64> pre;      // per pattern: answered from the listing (and its exact row length) or not
     DevBuf<i64> gright;   // right end of the interval as phase A sees it (== left for listed rows)
     if (lst) {
-        c.dcount = lst->dcount;
+        c.listed = true;
         pre.alloc(npat, st);
         gright.alloc(npat, st);
     }
@@ -1636,7 +1659,8 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     // the listed rows: streamed from the document listing into their CSR rows
     if (nlisted) {
         auto emit = [&](auto kernel) {
-            const int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
+            int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
+            if (const char* e = getenv("CDB_EMIT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // experiment knob
             const i64 grid = std::min<i64>(ntiles, (i64)num_sms() * per_sm);
             kernel<<<(unsigned)grid, kTileWarps * 32, 0, st>>>(lst->lo, lst->hi, lst->base, pre.p, left.p, right.p, row_off.p, npat, pairs.p);
         };
