@@ -169,6 +169,16 @@ struct FKeyDev {
     const i64* row_off;  // string: this batch's id-ordered rows
     const i64* pairs;
     const u8* row_flags; //         bit 0: the row's counts are not all 1
+    // rows answered from the document listing in which no document repeats are not written into pairs (locate.cuh:
+    // LazyListed): pre[row] says which, the row is listing[left[row] ..) + lst_base with every count 1; need[row] is set
+    // for the rows a merge reads in full, which are then written after all
+    const u64* pre;
+    const i64* left;
+    const u32* lst_lo;
+    const void* lst_hi;
+    i64 lst_base;
+    int lst_hw;
+    u8* need;
     const u64* vkey;     // numeric
     const i64* vid;
     const u64* ikey;
@@ -202,6 +212,10 @@ struct FArgs {
     // one-keyword requests whose counts do not all tie: handed from filter_direct_kernel to filter_direct_sort_kernel
     u32* slow_list;
     unsigned long long* slow_count;
+    // one-keyword requests whose row has a repeated document: handed from filter_direct_batch_kernel to filter_direct_kernel
+    u32* flag_list;
+    unsigned long long* flag_count;
+    unsigned long long* cls_count;  // [5] requests per class (size_kernel)
 };
 
 // CLS_DIRECT: warp path whose single term is the whole request (no other key, no $correlation range): nothing to merge
@@ -282,6 +296,14 @@ __global__ void __launch_bounds__(256) size_kernel(FArgs A) {
     A.cls[r] = cls;
     A.alloc[r] = alloc;
     A.tbig[r] = tbig;
+    // requests per class, so that the host fetches the class array only when some request needs its attention
+    const u32 am = __activemask();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c <= CLS_DIRECT; ++c) {
+        const u32 m = __ballot_sync(am, cls == c);
+        if (m && lane == __ffs(m) - 1) atomicAdd(A.cls_count + c, (unsigned long long)__popc(m));
+    }
 }
 
 // ---- the merge ------------------------------------------------------------------------------------------------------
@@ -585,10 +607,96 @@ struct DirectScratch {
 };
 constexpr int kFDirectWarps = 8;
 
+// The usual one-keyword request: no count of its row exceeds 1 (the locate's row flag is clear), so every $correlation
+// ties and the span is cut out of the row through the permutation table.  A warp takes 32 requests: every lane walks the
+// descriptors of ONE request (term -> row -> offsets -> span: a chain of eight dependent loads, which a warp per request
+// spent 3 ms per 10^6 requests waiting for), then the warp copies the spans four requests at a time — permutation-table
+// entries, then the elements (from the row, or from the document listing when the locate left the row unwritten), then the
+// stores.  Requests whose row has a repeated document go to filter_direct_kernel through flag_list.
+__global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_batch_kernel(FArgs A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 r = ((i64)blockIdx.x * kFDirectWarps + warp) * 32 + lane;
+    int key = 0;
+    u32 cnt = 0;
+    bool lazy = false;
+    u64 src_off = 0, out_off = 0;
+    i64 from = 0;  // first listing entry of the row (lazy) or first pair of the row
+    if (r < A.nreq && A.cls[r] == CLS_DIRECT) {
+        const i64 t0 = A.req_term_off[r];
+        key = A.terms[t0].key;
+        const FKeyDev& F = A.keys[key];
+        const i64 rowi = A.term_row[t0];
+        const i64 r0 = F.row_off[rowi];
+        const u64 n = (u64)(F.row_off[rowi + 1] - r0);
+        u64 sb, se;
+        request_span(A, r, n, &sb, &se);
+        if (F.row_flags[rowi] & 1) {
+            A.flag_list[atomicAdd(A.flag_count, 1ull)] = (u32)r;
+        } else {
+            A.matched[r] = n;
+            A.fin_len[r] = se - sb;
+            A.raw_len[r] = se - sb;
+            if (se > sb) {
+                cnt = (u32)(se - sb);
+                src_off = n * (n - 1) / 2 + sb;
+                out_off = A.raw_off[r];
+                const u64 p = F.pre ? F.pre[rowi] : 0;
+                lazy = (p & kPreListed) && !(p & kPreRepeat);
+                from = lazy ? F.left[rowi] : r0;
+            }
+        }
+    }
+    u32 todo = __ballot_sync(0xffffffffu, cnt != 0);
+    while (todo) {
+        int who[4];
+        u32 c4[4];
+        u64 so[4], oo[4];
+        i64 fr[4];
+        int ky[4];
+        bool lz[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            who[g] = todo ? __ffs(todo) - 1 : -1;
+            if (todo) todo &= todo - 1;
+            const int w = who[g] < 0 ? 0 : who[g];
+            c4[g] = __shfl_sync(0xffffffffu, cnt, w);
+            so[g] = __shfl_sync(0xffffffffu, src_off, w);
+            oo[g] = __shfl_sync(0xffffffffu, out_off, w);
+            fr[g] = __shfl_sync(0xffffffffu, from, w);
+            ky[g] = __shfl_sync(0xffffffffu, key, w);
+            lz[g] = __shfl_sync(0xffffffffu, (int)lazy, w) != 0;
+            if (who[g] < 0) c4[g] = 0;
+        }
+        u32 cmax = max(max(c4[0], c4[1]), max(c4[2], c4[3]));
+        for (u32 j0 = 0; j0 < cmax; j0 += 32) {
+            const u32 j = j0 + lane;
+            u32 idx[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) idx[g] = j < c4[g] ? (u32)__ldg(A.pi + so[g] + j) : 0u;
+            longlong2 v[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (j < c4[g]) {
+                    const FKeyDev& K = A.keys[ky[g]];
+                    if (lz[g])
+                        v[g] = make_longlong2(K.lst_base + (i64)listed_row_value(K.lst_lo, K.lst_hi, K.lst_hw, fr[g] + (i64)idx[g]), 1);
+                    else
+                        v[g] = *reinterpret_cast<const longlong2*>(K.pairs + 2 * (fr[g] + (i64)idx[g]));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (j < c4[g]) *reinterpret_cast<longlong2*>(A.raw + 2 * (oo[g] + j)) = v[g];
+        }
+    }
+}
+
+// One-keyword requests whose row has a document hit more than once (flag_list): a warp per request reads the counts.
 __global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const i64 r = (i64)blockIdx.x * kFDirectWarps + warp;
-    if (r >= A.nreq || A.cls[r] != CLS_DIRECT) return;
+    const unsigned long long nflag = *A.flag_count;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * kFDirectWarps + warp; k < nflag; k += (unsigned long long)gridDim.x * kFDirectWarps) {
+    const i64 r = (i64)A.flag_list[k];
     const cdb_filter_term t = A.terms[A.req_term_off[r]];
     const FKeyDev& F = A.keys[t.key];
     const i64 rowi = A.term_row[A.req_term_off[r]];
@@ -602,7 +710,7 @@ __global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs
         A.fin_len[r] = se - sb;
         A.raw_len[r] = se - sb;
     }
-    if (se <= sb) return;
+    if (se <= sb) continue;
     // the locate already knows whether every count of the row is 1 (no document hit twice): then all $correlations tie
     // and the row is not read at all beyond the span's elements
     i64 mn = 1, mx = 1;
@@ -626,12 +734,33 @@ __global__ void __launch_bounds__(kFDirectWarps * 32) filter_direct_kernel(FArgs
         // own, one 32-thread CTA per such row — left here, one slow lane kept its whole 8-request CTA resident for
         // ~150 us and the kernel ran at 17 % occupancy (3.1 ms instead of well under 1).
         if (lane == 0) A.slow_list[atomicAdd(A.slow_count, 1ull)] = (u32)r;
-        return;
+        continue;
     }
     i64* out = A.raw + 2 * A.raw_off[r];
     const u16* src = A.pi + n * (n - 1) / 2;
+    if (F.pre && (F.pre[rowi] & kPreListed) && !(F.pre[rowi] & kPreRepeat)) {
+        // the row was never written: its elements come straight from the document listing (every $correlation is 1)
+        const i64 l = F.left[rowi];
+        for (u64 j = sb + lane; j < se; j += 32)
+            *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) =
+                make_longlong2(F.lst_base + (i64)listed_row_value(F.lst_lo, F.lst_hi, F.lst_hw, l + (i64)src[j]), 1);
+        continue;
+    }
     for (u64 j = sb + lane; j < se; j += 32)
         *reinterpret_cast<longlong2*>(out + 2 * (j - sb)) = *reinterpret_cast<const longlong2*>(row + 2 * (u64)src[j]);
+    }
+}
+
+// requests that merge rows (anything but CLS_DIRECT) read them in full: mark their unwritten rows
+__global__ void __launch_bounds__(256) mark_need_kernel(FArgs A) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.nreq) return;
+    const u8 c = A.cls[r];
+    if (c != CLS_WARP && c != CLS_CTA) return;
+    for (i64 t = A.req_term_off[r]; t < A.req_term_off[r + 1]; ++t) {
+        const FKeyDev& K = A.keys[A.terms[t].key];
+        if (K.kind == 0 && K.need) K.need[A.term_row[t]] = 1;
+    }
 }
 
 // The rows filter_direct_kernel handed over: one 32-thread CTA per row (persistent grid over the list), lane 0 runs the
@@ -857,6 +986,8 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
     std::vector<FKeyDev> hkeys((size_t)std::max(b.nkeys, 1));
     std::vector<cdb_device_result> results((size_t)b.nkeys);
     for (auto& r : results) std::memset(&r, 0, sizeof(r));
+    std::vector<std::unique_ptr<LazyListed>> lazies((size_t)b.nkeys);
+    std::vector<DevBuf<u8>> needs((size_t)b.nkeys);
     auto free_results = [&] {
         for (auto& r : results) cdb_device_result_free(&r);
     };
@@ -898,10 +1029,23 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
                 CDB_LAUNCH_CHECK();
                 CDB_CUDA(cudaMemcpyAsync(poff.p + nkw, len.p + nterm, 8, cudaMemcpyDeviceToDevice, st));
                 lap("keywords of one key packed");
-                locate_device(*ix, pat.p, poff.p, nkw, st, &results[k], /*id_order=*/true);  // throws on an empty keyword
+                lazies[k].reset(new LazyListed());
+                locate_device(*ix, pat.p, poff.p, nkw, st, &results[k], /*id_order=*/true, nullptr, nullptr, lazies[k].get());  // throws on an empty keyword
                 F.row_off = results[k].row_off;
                 F.pairs = results[k].pairs;
                 F.row_flags = results[k].row_flags;
+                if (lazies[k]->active) {
+                    const LazyListed& z = *lazies[k];
+                    F.pre = z.pre;
+                    F.left = results[k].left;
+                    F.lst_lo = z.lst->lo;
+                    F.lst_hi = z.lst->hi;
+                    F.lst_base = z.lst->base;
+                    F.lst_hw = z.lst->hw;
+                    needs[k].alloc((size_t)nkw, st);
+                    CDB_CUDA(cudaMemsetAsync(needs[k].p, 0, (size_t)nkw, st));
+                    F.need = needs[k].p;
+                }
                 lap("locate in id order");
             }
         }
@@ -928,14 +1072,18 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         A.tbig = d_tbig.p;
         A.err = d_err.p;
         const unsigned rgrid = (unsigned)ceil_div(nreq, 256);
+        DevBuf<unsigned long long> d_cls_count(5, st);
+        CDB_CUDA(cudaMemsetAsync(d_cls_count.p, 0, 40, st));
+        A.cls_count = d_cls_count.p;
         size_kernel<<<rgrid, 256, 0, st>>>(A);
         CDB_LAUNCH_CHECK();
         prim::exclusive_scan<u64>(d_alloc.p, o.raw_off.p, (u64)nreq, st);
         prim::exclusive_scan<u64>(d_tbig.p, d_tbig.p, (u64)nreq, st);
-        std::vector<u8> hcls((size_t)nreq);
+        std::vector<u8> hcls;
+        unsigned long long ncls[5] = {0, 0, 0, 0, 0};
         u64 tot[2];
         int herr = 0;
-        CDB_CUDA(cudaMemcpyAsync(hcls.data(), d_cls.p, (size_t)nreq, cudaMemcpyDeviceToHost, st));
+        CDB_CUDA(cudaMemcpyAsync(ncls, d_cls_count.p, 40, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaMemcpyAsync(&tot[0], o.raw_off.p + nreq, 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaMemcpyAsync(&tot[1], d_tbig.p + nreq, 8, cudaMemcpyDeviceToHost, st));
         CDB_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, st));
@@ -943,14 +1091,31 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         lap("sizes and classes");
         if (herr == 1) throw Error(CDB_ERR_ARG, "cdb_filter: a request has more than 64 terms");
         if (herr) throw Error(CDB_ERR_ARG, "cdb_filter: a term names a key, range or keyword outside the batch");
+        // which requests take the CTA path or are numeric-only: the class array comes to the host only when there are any
+        // (walking 10^6 classes here cost more than the kernels of a batch of one-keyword requests)
         std::vector<i64> big, num;
-        i64 ndirect = 0, nwarp = 0;
-        for (i64 r = 0; r < nreq; ++r) {
-            const u8 c = hcls[r];
-            if (c == CLS_CTA) big.push_back(r);
-            if (c == CLS_NUM) num.push_back(r);
-            ndirect += c == CLS_DIRECT;
-            nwarp += c == CLS_WARP || c == CLS_NONE;
+        const i64 ndirect = (i64)ncls[CLS_DIRECT], nwarp = (i64)(ncls[CLS_WARP] + ncls[CLS_NONE]);
+        const i64 nmerge = (i64)(ncls[CLS_WARP] + ncls[CLS_CTA]);
+        if (ncls[CLS_CTA] + ncls[CLS_NUM]) {
+            hcls.resize((size_t)nreq);
+            CDB_CUDA(cudaMemcpyAsync(hcls.data(), d_cls.p, (size_t)nreq, cudaMemcpyDeviceToHost, st));
+            CDB_CUDA(cudaStreamSynchronize(st));
+            for (i64 r = 0; r < nreq; ++r) {
+                const u8 c = hcls[r];
+                if (c == CLS_CTA) big.push_back(r);
+                if (c == CLS_NUM) num.push_back(r);
+            }
+        }
+        // rows left unwritten by the locate (answered from the document listing) that a merge reads in full
+        if (nmerge) {
+            bool any = false;
+            for (int k = 0; k < b.nkeys; ++k) any = any || (lazies[k] && lazies[k]->active);
+            if (any) {
+                mark_need_kernel<<<rgrid, 256, 0, st>>>(A);
+                CDB_LAUNCH_CHECK();
+                for (int k = 0; k < b.nkeys; ++k)
+                    if (lazies[k] && lazies[k]->active) emit_listed_rows(results[k], *lazies[k], needs[k].p, st);
+            }
         }
         o.raw.alloc((size_t)tot[0] * 2, st);
         A.raw_off = o.raw_off.p;
@@ -960,15 +1125,20 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
         A.matched = o.matched.p;
         A.pi = sort_table(filter_device_of(b), st);
         // ---- the merges
-        DevBuf<u32> slow_list;
+        DevBuf<u32> slow_list, flag_list;
         DevBuf<unsigned long long> slow_count;
         if (ndirect) {
             slow_list.alloc((size_t)nreq, st);
-            slow_count.alloc(1, st);
-            CDB_CUDA(cudaMemsetAsync(slow_count.p, 0, 8, st));
+            flag_list.alloc((size_t)nreq, st);
+            slow_count.alloc(2, st);
+            CDB_CUDA(cudaMemsetAsync(slow_count.p, 0, 16, st));
             A.slow_list = slow_list.p;
             A.slow_count = slow_count.p;
-            filter_direct_kernel<<<(unsigned)ceil_div(nreq, kFDirectWarps), kFDirectWarps * 32, 0, st>>>(A);
+            A.flag_list = flag_list.p;
+            A.flag_count = slow_count.p + 1;
+            filter_direct_batch_kernel<<<(unsigned)ceil_div(nreq, kFDirectWarps * 32), kFDirectWarps * 32, 0, st>>>(A);
+            CDB_LAUNCH_CHECK();
+            filter_direct_kernel<<<(unsigned)std::min<i64>(ceil_div(nreq, kFDirectWarps), (i64)num_sms() * 8), kFDirectWarps * 32, 0, st>>>(A);
             CDB_LAUNCH_CHECK();
             filter_direct_sort_kernel<<<(unsigned)std::min<i64>(nreq, (i64)num_sms() * 32), 32, 0, st>>>(A);
             CDB_LAUNCH_CHECK();
@@ -1006,6 +1176,17 @@ void filter_batch_device(const cdb_filter_batch& b, cudaStream_t st, FilterOut& 
             CDB_LAUNCH_CHECK();
         }
         lap("CTA-path merges, numeric scans");
+        // ---- every request is a one-keyword request (or matches nothing): a request's slot in raw[] is exactly its answer
+        // (alloc == span length == final length), so raw[] IS the compact result
+        if (ncls[CLS_WARP] + ncls[CLS_CTA] + ncls[CLS_NUM] == 0) {
+            CDB_CUDA(cudaStreamSynchronize(st));
+            o.total_fin = tot[0];
+            o.fin = std::move(o.raw);
+            o.fin_off = std::move(o.raw_off);
+            lap("compaction");
+            free_results();
+            return;
+        }
         // ---- compact result: finished rows move to their final place, pending rows (CTA path, numeric-only) keep a hole
         prim::exclusive_scan<u64>(d_fin_len.p, o.fin_off.p, (u64)nreq, st);
         CDB_CUDA(cudaMemcpyAsync(&o.total_fin, o.fin_off.p + nreq, 8, cudaMemcpyDeviceToHost, st));

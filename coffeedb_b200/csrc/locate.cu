@@ -64,11 +64,7 @@ static SearchCtx make_ctx(const Index& ix) {
     return SearchCtx{ix.d_sa, ix.n, ix.bits1, ix.mask, ix.d_off, ix.d_text, ix.d_ptab, ix.pt_b, ix.pt_k, false};
 }
 
-// per-pattern word of a row that is answered from the document listing: bit 63 set, bit 62 = some document repeats,
-// low bits = distinct documents (the exact row length); 0 = the row takes the general path
-constexpr u64 kPreListed = 1ull << 63;
-constexpr u64 kPreRepeat = 1ull << 62;
-constexpr u64 kPreCount = kPreRepeat - 1;
+// (kPreListed / kPreRepeat / kPreCount — the per-pattern word of a row answered from the document listing — are in locate.cuh)
 // A directory entry holds an SA rank in its low 48 bits.  Once a listing has been built, the high bits of ptab[c] describe
 // bucket c (ranks [ptab[c], ptab[c+1])): bit 63 = listed (1 .. kWarpCap suffixes), bit 62 = some document occurs more than
 // once, bits 48..58 = distinct documents.  The search finds them in the entry it reads anyway.
@@ -1114,7 +1110,7 @@ __device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l,
     if (remap) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (r * 32 + lane < occ) x[r] = __ldg(remap + x[r]);
+            if (r * 32 + lane < occ) x[r] = ld_stream_u32(remap + x[r]);
     }
     bool sorted = false;
     if constexpr (R >= kBucketMinR) {
@@ -1146,7 +1142,8 @@ __device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l,
     for (int r = 0; r < R; ++r) {
         const int i = r * 32 + lane;
         x[r] = s_a[pad_idx(i)];
-        v[r] = i < occ ? (u64)(__ldg(table + x[r]) - base) : 0ull;
+        // (no L1 allocation: a caching load of these random 8-byte reads moved ~110 bytes of DRAM per lookup)
+        v[r] = i < occ ? (u64)((i64)ld_stream_u64(reinterpret_cast<const u64*>(table) + x[r]) - base) : 0ull;
     }
     bool dup = false;
     u32 carry_x = 0;
@@ -1254,7 +1251,10 @@ template <int HW>
 __global__ void __launch_bounds__(kTileWarps * 32, CDB_EMIT_MINB) listing_emit_kernel(const u32* __restrict__ lo, const void* __restrict__ hi, i64 base,
                                                                      const u64* __restrict__ pre, const i64* __restrict__ left,
                                                                      const i64* __restrict__ right, const u64* __restrict__ row_off,
-                                                                     i64 npat, i64* __restrict__ pairs) {
+                                                                     i64 npat, i64* __restrict__ pairs, int mode,
+                                                                     const u8* __restrict__ need) {
+    // mode 0: every listed row; 1: only the rows in which a document repeats (the others are read lazily by the caller);
+    // 2: the rows without repeats that the caller needs in full after all (need[q] != 0)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 stride = (i64)gridDim.x * kTileWarps;
     const u64 pol = l2_policy_evict_first();
@@ -1277,7 +1277,10 @@ __global__ void __launch_bounds__(kTileWarps * 32, CDB_EMIT_MINB) listing_emit_k
             rn = right[qn];
             outn = row_off[qn];
         }
-        if (p & kPreListed) {
+        bool go = (p & kPreListed) != 0;
+        if (mode == 1) go = go && (p & kPreRepeat);
+        if (mode == 2) go = go && !(p & kPreRepeat) && need[q];
+        if (go) {
             const int occ = (int)(rg - l);
             if (!(p & kPreRepeat)) {
                 for (int j0 = 0; j0 < occ; j0 += 32 * kEmU) {
@@ -1440,9 +1443,33 @@ std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st
 }
 
 // ---- host driver ------------------------------------------------------------------------------------------------
+static void launch_listing_emit(const Listing& L, const u64* pre, const i64* left, const i64* right, const u64* row_off, i64 npat,
+                                i64* pairs, int mode, const u8* need, cudaStream_t st) {
+    auto emit = [&](auto kernel) {
+        int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
+        if (const char* e = getenv("CDB_EMIT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // experiment knob
+        const i64 grid = std::min<i64>(ceil_div(npat, kTileWarps), (i64)num_sms() * per_sm);
+        kernel<<<(unsigned)grid, kTileWarps * 32, 0, st>>>(L.lo, L.hi, L.base, pre, left, right, row_off, npat, pairs, mode, need);
+    };
+    switch (L.hw) {
+        case 0: emit(listing_emit_kernel<0>); break;
+        case 1: emit(listing_emit_kernel<1>); break;
+        case 2: emit(listing_emit_kernel<2>); break;
+        default: emit(listing_emit_kernel<4>); break;
+    }
+    CDB_LAUNCH_CHECK();
+}
+
+void emit_listed_rows(const cdb_device_result& res, const LazyListed& lazy, const u8* d_need, cudaStream_t st) {
+    if (!lazy.active || !lazy.lst || res.npat <= 0) return;
+    launch_listing_emit(*lazy.lst, lazy.pre, res.left, res.right, reinterpret_cast<const u64*>(res.row_off), res.npat, res.pairs, 2,
+                        d_need, st);
+}
+
 template <typename SAT>
 static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                         cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user) {
+                         cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user,
+                         LazyListed* lazy) {
     const SAT* sa = reinterpret_cast<const SAT*>(ix.d_sa);
     // id order: keys are id ranks (rank_tab) and the table translate reads is ids_by_rank; when the ids already ascend with
     // the doc index both orders coincide and nothing changes
@@ -1658,19 +1685,13 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     CDB_CUDA(cudaEventRecord(ev[5], st));
     // the listed rows: streamed from the document listing into their CSR rows
     if (nlisted) {
-        auto emit = [&](auto kernel) {
-            int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
-            if (const char* e = getenv("CDB_EMIT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // experiment knob
-            const i64 grid = std::min<i64>(ntiles, (i64)num_sms() * per_sm);
-            kernel<<<(unsigned)grid, kTileWarps * 32, 0, st>>>(lst->lo, lst->hi, lst->base, pre.p, left.p, right.p, row_off.p, npat, pairs.p);
-        };
-        switch (lst->hw) {
-            case 0: emit(listing_emit_kernel<0>); break;
-            case 1: emit(listing_emit_kernel<1>); break;
-            case 2: emit(listing_emit_kernel<2>); break;
-            default: emit(listing_emit_kernel<4>); break;
+        // a lazy caller reads the rows without repeats from the listing itself
+        launch_listing_emit(*lst, pre.p, left.p, right.p, row_off.p, npat, pairs.p, lazy ? 1 : 0, nullptr, st);
+        if (lazy) {
+            lazy->lst = lst;
+            lazy->stream = st;
+            lazy->active = true;
         }
-        CDB_LAUNCH_CHECK();
     }
     CDB_CUDA(cudaEventRecord(ev[7], st));
     for (LargeChunk& lc : lchunks) {
@@ -1710,6 +1731,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     out->stats32 = stats.detach();
     out->row_flags = rowflag.detach();
     out->_owner = (void*)st;
+    if (lazy && lazy->active) lazy->pre = pre.detach();
 }
 
 
@@ -1852,11 +1874,11 @@ bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, 
 }
 
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
-                   cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user) {
+                   cdb_device_result* out, bool id_order, cdb_rows_ready_fn rows_ready, void* rows_ready_user, LazyListed* lazy) {
     if (ix.width == 4)
-        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user);
+        locate_typed<u32>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user, lazy);
     else
-        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user);
+        locate_typed<u64>(ix, d_pat, d_pat_off, npat, st, out, id_order, rows_ready, rows_ready_user, lazy);
 }
 
 }  // namespace cdb

@@ -7,9 +7,39 @@ namespace cdb {
 // interval's doc indices are mapped to id ranks before they are sorted, and translated through ids_by_rank.
 // rows_ready: called on the host once the kernels that produce stats32 (per-pattern row length and occurrences) have been
 // enqueued, before translate is — a sharded caller launches its exchange on another stream from there (cdb_locate_batch_device_ex).
+// lazy: a caller that reads rows selectively (cdb_filter) passes a LazyListed — the rows answered from the document listing
+// in which no document repeats are then NOT written into out->pairs (their CSR slots stay unwritten); the caller reads
+// them from the listing (listed_row_value) and asks for the ones it needs in full with emit_listed_rows.
+struct LazyListed {
+    std::shared_ptr<Listing> lst;  // held while the rows are in use
+    u64* pre = nullptr;            // device [npat]: kPreListed | kPreRepeat | row length per row (0: an ordinary row); owned
+    cudaStream_t stream = nullptr;
+    bool active = false;           // some rows were left unwritten
+    ~LazyListed() {
+        if (pre) cudaFreeAsync(pre, stream);
+    }
+};
 void locate_device(const Index& ix, const u8* d_pat, const i64* d_pat_off, i64 npat, cudaStream_t st,
                    cdb_device_result* out, bool id_order = false, cdb_rows_ready_fn rows_ready = nullptr,
-                   void* rows_ready_user = nullptr);
+                   void* rows_ready_user = nullptr, LazyListed* lazy = nullptr);
+// writes the unwritten listed rows q with need[q] != 0 into res.pairs
+void emit_listed_rows(const cdb_device_result& res, const LazyListed& lazy, const u8* d_need, cudaStream_t st);
+
+// per-pattern word of a row that is answered from the document listing: bit 63 set, bit 62 = some document repeats,
+// low bits = distinct documents (the exact row length); 0 = the row takes the general path
+constexpr u64 kPreListed = 1ull << 63;
+constexpr u64 kPreRepeat = 1ull << 62;
+constexpr u64 kPreCount = kPreRepeat - 1;
+#ifdef __CUDACC__
+// (id - base) of listing entry i; hw = bytes of the high plane (0, 1, 2, 4)
+__device__ __forceinline__ u64 listed_row_value(const u32* __restrict__ lo, const void* __restrict__ hi, int hw, i64 i) {
+    u64 v = (u64)__ldg(lo + i);
+    if (hw == 1) v |= (u64)__ldg(reinterpret_cast<const u8*>(hi) + i) << 32;
+    else if (hw == 2) v |= (u64)__ldg(reinterpret_cast<const u16*>(hi) + i) << 32;
+    else if (hw == 4) v |= (u64)__ldg(reinterpret_cast<const u32*>(hi) + i) << 32;
+    return v;
+}
+#endif
 // Small-batch fast path (locate.cu, experimental): one upload, two launches, one synchronisation.  On success the
 // rows are in mapped pinned memory of the calling thread — valid until its next call: row q has rowlen[q] pairs at
 // pairs + 2 * (rowocc[0] + ... + rowocc[q-1]).  Returns false when the batch has to take the general path.
