@@ -1355,15 +1355,28 @@ static bool big_malloc(void** p, size_t bytes, int device) {
     return false;
 }
 
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() {
+        CDB_CUDA(cudaEventCreate(&a));
+        CDB_CUDA(cudaEventCreate(&b));
+    }
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// *deferred: the listing was not built because the other order's would have to go and this order has not been asked for
+// often enough yet (see below) — the caller takes the suffix-array path and asks again next time
 template <typename SAT>
-static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, cudaStream_t st) {
+static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, cudaStream_t st, bool* deferred) {
     // order 1 is only asked for when the ids do not ascend with the doc index: rank_tab / ids_by_rank exist then
     const u32* remap = order ? ix.d_rank_tab : nullptr;
     const i64* table = order ? ix.d_ids_by_rank : ix.d_ids;
     const u64 nentries = 1ull << (ix.pt_b * ix.pt_k);
-    cudaEvent_t e0, e1;
-    CDB_CUDA(cudaEventCreate(&e0));
-    CDB_CUDA(cudaEventCreate(&e1));
+    EventPair evp;
+    const cudaEvent_t e0 = evp.a, e1 = evp.b;
     CDB_CUDA(cudaEventRecord(e0, st));
     // width of (id - smallest id)
     long long h_mm[2] = {0x7fffffffffffffffll, -0x7fffffffffffffffll - 1};
@@ -1390,8 +1403,16 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     auto other_bytes = [&]() { return ix.listing[other] && ix.listing[other] != ix.listing[order] ? ix.listing[other]->bytes : (size_t)0; };
     if (avail < need + keep_free || need + other_bytes() > budget) {
         // make room: the listing of the other order goes (it is rebuilt when that order is asked for again; calls that are
-        // using it keep it alive until they return)
+        // using it keep it alive until they return) — but only once this order has been asked for CDB_LISTING_SWAP_AFTER
+        // times (default 2) with no call of the other order in between: callers that alternate between query() and
+        // filter() keep one listing and pay the suffix-array path for the other order instead of a rebuild per call
         if (other_bytes()) {
+            int after = 2;
+            if (const char* e = getenv("CDB_LISTING_SWAP_AFTER")) after = atoi(e);
+            if (++ix.listing_miss[order] < after) {
+                *deferred = true;
+                return {};
+            }
             ix.listing[other].reset();
             ix.listing_state[other] = 0;
             avail = device_memory_available(ix.device, &total_b);
@@ -1421,8 +1442,6 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     CDB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     L->build_ms = ms;
     if (getenv("CDB_DEBUG_TIMING")) fprintf(stderr, "[cdb] document listing (order %d, %d + 4 bytes per suffix): %.1f ms%s\n", order, hw, ms, h_flag ? " — dropped: two documents share an id" : "");
     if (h_flag) return {};
@@ -1432,13 +1451,20 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
 std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st) {
     if (!ix.d_ptab || ix.pt_k <= 0 || ix.n <= 0 || ix.nd <= 0) return {};
     std::lock_guard<std::mutex> lk(ix.listing_mu);
-    if (ix.listing_state[order] > 0) return ix.listing[order];
+    if (ix.listing_state[order] > 0) {
+        ix.listing_miss[1 - order] = 0;
+        return ix.listing[order];
+    }
     if (ix.listing_state[order] < 0) return {};
     const char* e = getenv("CDB_LISTING");
     std::shared_ptr<Listing> L;
-    if (!e || atoi(e) != 0) L = ix.width == 4 ? build_listing_typed<u32>(ix, order, st) : build_listing_typed<u64>(ix, order, st);
+    bool deferred = false;
+    if (!e || atoi(e) != 0)
+        L = ix.width == 4 ? build_listing_typed<u32>(ix, order, st, &deferred) : build_listing_typed<u64>(ix, order, st, &deferred);
+    if (deferred) return {};
     ix.listing[order] = L;
     ix.listing_state[order] = L ? 1 : -1;
+    ix.listing_miss[order] = 0;
     return L;
 }
 

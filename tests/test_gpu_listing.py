@@ -156,10 +156,23 @@ def test_id_order_listing_through_filter(budget_mb, monkeypatch):
         monkeypatch.setenv("CDB_LISTING_BUDGET_MB", budget_mb)
         assert ix.listing_info(0)["bytes"] > (1 << 19)
     got = cdb.filter_batch({"t": ix}, reqs)
+    if budget_mb:
+        # the other order's listing is in the way: the first call takes the suffix-array path, the second one swaps
+        assert not ix.listing_info(1)["present"] and ix.listing_info(0)["present"]
+        again = cdb.filter_batch({"t": ix}, reqs)
+        for (gp, gm), (wp, wm) in zip(got, again):
+            assert gm == wm and np.array_equal(gp, wp)
     assert ix.listing_info(1)["present"]
     assert ix.listing_info(0)["present"] == (budget_mb is None)
     monkeypatch.setenv("CDB_SMALL_BATCH", "0")
     row_off, pairs = ix.locate_batch(kws)  # doc order again
+    if budget_mb:
+        assert cdb.last_locate_stats()["nlisted"] == 0 and ix.listing_info(1)["present"]
+        # alternating orders never swap: the listing in place stays, the other order keeps the suffix-array path
+        cdb.filter_batch({"t": ix}, reqs[:50])
+        ix.locate_batch(kws)
+        assert cdb.last_locate_stats()["nlisted"] == 0 and ix.listing_info(1)["present"] and not ix.listing_info(0)["present"]
+        ix.locate_batch(kws)  # twice in a row: now it swaps
     assert cdb.last_locate_stats()["nlisted"] > 0
     assert ix.listing_info(0)["present"] and ix.listing_info(1)["present"] == (budget_mb is None)
     monkeypatch.delenv("CDB_LISTING_BUDGET_MB", raising=False)
