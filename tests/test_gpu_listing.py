@@ -99,8 +99,7 @@ def test_only_listed_keywords_skip_the_gather(bits, monkeypatch):
     if k == 1:
         assert st["nlisted"] == 0 and st["nlarge"] > 0
     else:
-        assert st["nlisted"] >= 700 and st["gather_ms"] < 0.05 and st["translate_ms"] < 0.05
-        assert st["listed_pairs"] == st["pairs"]
+        assert st["nlisted"] >= 700 and st["listed_pairs"] == st["pairs"]
     ix.close()
 
 
