@@ -381,7 +381,7 @@ def query_pool_leg():
     exe = os.path.join(ROOT, "tools", "_build", "query_pool_bench")
     if not os.path.exists(exe):
         return {"error": "tools/_build/query_pool_bench has not been built (__graft_entry__.build())"}
-    r = subprocess.run([exe, "10000000", "100", "5", "400"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "10000000", "100", "5", "2000"], capture_output=True, text=True, timeout=300)
     out = {"threads": {}, "what": "C++ worker threads calling string_index::query, one 5-byte keyword per call, 10^7 docs x 100 B"}
     for line in r.stdout.splitlines():
         m = re.match(r"\s*(\d+) threads:\s+(\d+) queries/s\s+\((\d+) queries in (\d+) device batches", line)

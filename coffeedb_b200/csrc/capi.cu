@@ -124,6 +124,7 @@ struct HostResultOwner {
     // cdb_query: the result is a view of one row of a shared batch result (kept alive by `shared`)
     void* shared = nullptr;  // std::shared_ptr<QueryBatchResult>*
     int64_t view_off[2] = {0, 0};
+    bool plain = false;  // row_off / pairs come from malloc (small batches: rows are copied by the CPU, nothing is DMA'd into them)
 };
 
 // One coalesced device batch of cdb_query callers: a host cdb_result, released when its last row view goes.
@@ -934,8 +935,10 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
             if (locate_small(*ix, (const u8*)pat, pat_off, npat, st, &sr)) {
                 i64 total_pairs = 0;
                 for (i64 q = 0; q < npat; ++q) total_pairs += (i64)sr.rowlen[q];
-                own->row_off = g_pinned.get((size_t)(npat + 1) * 8, &own->row_cap);
-                own->pairs = g_pinned.get((size_t)(total_pairs ? total_pairs : 1) * 16, &own->pairs_cap);
+                own->plain = true;
+                own->row_off = malloc((size_t)(npat + 1) * 8);
+                own->pairs = malloc((size_t)(total_pairs ? total_pairs : 1) * 16);
+                if (!own->row_off || !own->pairs) throw Error(CDB_ERR_NOMEM, "cdb_locate_batch: out of host memory");
                 i64* ro = (i64*)own->row_off;
                 i64* pr = (i64*)own->pairs;
                 ro[0] = 0;
@@ -959,8 +962,8 @@ cdb_status cdb_locate_batch(const cdb_index* h, const void* pat, const int64_t* 
             }
         } catch (...) {
             cudaStreamSynchronize(st);
-            if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
-            if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+            free(own->row_off);  // the small path only ever mallocs
+            free(own->pairs);
             delete own;
             throw;
         }
@@ -1013,8 +1016,13 @@ void cdb_result_free(cdb_result* r) {
     if (!r || !r->_owner) return;
     HostResultOwner* own = static_cast<HostResultOwner*>(r->_owner);
     if (own->shared) delete static_cast<std::shared_ptr<QueryBatchResult>*>(own->shared);
-    if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
-    if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+    if (own->plain) {
+        free(own->row_off);
+        free(own->pairs);
+    } else {
+        if (own->row_off) g_pinned.put(own->row_off, own->row_cap);
+        if (own->pairs) g_pinned.put(own->pairs, own->pairs_cap);
+    }
     delete own;
     std::memset(r, 0, sizeof(*r));
 }

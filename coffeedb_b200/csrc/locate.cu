@@ -1834,22 +1834,59 @@ struct SmallCtx {
 static constexpr size_t kSmallInBytes = 64 + 8 * (kSmallMaxPat + 1) + kSmallPatBytes;
 static constexpr size_t kSmallOutBytes = (kSmallHdrWords + 2 * kSmallMaxPat) * 8 + kSmallCapPairs * 16;
 
-static SmallCtx& small_ctx(int device) {
-    static thread_local std::map<int, SmallCtx> ctxs;  // lives as long as the thread (like its stream)
-    SmallCtx& c = ctxs[device];
-    if (!c.h_in) {
-        CDB_CUDA(cudaHostAlloc((void**)&c.h_in, kSmallInBytes, cudaHostAllocDefault));
-        CDB_CUDA(cudaMalloc((void**)&c.d_in, kSmallInBytes));
-        CDB_CUDA(cudaMalloc((void**)&c.d_tmp, (size_t)kSmallMaxPat * 32 + 64));
-        CDB_CUDA(cudaHostAlloc((void**)&c.h_out, kSmallOutBytes, cudaHostAllocMapped));
-        CDB_CUDA(cudaHostGetDevicePointer((void**)&c.d_out, c.h_out, 0));
+// The buffer sets are pooled per device, not kept per host thread: behind cdb_query any of the server's worker threads may
+// lead a batch, and a set per thread cost every new leader ~1 ms of page-locked allocations.  A set is checked out for
+// one call and goes back when the caller has copied its rows (SmallResult's destructor).
+static std::mutex g_small_mu;
+static std::map<int, std::vector<SmallCtx*>> g_small_free;
+
+static SmallCtx* small_ctx_checkout(int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_small_mu);
+        auto& v = g_small_free[device];
+        if (!v.empty()) {
+            SmallCtx* c = v.back();
+            v.pop_back();
+            return c;
+        }
+    }
+    SmallCtx* c = new SmallCtx();
+    try {
+        CDB_CUDA(cudaHostAlloc((void**)&c->h_in, kSmallInBytes, cudaHostAllocDefault));
+        CDB_CUDA(cudaMalloc((void**)&c->d_in, kSmallInBytes));
+        CDB_CUDA(cudaMalloc((void**)&c->d_tmp, (size_t)kSmallMaxPat * 32 + 64));
+        CDB_CUDA(cudaHostAlloc((void**)&c->h_out, kSmallOutBytes, cudaHostAllocMapped));
+        CDB_CUDA(cudaHostGetDevicePointer((void**)&c->d_out, c->h_out, 0));
+    } catch (...) {
+        if (c->h_in) cudaFreeHost(c->h_in);
+        if (c->d_in) cudaFree(c->d_in);
+        if (c->d_tmp) cudaFree(c->d_tmp);
+        if (c->h_out) cudaFreeHost(c->h_out);
+        delete c;
+        throw;
     }
     return c;
 }
 
+static void small_ctx_return(int device, SmallCtx* c) {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    g_small_free[device].push_back(c);
+}
+
+SmallResult::~SmallResult() {
+    if (_ctx) small_ctx_return(_device, static_cast<SmallCtx*>(_ctx));
+}
+
 template <typename SAT>
 static bool locate_small_typed(const Index& ix, const u8* pat, const i64* pat_off, int npat, cudaStream_t st, SmallResult* res) {
-    SmallCtx& sc = small_ctx(ix.device);
+    struct Lease {  // back to the pool on every way out, unless the result takes it over
+        int device;
+        SmallCtx* c;
+        ~Lease() {
+            if (c) small_ctx_return(device, c);
+        }
+    } lease{ix.device, small_ctx_checkout(ix.device)};
+    SmallCtx& sc = *lease.c;
     const i64 p0 = pat_off[0], pbytes = pat_off[npat] - p0;
     std::memset(sc.h_in, 0, 64);
     i64* h_off = reinterpret_cast<i64*>(sc.h_in + 64);
@@ -1883,6 +1920,9 @@ static bool locate_small_typed(const Index& ix, const u8* pat, const i64* pat_of
     res->rowlen = h + kSmallHdrWords;
     res->rowocc = res->rowlen + kSmallMaxPat;
     res->pairs = reinterpret_cast<const i64*>(res->rowocc + kSmallMaxPat);
+    res->_ctx = lease.c;  // the rows stay valid until the result goes
+    res->_device = ix.device;
+    lease.c = nullptr;
     return true;
 }
 

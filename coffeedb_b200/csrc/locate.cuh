@@ -40,14 +40,20 @@ __device__ __forceinline__ u64 listed_row_value(const u32* __restrict__ lo, cons
     return v;
 }
 #endif
-// Small-batch fast path (locate.cu, experimental): one upload, two launches, one synchronisation.  On success the
-// rows are in mapped pinned memory of the calling thread — valid until its next call: row q has rowlen[q] pairs at
+// Small-batch fast path (locate.cu): one upload, two launches, one synchronisation.  On success the rows are in mapped
+// pinned memory checked out of a per-device pool — valid until the SmallResult is destroyed: row q has rowlen[q] pairs at
 // pairs + 2 * (rowocc[0] + ... + rowocc[q-1]).  Returns false when the batch has to take the general path.
 struct SmallResult {
     i64 total_occ = 0;
     const u64* rowlen = nullptr;
     const u64* rowocc = nullptr;
     const i64* pairs = nullptr;
+    void* _ctx = nullptr;  // the buffer set the rows live in (returned to the pool by the destructor)
+    int _device = 0;
+    SmallResult() {}
+    SmallResult(const SmallResult&) = delete;
+    SmallResult& operator=(const SmallResult&) = delete;
+    ~SmallResult();
 };
 int small_batch_limit();  // CDB_SMALL_BATCH (0 = path disabled)
 bool locate_small(const Index& ix, const u8* pat, const i64* pat_off, i64 npat, cudaStream_t st, SmallResult* res);

@@ -8,8 +8,10 @@
 //   * a caller appends its keyword to the open batch; the first one in becomes the batch's leader;
 //   * the leader waits until fewer than `max_in_flight` batches are on the device (no timer: with an idle device it
 //     goes at once, so a lone query pays no extra latency), closes the batch and runs it through the backend;
-//   * callers that arrive meanwhile fill the next batch; followers sleep until their batch is done and then read
-//     their own row out of the shared result (no copy by the leader).
+//   * callers that arrive meanwhile fill the next batch; followers wait until their batch is done and then read
+//     their own row out of the shared result (no copy by the leader).  They wait WITHOUT the queue's mutex — a short
+//     spin on the batch's flag, then the batch's own condition variable — and read the finished batch without any lock:
+//     when 64 followers woke up through one mutex, handing it from one to the next cost more than the device batch.
 //
 // Header-only and CUDA-free: `Backend` is any callable
 //     std::shared_ptr<Result> backend(const std::string& bytes, const std::vector<int64_t>& off)
@@ -17,6 +19,7 @@
 // `const int64_t* pairs` ((id, count) pairs, as cdb_result).  capi.cu instantiates it over the locate path
 // (cdb_query); tests/host/test_batcher.cpp drives it with a host-only stand-in.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -26,6 +29,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -60,7 +64,7 @@ public:
     // Blocks until no caller is inside query(); the owner must not start new queries while destroying.
     ~micro_batcher() {
         std::unique_lock<std::mutex> lk(mu_);
-        idle_cv_.wait(lk, [&] { return active_ == 0; });
+        idle_cv_.wait(lk, [&] { return active_.load(std::memory_order_acquire) == 0; });
     }
 
     // string_index::query(keyword) for one keyword (src/index.cpp:237-326), coalesced with concurrent callers.
@@ -68,9 +72,9 @@ public:
         // the reference rejects an empty keyword before touching the index (src/index.cpp:239-241); doing it here keeps
         // one bad request from failing the strangers that share its batch
         if (keyword.empty()) throw std::runtime_error("Empty keywords are not allowed");
+        active_.fetch_add(1, std::memory_order_acq_rel);
+        leave_guard leave{this};
         std::unique_lock<std::mutex> lk(mu_);
-        ++active_;
-        leave_guard leave{this, &lk};
         if (!open_) open_ = std::make_shared<batch>();
         std::shared_ptr<batch> b = open_;
         // strong guarantee: the keyword's bytes and offset go in first (either may throw bad_alloc, and a slot without
@@ -104,12 +108,29 @@ public:
             }
             lk.lock();
             --in_flight_;
-            b->done = true;
             slot_cv_.notify_all();
-            b->cv.notify_all();
+            lk.unlock();
+            {
+                std::lock_guard<std::mutex> bl(b->mu);  // pairs with the followers' predicate check: no lost wake-up
+                b->done.store(true, std::memory_order_release);
+            }
+            b->done_cv.notify_all();
         } else {
-            b->cv.wait(lk, [&] { return b->done; });
+            lk.unlock();
+            // the batch is on the device for a few tens of microseconds: look at its flag for about that long before sleeping
+            const auto t_give_up = std::chrono::steady_clock::now() + std::chrono::microseconds(80);
+            for (int spin = 0; !b->done.load(std::memory_order_acquire); ++spin) {
+                if ((spin & 31) == 31) {
+                    if (std::chrono::steady_clock::now() > t_give_up) break;
+                    std::this_thread::yield();
+                }
+            }
+            if (!b->done.load(std::memory_order_acquire)) {
+                std::unique_lock<std::mutex> bl(b->mu);
+                b->done_cv.wait(bl, [&] { return b->done.load(std::memory_order_acquire); });
+            }
         }
+        // from here on the batch is immutable: read without a lock
         if (b->error) std::rethrow_exception(b->error);
         row_view v;
         v.owner = b->result;
@@ -129,17 +150,20 @@ private:
         std::string bytes;
         std::vector<int64_t> off{0};
         size_t n = 0;
-        bool done = false;
+        std::atomic<bool> done{false};
         std::shared_ptr<Result> result;
         std::exception_ptr error;
-        std::condition_variable cv;  // followers: done; leader (with linger): full
+        std::condition_variable cv;       // leader (with linger): full — under the queue's mutex
+        std::mutex mu;                    // followers that gave up spinning sleep here, not on the queue's mutex
+        std::condition_variable done_cv;
     };
-    struct leave_guard {  // --active_ under the lock on every way out of query()
+    struct leave_guard {  // --active_ on every way out of query(); the destructor of the queue waits for 0
         micro_batcher* self;
-        std::unique_lock<std::mutex>* lk;
         ~leave_guard() {
-            if (!lk->owns_lock()) lk->lock();
-            if (--self->active_ == 0) self->idle_cv_.notify_all();
+            if (self->active_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                std::lock_guard<std::mutex> lk(self->mu_);
+                self->idle_cv_.notify_all();
+            }
         }
     };
 
@@ -151,7 +175,7 @@ private:
     std::condition_variable slot_cv_, idle_cv_;
     std::shared_ptr<batch> open_;
     int in_flight_ = 0;
-    int active_ = 0;
+    std::atomic<int> active_{0};
     micro_batcher_stats stats_;
 };
 
