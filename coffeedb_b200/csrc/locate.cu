@@ -1100,7 +1100,8 @@ __global__ void ids_minmax_kernel(const i64* __restrict__ ids, i64 nd, long long
 template <typename SAT, int R>
 __device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l, int occ, u64 mask, u32 bucket_mul, u32* s_a, u32* s_b,
                                               int lane, const u32* __restrict__ remap, const i64* __restrict__ table, i64 base,
-                                              int hw, u32* __restrict__ out_lo, void* __restrict__ out_hi, int* __restrict__ dup_flag) {
+                                              int hw, u32* __restrict__ out_lo, void* __restrict__ out_hi, int* __restrict__ dup_flag,
+                                              u16* __restrict__ seg_row, int nranges, int rshift) {
     u32 x[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -1137,6 +1138,29 @@ __device__ __forceinline__ u32 listing_bucket(const SAT* __restrict__ sa, i64 l,
         for (int r = 0; r < R; ++r) da[r] = x[r];
     }
     __syncwarp();
+    if (seg_row) {
+        // two-phase build: the sorted KEYS go out now (coalesced), with the row's split points at the doc-range boundaries;
+        // listing_translate_kernel turns them into ids range by range, so that the slice of ids[] in use stays in L2
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = r * 32 + lane;
+            if (i < occ) out_lo[l + i] = s_a[pad_idx(i)];
+        }
+        for (int r = lane; r <= nranges; r += 32) {
+            const u64 bound = (u64)r << rshift;
+            int lo = 0, hi = occ;  // first rank whose key is >= bound
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((u64)s_a[pad_idx(mid)] < bound)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            seg_row[r * kTileWarps] = (u16)lo;
+        }
+        __syncwarp();
+        return (u32)nh;
+    }
     u64 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -1178,24 +1202,29 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) listing_build_kernel(const
                                                                           u64* ptab, u64 nentries,
                                                                           const u32* __restrict__ remap, const i64* __restrict__ table,
                                                                           i64 base, int hw, u32* __restrict__ out_lo,
-                                                                          void* __restrict__ out_hi, int* __restrict__ dup_flag) {
+                                                                          void* __restrict__ out_hi, int* __restrict__ dup_flag,
+                                                                          u16* __restrict__ seg, int nranges, int rshift) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 c = (u64)blockIdx.x * kTileWarps + warp;
     if (c >= nentries) return;
+    // seg layout as gather_kernel's: [c / 8][r = 0..nranges][c % 8]
+    u16* seg_row = seg ? seg + (size_t)(c / kTileWarps) * (nranges + 1) * kTileWarps + (c % kTileWarps) : nullptr;
     // other warps tag their own entries while this one reads: 8-byte accesses, the rank bits never change
     const u64 e_lo = *reinterpret_cast<const volatile u64*>(ptab + c);
     const i64 l = (i64)(e_lo & kPtRank);
     const i64 occ64 = (i64)(*reinterpret_cast<const volatile u64*>(ptab + c + 1) & kPtRank) - l;
     if (occ64 <= 0 || occ64 > kWarpCap) {
         if (lane == 0 && (e_lo >> kPtCountShift)) ptab[c] = e_lo & kPtRank;
+        if (seg_row)
+            for (int r = lane; r <= nranges; r += 32) seg_row[r * kTileWarps] = 0;
         return;
     }
     u32* s_a = reinterpret_cast<u32*>(smem_raw + (size_t)warp * warp_smem_bytes<32>());
     u32* s_b = s_a + 32 * 32 + 32;
     const int occ = (int)occ64;
     u32 d;
-#define CDB_LB(RR) listing_bucket<SAT, RR>(sa, l, occ, mask, bucket_mul, s_a, s_b, lane, remap, table, base, hw, out_lo, out_hi, dup_flag)
+#define CDB_LB(RR) listing_bucket<SAT, RR>(sa, l, occ, mask, bucket_mul, s_a, s_b, lane, remap, table, base, hw, out_lo, out_hi, dup_flag, seg_row, nranges, rshift)
     if (occ <= 32) d = CDB_LB(1);
     else if (occ <= 64) d = CDB_LB(2);
     else if (occ <= 128) d = CDB_LB(4);
@@ -1204,6 +1233,116 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) listing_build_kernel(const
     else d = CDB_LB(32);
 #undef CDB_LB
     if (lane == 0) ptab[c] = (u64)l | (1ull << 63) | (d != (u32)occ ? (1ull << 62) : 0ull) | ((u64)d << kPtCountShift);
+}
+
+// Phase 2 of the two-phase listing build: lo[] holds the sorted keys (doc indices / id ranks) of every listed bucket; they
+// become (id - base) in place.  Same order of work as translate_kernel — item = (doc range, block of 32 buckets), handed
+// out through one ticket so that the whole grid looks up one <= 32 MB slice of the table at a time (L2 evict_last) —
+// because looked up bucket by bucket every random 8-byte read cost a ~110-byte DRAM fetch (1.18 TB for 10^10 suffixes).
+constexpr int kLtU = 4;
+__global__ void __launch_bounds__(kTrWarps * 32) listing_translate_kernel(u32* __restrict__ lo, void* __restrict__ hi, int hw,
+                                                                          const u64* __restrict__ ptab, const u16* __restrict__ seg,
+                                                                          const i64* __restrict__ table, i64 base, u64 nentries,
+                                                                          int nranges, unsigned long long* ticket) {
+    __shared__ u32 s_excl[kTrWarps][32];
+    __shared__ u64 s_pos[kTrWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 ntile = (i64)((nentries + 31) >> 5);
+    const i64 nitems = ntile * nranges;
+    const u64 pol_keep = l2_policy_evict_last();
+    const u64 pol_stream = l2_policy_evict_first();
+    const u64* tab = reinterpret_cast<const u64*>(table);
+    for (;;) {
+        i64 item = 0;
+        if (lane == 0) item = (i64)atomicAdd(ticket, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int r = (int)(item / ntile);
+        const u64 c = (u64)(item - (i64)r * ntile) * 32 + lane;
+        u32 len = 0;
+        u64 pos0 = 0;
+        if (c < nentries) {
+            const u16* sg = seg + ((size_t)(c / kTileWarps) * (nranges + 1) + r) * kTileWarps + (c % kTileWarps);
+            const u32 s = sg[0], e = sg[kTileWarps];
+            len = e - s;
+            if (len) pos0 = (__ldg(ptab + c) & kPtRank) + s;
+        }
+        u32 incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot == 0) continue;
+        __syncwarp();
+        s_excl[warp][lane] = incl - len;
+        s_pos[warp][lane] = pos0 - (incl - len);
+        __syncwarp();
+        for (u32 i0 = 0; i0 < tot; i0 += 32 * kLtU) {
+            u64 p[kLtU];
+            u32 key[kLtU];
+#pragma unroll
+            for (int u = 0; u < kLtU; ++u) {
+                const u32 idx = i0 + u * 32 + lane;
+                if (idx < tot) {
+                    int j = 0;  // largest j with excl[j] <= idx
+#pragma unroll
+                    for (int st = 16; st; st >>= 1)
+                        if (s_excl[warp][j + st] <= idx) j += st;
+                    p[u] = s_pos[warp][j] + idx;
+                    key[u] = ld_hint_u32(lo + p[u], pol_stream);
+                }
+            }
+            __syncwarp();
+            u64 v[kLtU];
+#pragma unroll
+            for (int u = 0; u < kLtU; ++u) {
+                const u32 idx = i0 + u * 32 + lane;
+                if (idx < tot) v[u] = (u64)((i64)ld_hint_u64(tab + key[u], pol_keep) - base);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kLtU; ++u) {
+                const u32 idx = i0 + u * 32 + lane;
+                if (idx < tot) {
+                    lo[p[u]] = (u32)v[u];
+                    const u32 h = (u32)(v[u] >> 32);
+                    if (hw == 1) reinterpret_cast<u8*>(hi)[p[u]] = (u8)h;
+                    else if (hw == 2) reinterpret_cast<u16*>(hi)[p[u]] = (u16)h;
+                    else if (hw == 4) reinterpret_cast<u32*>(hi)[p[u]] = h;
+                }
+            }
+        }
+    }
+}
+
+__global__ void adjacent_equal_kernel(const u64* __restrict__ keys, i64 n, int* __restrict__ flag) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && keys[i] == keys[i + 1]) *flag = 1;
+}
+__global__ void ids_keys_kernel(const i64* __restrict__ ids, i64 nd, u64* __restrict__ keys) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nd) keys[i] = (u64)ids[i];
+}
+
+// do two documents share an id?  (a listed row could not tell them apart: the listing is refused then)
+static bool ids_have_duplicates(const Index& ix, cudaStream_t st) {
+    const i64 nd = ix.nd;
+    if (nd < 2) return false;
+    BigBuf<u64> k0((size_t)nd), k1((size_t)nd);
+    const unsigned grid = (unsigned)ceil_div(nd, 256);
+    ids_keys_kernel<<<grid, 256, 0, st>>>(ix.d_ids, nd, k0.p);
+    CDB_LAUNCH_CHECK();
+    const int cur = rs::radix_sort_pairs<rs::NoValue>(k0.p, k1.p, nullptr, nullptr, (u64)nd, 0, 64, st);
+    DevBuf<int> flag(1, st);
+    CDB_CUDA(cudaMemsetAsync(flag.p, 0, 4, st));
+    adjacent_equal_kernel<<<grid, 256, 0, st>>>(cur ? k1.p : k0.p, nd, flag.p);
+    CDB_LAUNCH_CHECK();
+    int h = 0;
+    CDB_CUDA(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CDB_CUDA(cudaStreamSynchronize(st));
+    return h != 0;
 }
 
 template <int HW>
@@ -1432,10 +1571,41 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     const u32 bucket_mul = use_buckets && ix.nd > 0 ? (u32)std::min<u64>(0xffffffffull, (1024ull << 32) / (u64)ix.nd) : 0u;
     const size_t smem = (size_t)kTileWarps * warp_smem_bytes<32>();
     CDB_CUDA(cudaFuncSetAttribute(listing_build_kernel<SAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Two phases when the table of ids is larger than L2 can hold (CDB_LISTING_TWO_PHASE forces 1 / 0): sorted keys + split
+    // points first, ids range by range afterwards.  One phase otherwise: the lookups hit L2 anyway.
+    int nranges, rshift;
+    ids_ranges(ix.nd, &nranges, &rshift);
+    bool two = (size_t)ix.nd * 8 > ((size_t)48 << 20);
+    if (const char* e = getenv("CDB_LISTING_TWO_PHASE")) two = atoi(e) != 0;
+    BigBuf<u16> seg;
+    if (two) {
+        if (ids_have_duplicates(ix, st)) return {};
+        const size_t nseg = (size_t)ceil_div((i64)nentries, kTileWarps) * kTileWarps * (nranges + 1);
+        u16* p = nullptr;
+        if (big_malloc((void**)&p, nseg * 2, ix.device)) {
+            seg.p = p;
+            seg.n = nseg;
+        } else {
+            two = false;
+        }
+    }
     listing_build_kernel<SAT><<<(unsigned)ceil_div((i64)nentries, kTileWarps), kTileWarps * 32, smem, st>>>(
         reinterpret_cast<const SAT*>(ix.d_sa), ix.mask, bucket_mul, ix.d_ptab, nentries, remap, table, L->base, hw, L->lo, L->hi,
-        L->d_flag);
+        L->d_flag, seg.p, nranges, rshift);
     CDB_LAUNCH_CHECK();
+    EventPair evm;
+    CDB_CUDA(cudaEventRecord(evm.a, st));
+    if (two) {
+        DevBuf<unsigned long long> ticket(1, st);
+        CDB_CUDA(cudaMemsetAsync(ticket.p, 0, 8, st));
+        const i64 nitems = ceil_div((i64)nentries, 32) * nranges;
+        const int per_sm = resident_ctas((const void*)listing_translate_kernel, kTrWarps * 32);
+        const int grid = (int)std::min<i64>(ceil_div(nitems, kTrWarps), (i64)num_sms() * per_sm);
+        listing_translate_kernel<<<grid, kTrWarps * 32, 0, st>>>(L->lo, L->hi, hw, ix.d_ptab, seg.p, table, L->base, nentries, nranges,
+                                                                  ticket.p);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA(cudaStreamSynchronize(st));  // seg and the ticket are released below
+    }
     int h_flag = 0;
     CDB_CUDA(cudaMemcpyAsync(&h_flag, L->d_flag, 4, cudaMemcpyDeviceToHost, st));
     CDB_CUDA(cudaEventRecord(e1, st));
@@ -1443,7 +1613,12 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     L->build_ms = ms;
-    if (getenv("CDB_DEBUG_TIMING")) fprintf(stderr, "[cdb] document listing (order %d, %d + 4 bytes per suffix): %.1f ms%s\n", order, hw, ms, h_flag ? " — dropped: two documents share an id" : "");
+    if (getenv("CDB_DEBUG_TIMING")) {
+        float ms1 = 0;
+        cudaEventElapsedTime(&ms1, e0, evm.a);
+        fprintf(stderr, "[cdb] document listing (order %d, %d + 4 bytes per suffix, %s): %.1f ms (%.1f ms up to the end of the sort phase)%s\n", order, hw,
+                two ? "two phases" : "one phase", ms, ms1, h_flag ? " — dropped: two documents share an id" : "");
+    }
     if (h_flag) return {};
     return L;
 }

@@ -186,3 +186,38 @@ def test_id_order_listing_through_filter(budget_mb, monkeypatch):
     assert np.array_equal(row_off, row_off0) and np.array_equal(pairs, pairs0)
     ix.close()
     ix0.close()
+
+
+@pytest.mark.parametrize("range_bits", ["8", "11", "22"])
+def test_two_phase_build_equals_one_phase(range_bits, monkeypatch):
+    """Indexes whose ids[] outgrow L2 build the listing in two phases (sorted keys + split points, then ids range by range:
+    listing_translate_kernel); forced here at small size, with many / a few / one doc range, in both orders."""
+    monkeypatch.setenv("CDB_SMALL_BATCH", "0")
+    rng = np.random.default_rng(5)
+    text, off, _ = corpora.ragged(6000, 90, seed=29, alphabet=b"abcd")
+    ids = ID_KINDS["40 bits"](len(off) - 1, rng)
+    monkeypatch.setenv("CDB_LISTING_TWO_PHASE", "0")
+    one = build(text, off, ids)
+    k = one.prefix_directory()["symbols"]
+    pats = all_lengths_patterns(text, off, k, seed=41)
+    row_off1, pairs1 = one.locate_batch(pats)
+    assert cdb.last_locate_stats()["nlisted"] > 0
+    kws = [p for p in pats if len(p) == k and max(p) < 0x80][:300]
+    reqs = _requests(kws)
+    want = cdb.filter_batch({"t": one}, reqs)
+    monkeypatch.setenv("CDB_LISTING_TWO_PHASE", "1")
+    monkeypatch.setenv("CDB_RANGE_BITS", range_bits)
+    two = build(text, off, ids)
+    assert two.listing_info(0)["present"] and two.listing_info(0)["hi_bytes"] == 1
+    row_off2, pairs2 = two.locate_batch(pats)
+    assert cdb.last_locate_stats()["nlisted"] > 0
+    assert np.array_equal(row_off1, row_off2) and np.array_equal(pairs1, pairs2)
+    got = cdb.filter_batch({"t": two}, reqs)
+    assert two.listing_info(1)["present"]
+    for (gp, gm), (wp, wm) in zip(got, want):
+        assert gm == wm and np.array_equal(gp, wp)
+    # duplicate ids are found by the two-phase build's own check
+    dup = build(text, off, np.repeat(ids[::2], 2)[: len(ids)].copy())  # pairs of documents share an id
+    assert not dup.listing_info(0)["present"]
+    for ix in (one, two, dup):
+        ix.close()
