@@ -1,4 +1,9 @@
 #pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 #include "index.cuh"
 
 namespace cdb {
@@ -30,6 +35,50 @@ void emit_listed_rows(const cdb_device_result& res, const LazyListed& lazy, cons
 constexpr u64 kPreListed = 1ull << 63;
 constexpr u64 kPreRepeat = 1ull << 62;
 constexpr u64 kPreCount = kPreRepeat - 1;
+// A directory entry holds an SA rank in its low 48 bits.  Once a listing has been built, the high bits of ptab[c] describe
+// bucket c (ranks [ptab[c], ptab[c+1])): bit 63 = listed (1 .. kWarpCap suffixes), bit 62 = some document occurs more than
+// once, bits 48..58 = distinct documents.  The search finds them in the entry it reads anyway.
+constexpr u64 kPtRank = (1ull << 48) - 1;
+constexpr int kPtCountShift = 48;
+constexpr u64 kPtCountMask = 0x7ffull;
+
+constexpr int kMaxRanges = 64;   // doc-range partitions of ids[] used by translate_kernel (each <= ~32 MB of ids)
+constexpr int kTrWarps = 8;      // warps per CTA of translate_kernel / listing_translate_kernel
+
+// resident CTAs per SM of a kernel (its persistent grids are exactly one wave), cached per kernel and device
+inline int resident_ctas(const void* kernel, int threads, size_t smem = 0) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    CDB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({kernel, dev});
+    if (it != cache.end()) return it->second;
+    int v = 0;
+    CDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem));
+    v = v > 0 ? v : 1;
+    cache[{kernel, dev}] = v;
+    return v;
+}
+
+// Doc-range partition of ids[] for translate_kernel: ranges of 2^rshift documents (default 2^22 = 32 MB of ids,
+// CDB_RANGE_BITS overrides), at most kMaxRanges of them.
+inline void ids_ranges(i64 nd, int* nranges, int* rshift) {
+    const char* e = getenv("CDB_RANGE_BITS");  // read per call: the tests switch it to exercise many ranges
+    const int env_bits = e ? atoi(e) : 22;
+    int sh = env_bits < 8 ? 8 : (env_bits > 40 ? 40 : env_bits);
+    while (ceil_div(nd > 0 ? nd : 1, (i64)1 << sh) > kMaxRanges) ++sh;
+    *rshift = sh;
+    *nranges = (int)ceil_div(nd > 0 ? nd : 1, (i64)1 << sh);
+}
+
+// listing.cu: the rows of a batch that are answered from the document listing.  mode 0: every listed row; 1: only the rows in
+// which a document repeats (the others are read lazily by the caller); 2: the rows without repeats with need[q] != 0
+void launch_listing_emit(const Listing& L, const u64* pre, const i64* left, const i64* right, const u64* row_off, i64 npat, i64* pairs,
+                         int mode, const u8* need, cudaStream_t st);
+// listing.cu: rowlen[q] = the listed rows' lengths (from pre[]); the other rows are zeroed when write_zero
+void launch_listing_rowlen(const u64* pre, i64 npat, u64* rowlen, int write_zero, cudaStream_t st);
+
 #ifdef __CUDACC__
 // (id - base) of listing entry i; hw = bytes of the high plane (0, 1, 2, 4)
 __device__ __forceinline__ u64 listed_row_value(const u32* __restrict__ lo, const void* __restrict__ hi, int hw, i64 i) {
