@@ -1018,7 +1018,11 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<int32_t> stats((size_t)npat * 2, st);
     stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, pre.p, stats.p, rowflag.p);
     CDB_LAUNCH_CHECK();
-    if (rows_ready) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
+    // (a batch answered from the listing alone has no translate to hide the exchange under: its hook runs after the emit
+    // kernel is enqueued — CDB_HOOK_AFTER_EMIT=0 keeps it here — so that the persistent emit grid finds every SM free)
+    const char* env_hook = getenv("CDB_HOOK_AFTER_EMIT");
+    const bool hook_late = rows_ready && !general && nlisted && (!env_hook || atoi(env_hook) != 0);
+    if (rows_ready && !hook_late) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     if (general) {
@@ -1042,6 +1046,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         }
     }
     CDB_CUDA(cudaEventRecord(ev[7], st));
+    if (hook_late) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
     for (LargeChunk& lc : lchunks) {
         if (lc.nu == 0) continue;
         const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), num_sms() * 16);
