@@ -312,10 +312,11 @@ class StringIndex:
         return res
 
     def locate_batch_device_ex(self, d_pat_ptr: int, d_pat_off_ptr: int, npat: int, stream: int, rows_ready) -> DeviceResult:
-        """locate_batch_device with the sharded caller's hook: rows_ready(stats32_ptr, npat) runs once the per-pattern
-        (row length, occurrences) are enqueued, before the pairs are filled."""
+        """locate_batch_device with the sharded caller's hook: rows_ready(stats32_ptr, npat, stream_handle) runs once the
+        per-pattern (row length, occurrences) are enqueued; they are ready on `stream_handle` (the launching stream, or a
+        side stream of the library when the rows are being streamed from the document listing at that moment)."""
         res = DeviceResult()
-        cb = ROWS_READY_FN(lambda _user, stats, n, _st: rows_ready(stats, n))
+        cb = ROWS_READY_FN(lambda _user, stats, n, st: rows_ready(stats, n, st))
         _check(self._L.cdb_locate_batch_device_ex(self._h, d_pat_ptr, d_pat_off_ptr, npat, stream, cb, None, C.byref(res)))
         return res
 

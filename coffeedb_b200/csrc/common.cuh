@@ -133,7 +133,7 @@ struct BigBuf {
 // Per host thread and device: one non-blocking stream and a set of timing events, created on first use and kept (a
 // query() per request must not pay stream and event creation every time).
 struct ThreadCtx {
-    static constexpr int kEvents = 8;
+    static constexpr int kEvents = 10;
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // device-to-host copies that run under the next part's kernels (cdb_filter)

@@ -590,11 +590,13 @@ std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st
 }
 
 void launch_listing_emit(const Listing& L, const u64* pre, const i64* left, const i64* right, const u64* row_off, i64 npat,
-                                i64* pairs, int mode, const u8* need, cudaStream_t st) {
+                                i64* pairs, int mode, const u8* need, cudaStream_t st, int spare_ctas) {
     auto emit = [&](auto kernel) {
         int per_sm = resident_ctas((const void*)kernel, kTileWarps * 32);
         if (const char* e = getenv("CDB_EMIT_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // experiment knob
-        const i64 grid = std::min<i64>(ceil_div(npat, kTileWarps), (i64)num_sms() * per_sm);
+        // spare_ctas: room left for a collective that runs beside this persistent grid (a sharded caller's all_gather)
+        const i64 wave = std::max<i64>((i64)num_sms(), (i64)num_sms() * per_sm - spare_ctas);
+        const i64 grid = std::min<i64>(ceil_div(npat, kTileWarps), wave);
         kernel<<<(unsigned)grid, kTileWarps * 32, 0, st>>>(L.lo, L.hi, L.base, pre, left, right, row_off, npat, pairs, mode, need);
     };
     switch (L.hw) {
@@ -609,7 +611,7 @@ void launch_listing_emit(const Listing& L, const u64* pre, const i64* left, cons
 void emit_listed_rows(const cdb_device_result& res, const LazyListed& lazy, const u8* d_need, cudaStream_t st) {
     if (!lazy.active || !lazy.lst || res.npat <= 0) return;
     launch_listing_emit(*lazy.lst, lazy.pre, res.left, res.right, reinterpret_cast<const u64*>(res.row_off), res.npat, res.pairs, 2,
-                        d_need, st);
+                        d_need, st, 0);
 }
 
 void launch_listing_rowlen(const u64* pre, i64 npat, u64* rowlen, int write_zero, cudaStream_t st) {

@@ -1018,11 +1018,17 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     DevBuf<int32_t> stats((size_t)npat * 2, st);
     stats32_kernel<<<(unsigned)ceil_div(npat, 256), 256, 0, st>>>(row_off.p, left.p, right.p, npat, seg.p, nranges, pre.p, stats.p, rowflag.p);
     CDB_LAUNCH_CHECK();
-    // (a batch answered from the listing alone has no translate to hide the exchange under: its hook runs after the emit
-    // kernel is enqueued — CDB_HOOK_AFTER_EMIT=0 keeps it here — so that the persistent emit grid finds every SM free)
+    // A batch answered from the listing alone has no translate to hide the exchange under, and the hook's host work (tens of
+    // microseconds in a Python caller) would keep the device waiting for the emit kernel.  The emit kernel is therefore
+    // enqueued FIRST and the hook runs afterwards on a side stream that only waits for the statistics (recorded here): the
+    // caller's collective is in the queue at once and runs as soon as SMs are free.  (Leaving 64 of the emit grid's 592 CTAs
+    // out to make room for it cost the emit kernel 10 % and bought nothing measurable on 2 GPUs: launch_listing_emit's
+    // spare_ctas stays 0.)
+    // CDB_HOOK_AFTER_EMIT=0 keeps the hook here, on the launching stream.
     const char* env_hook = getenv("CDB_HOOK_AFTER_EMIT");
     const bool hook_late = rows_ready && !general && nlisted && (!env_hook || atoi(env_hook) != 0);
     if (rows_ready && !hook_late) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
+    if (hook_late) CDB_CUDA(cudaEventRecord(ev[8], st));
     CDB_CUDA(cudaEventRecord(ev[4], st));
     // phase B: doc index -> id, ordered by doc range so that the ids[] slice in use is L2-resident
     if (general) {
@@ -1038,7 +1044,7 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
     // the listed rows: streamed from the document listing into their CSR rows
     if (nlisted) {
         // a lazy caller reads the rows without repeats from the listing itself
-        launch_listing_emit(*lst, pre.p, left.p, right.p, row_off.p, npat, pairs.p, lazy ? 1 : 0, nullptr, st);
+        launch_listing_emit(*lst, pre.p, left.p, right.p, row_off.p, npat, pairs.p, lazy ? 1 : 0, nullptr, st, 0);
         if (lazy) {
             lazy->lst = lst;
             lazy->stream = st;
@@ -1046,7 +1052,12 @@ static void locate_typed(const Index& ix, const u8* d_pat, const i64* d_pat_off,
         }
     }
     CDB_CUDA(cudaEventRecord(ev[7], st));
-    if (hook_late) rows_ready(rows_ready_user, stats.p, npat, (void*)st);
+    if (hook_late) {
+        ThreadCtx& tc = thread_ctx(ix.device);
+        if (!tc.copy_stream) CDB_CUDA(cudaStreamCreateWithFlags(&tc.copy_stream, cudaStreamNonBlocking));
+        CDB_CUDA(cudaStreamWaitEvent(tc.copy_stream, ev[8], 0));
+        rows_ready(rows_ready_user, stats.p, npat, (void*)tc.copy_stream);  // the statistics are ready on THIS stream
+    }
     for (LargeChunk& lc : lchunks) {
         if (lc.nu == 0) continue;
         const int grid = (int)std::min<i64>(ceil_div((i64)lc.nu, 256), num_sms() * 16);

@@ -74,8 +74,9 @@ inline void ids_ranges(i64 nd, int* nranges, int* rshift) {
 
 // listing.cu: the rows of a batch that are answered from the document listing.  mode 0: every listed row; 1: only the rows in
 // which a document repeats (the others are read lazily by the caller); 2: the rows without repeats with need[q] != 0
+// spare_ctas: CTAs the persistent grid leaves free (room for a collective that runs beside it)
 void launch_listing_emit(const Listing& L, const u64* pre, const i64* left, const i64* right, const u64* row_off, i64 npat, i64* pairs,
-                         int mode, const u8* need, cudaStream_t st);
+                         int mode, const u8* need, cudaStream_t st, int spare_ctas);
 // listing.cu: rowlen[q] = the listed rows' lengths (from pre[]); the other rows are zeroed when write_zero
 void launch_listing_rowlen(const u64* pre, i64 npat, u64* rowlen, int write_zero, cudaStream_t st);
 

@@ -189,7 +189,7 @@ class ShardedStringIndex:
                 dev = self.device
                 res = self.local.locate_batch_device_ex(
                     d_pat.data_ptr(), d_off.data_ptr(), npat, stream,
-                    lambda ptr, n: rows_ready(torch.as_tensor(_DevArray(ptr, 2 * n, "<i4"), device=dev)))
+                    lambda ptr, n, st: rows_ready(torch.as_tensor(_DevArray(ptr, 2 * n, "<i4"), device=dev), st))
             else:
                 res = self.local.locate_batch_device(d_pat.data_ptr(), d_off.data_ptr(), npat, stream)
             row_off = torch.as_tensor(_DevArray(res.row_off, npat + 1), device=self.device)
@@ -231,8 +231,9 @@ class ShardedStringIndex:
         early = {}
         hook = None
         if self.world > 1 and self.narrow and self.device.type == "cuda" and npat:
-            def hook(stats_t):
-                main = torch.cuda.current_stream(self.device)
+            def hook(stats_t, ready_stream=None):
+                # the stream the counts are ready on: the launching stream, or the library's side stream
+                main = torch.cuda.ExternalStream(ready_stream, device=self.device) if ready_stream else torch.cuda.current_stream(self.device)
                 if self._side is None:
                     self._side = torch.cuda.Stream(device=self.device)
                 ready = torch.cuda.Event()

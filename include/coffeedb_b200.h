@@ -194,7 +194,8 @@ cdb_status cdb_locate_batch_device(const cdb_index* idx, const void* d_pat, cons
                                    void* stream, cdb_device_result* out);
 /* Same, with a hook for sharded callers: `rows_ready(user, stats32, npat, stream)` runs on the calling host
  * thread as soon as the kernels that produce stats32 — per-pattern row length and occurrences, device [2*npat] — have been
- * enqueued on `stream`, BEFORE the kernel that fills the pairs is.  The callback records an event on `stream` and starts
+ * enqueued.  The callback records an event on the stream it is HANDED — the caller's `stream`, or, when the rows are being
+ * streamed from the document listing at that moment, a side stream of the library that only waits for stats32 — and starts
  * its exchange of stats32 (an NCCL all_gather) on another stream, where it runs under the rest of the locate. */
 typedef void (*cdb_rows_ready_fn)(void* user, const int32_t* stats32, int64_t npat, void* stream);
 cdb_status cdb_locate_batch_device_ex(const cdb_index* idx, const void* d_pat, const int64_t* d_pat_off, int64_t npat,
