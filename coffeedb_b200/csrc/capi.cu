@@ -41,6 +41,7 @@ void Index::free_device() {
     listing[1].reset();
     listing_state[0] = listing_state[1] = 0;
     listing_miss[0] = listing_miss[1] = 0;
+    listing_skip[0] = listing_skip[1] = 0;
     d_ptab = nullptr;
     d_rank_tab = nullptr;
     d_ids_by_rank = nullptr;

@@ -95,6 +95,7 @@ struct Index {
     mutable std::shared_ptr<Listing> listing[2];
     mutable int listing_state[2] = {0, 0};
     mutable int listing_miss[2] = {0, 0};  // calls of an order that found the other order's listing in its way (see get_listing)
+    mutable int listing_skip[2] = {0, 0};  // calls of an order to let pass before its build is tried again (memory was short)
     // cdb_query's coalescing queue (capi.cu), created on first use
     mutable std::mutex batcher_mu;
     mutable std::shared_ptr<void> batcher;

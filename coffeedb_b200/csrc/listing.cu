@@ -453,7 +453,9 @@ struct EventPair {
 };
 
 // *deferred: the listing was not built because the other order's would have to go and this order has not been asked for
-// often enough yet (see below) — the caller takes the suffix-array path and asks again next time
+// often enough yet (see below), or because device memory is short right now (e.g. calls in flight still hold the listing that
+// was dropped) — the caller takes the suffix-array path and the build is tried again later.  Any other empty result is final
+// for this index (ids too wide, two documents with one id, CDB_LISTING_MAX_HW).
 template <typename SAT>
 static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, cudaStream_t st, bool* deferred) {
     // order 1 is only asked for when the ids do not ascend with the doc index: rank_tab / ids_by_rank exist then
@@ -502,15 +504,23 @@ static std::shared_ptr<Listing> build_listing_typed(const Index& ix, int order, 
             ix.listing_state[other] = 0;
             avail = device_memory_available(ix.device, &total_b);
         }
-        if (avail < need + keep_free || need > budget) return {};
+        if (need > budget) return {};
+        if (avail < need + keep_free) {
+            *deferred = true;
+            ix.listing_skip[order] = 64;  // not before 64 more calls of this order: the check itself costs a scan of the ids
+            return {};
+        }
     }
     auto L = std::make_shared<Listing>();
     L->hw = hw;
     L->base = (i64)h_mm[0];
     L->bytes = need;
-    if (!big_malloc((void**)&L->lo, (size_t)ix.n * 4, ix.device)) return {};
-    if (hw && !big_malloc(&L->hi, (size_t)ix.n * hw, ix.device)) return {};
-    if (!big_malloc((void**)&L->d_flag, 4, ix.device)) return {};
+    if (!big_malloc((void**)&L->lo, (size_t)ix.n * 4, ix.device) || (hw && !big_malloc(&L->hi, (size_t)ix.n * hw, ix.device)) ||
+        !big_malloc((void**)&L->d_flag, 4, ix.device)) {
+        *deferred = true;
+        ix.listing_skip[order] = 64;
+        return {};
+    }
     CDB_CUDA(cudaMemsetAsync(L->d_flag, 0, 4, st));
     const char* env_buckets = getenv("CDB_GATHER_BUCKETS");
     const bool use_buckets = !env_buckets || atoi(env_buckets) != 0;
@@ -577,6 +587,10 @@ std::shared_ptr<Listing> get_listing(const Index& ix, int order, cudaStream_t st
         return ix.listing[order];
     }
     if (ix.listing_state[order] < 0) return {};
+    if (ix.listing_skip[order] > 0) {  // memory was short a moment ago
+        --ix.listing_skip[order];
+        return {};
+    }
     const char* e = getenv("CDB_LISTING");
     std::shared_ptr<Listing> L;
     bool deferred = false;
