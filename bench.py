@@ -972,6 +972,10 @@ def run_ours(args):
                        "doc_bytes": w["doclen"], "corpus_bytes": w["nd"] * w["doclen"], "patterns_per_step": npat,
                        "pattern_bytes": w["m"], "n_suffixes_per_gpu": n_shard, "sa_width": width,
                        "l2": "inputs (suffix array + text) far larger than L2, no flush needed",
+                       "answer_path": ("document listing: every keyword is as long as the prefix directory is deep, its row is streamed "
+                                       "from the per-bucket id list (sa_path = the same batches through the suffix-array path)"
+                                       if listed_rows == npat else
+                                       ("suffix array (search, gather, translate)" if not listed_rows else "mixed: listing + suffix array")),
                        "parallelism": "replica" if world == 1 else f"doc-range shards x{world}, NCCL pattern bcast + count merge"},
             "e2e": e2e_main,
             "e2e_full_rows": e2e_full,
