@@ -91,3 +91,54 @@ def test_directory_tag_round_trip():
     assert (123456 >> 63) == 0 and ((123456 >> K_PT_COUNT_SHIFT) & K_PT_COUNT_MASK) == 0
     # the count field holds every row length a listed bucket can have (<= 1024 suffixes) and stays clear of bits 62 / 63
     assert K_PT_COUNT_MASK >= 1024 and (K_PT_COUNT_MASK << K_PT_COUNT_SHIFT) < (1 << 62)
+
+
+def test_two_phase_build_visits_every_listed_entry_exactly_once():
+    """listing_build_kernel (two-phase) leaves, per directory bucket, the split points of its sorted keys at the doc-range
+    boundaries in seg[c / 8][r][c % 8]; listing_translate_kernel walks items (range r, 32 buckets), spreads its lanes over the
+    concatenated segments through an exclusive scan and `pos0 - excl` bases (unsigned wrap-around included) and must touch
+    every entry of every listed bucket exactly once, with a key inside the item's doc range."""
+    rng = np.random.default_rng(11)
+    M64 = (1 << 64) - 1
+    tile_warps = 8
+    for nentries, nd, rshift in ((64, 1000, 8), (96, 5000, 10), (32, 300, 40)):
+        nranges = max(1, -(-nd // (1 << rshift)))
+        sizes = rng.integers(0, 60, size=nentries)
+        sizes[rng.integers(0, nentries, size=nentries // 3)] = 0          # empty buckets
+        ptab = np.concatenate([[0], np.cumsum(sizes)])
+        keys = np.zeros(int(ptab[-1]), np.int64)
+        seg = np.zeros(-(-nentries // tile_warps) * tile_warps * (nranges + 1), np.int64)
+        for c in range(nentries):
+            row = np.sort(rng.integers(0, nd, size=sizes[c]))
+            keys[ptab[c]:ptab[c + 1]] = row
+            for r in range(nranges + 1):                                    # first rank whose key is >= r << rshift
+                seg[(c // tile_warps) * (nranges + 1) * tile_warps + r * tile_warps + c % tile_warps] = np.searchsorted(row, r << rshift)
+        visited = np.zeros(len(keys), np.int64)
+        ntile = -(-nentries // 32)
+        for item in range(ntile * nranges):
+            r, blk = divmod(item, ntile)
+            lens, pos0 = [], []
+            for lane in range(32):
+                c = blk * 32 + lane
+                ln = p0 = 0
+                if c < nentries:
+                    base = ((c // tile_warps) * (nranges + 1) + r) * tile_warps + c % tile_warps
+                    s, e = seg[base], seg[base + tile_warps]
+                    ln = int(e - s)
+                    if ln:
+                        p0 = int(ptab[c] + s)
+                lens.append(ln)
+                pos0.append(p0)
+            excl = np.concatenate([[0], np.cumsum(lens)])[:32]
+            s_pos = [(pos0[l] - int(excl[l])) & M64 for l in range(32)]     # u64 arithmetic on the device
+            tot = sum(lens)
+            for idx in range(tot):
+                j = 0
+                for st in (16, 8, 4, 2, 1):                                 # largest j with excl[j] <= idx
+                    if excl[j + st] <= idx:
+                        j += st
+                p = (s_pos[j] + idx) & M64
+                assert lens[j] > 0 and pos0[j] <= p < pos0[j] + lens[j]
+                assert (r << rshift) <= keys[p] < ((r + 1) << rshift)
+                visited[p] += 1
+        assert (visited == 1).all()
